@@ -1,0 +1,186 @@
+/* libsvdd_b200 -- C ABI of the B200-native SVDD decoding engine.
+ *
+ * The reference (masa-ue/SVDD) is pure Python/PyTorch and has no FFI; the seam
+ * this library slots under is the set of Python methods of
+ * `diffusion_gosai.Diffusion` that one reverse SVDD step is made of.  Every
+ * entry point below names the reference code (file:line under /root/reference)
+ * it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types in any signature;
+ *  - every function returns SVDD_OK (0) or a negative svdd_status;
+ *    svdd_last_error() returns a thread-local, human-readable message;
+ *  - all tensor arguments are DEVICE pointers owned by the caller (e.g. torch
+ *    allocations); the library never frees or retains them past the call.  The
+ *    only memory it owns are packed weights inside handles it created;
+ *  - every launch goes onto the `stream` argument (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream).  No hidden synchronisation, no host
+ *    allocation on the hot path: scratch memory comes from the caller
+ *    (`*_workspace_bytes` + `ws`), so calls are re-entrant across streams given
+ *    distinct workspaces and can be captured into CUDA graphs;
+ *  - there is no CPU fallback: on a device that is not sm_100 every compute
+ *    entry point fails with SVDD_ERR_UNSUPPORTED_DEVICE.
+ *
+ * Token tensors: `tok_dtype` selects SVDD_TOK_I64 (the reference's int64) or
+ * SVDD_TOK_U8 (the engine's compact internal state).  Token values: 0..3 =
+ * A,C,G,T ; 4 = MASK (diffusion_gosai.py:85,94-95).
+ */
+#ifndef SVDD_B200_H_
+#define SVDD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVDD_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum svdd_status {
+  SVDD_OK = 0,
+  SVDD_ERR_INVALID_ARGUMENT = -1,
+  SVDD_ERR_CUDA = -2,
+  SVDD_ERR_UNSUPPORTED_DEVICE = -3,
+  SVDD_ERR_WORKSPACE_TOO_SMALL = -4,
+  SVDD_ERR_MISSING_TENSOR = -5,
+  SVDD_ERR_INTERNAL = -6
+} svdd_status;
+
+typedef enum svdd_tok_dtype { SVDD_TOK_I64 = 0, SVDD_TOK_U8 = 1 } svdd_tok_dtype;
+
+/* A named fp32 device tensor: one entry of a (reference-layout) state_dict.
+ * Handles are built from arrays of these, looked up by the reference's own key
+ * names (e.g. "convs.3.weight", "conv_tower.blocks.2.0.conv.bias"). */
+typedef struct svdd_tensor {
+  const char* name;
+  const float* data; /* device pointer, contiguous, fp32 */
+  int32_t ndim;
+  int64_t shape[4];
+} svdd_tensor;
+
+/* ---- library ------------------------------------------------------------ */
+int svdd_version(void);
+const char* svdd_last_error(void);
+/* SVDD_OK iff `device` is a compute-capability 10.x GPU. */
+int svdd_device_check(int device);
+/* Number of kernels this library has launched in this process (monotonic);
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+int64_t svdd_launch_count(void);
+
+/* ---- stage 2: SUBS + move-chance mixing + Gumbel-max draw + carry-over ----
+ * Replaces, fused into one kernel:
+ *   Diffusion._subs_parameterization          diffusion_gosai.py:286-304
+ *   q_xs = exp(log_p)*(mc_t-mc_s); q[..,4]=mc_s   diffusion_gosai.py:1194-1196 (MC), 1393-1395 (PM), 1166-1169 (plain)
+ *   _sample_categorical x M                   diffusion_gosai.py:30-34, 1203 / 1402 / 1170
+ *   copy_flag*x + (1-copy_flag)*draw          diffusion_gosai.py:1199-1203
+ *
+ * logits [B,L,5] fp32 raw backbone output (is_log_p = 0) or post-SUBS
+ *        log-probs as returned by Diffusion.forward (is_log_p = 1);
+ * x      [B,L] current tokens; cand [M,B,L] output candidates (same dtype);
+ * U      [M,B,L,5] fp32 uniforms in [0,1) in the reference's draw order (one
+ *        rand_like per candidate, m-major), or NULL to use the in-kernel
+ *        Philox4x32-10 stream keyed by (seed, step, global row = row_offset+b);
+ * mc_t, mc_s  fp32 move chances 1-exp(-sigma(t)), 1-exp(-sigma(t-dt)) computed
+ *        on the host with the reference expression (diffusion_gosai.py:1176-1187);
+ * q_out  optional [B,L,5] fp32: the q_xs tensor the reference returns (or NULL).
+ */
+int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
+                     int tok_dtype, const float* U, uint64_t seed, int step,
+                     int64_t row_offset, float mc_t, float mc_s, void* cand,
+                     float* q_out, int B, int L, int M, void* stream);
+
+/* ---- stage 4: per-sequence selection + gather ----------------------------
+ * Replaces diffusion_gosai.py:1219-1227 / 1451-1459:
+ *   scores = stack(scores, dim=1); softmax(dim=1); argmax(dim=1);
+ *   final = stack([samples[idx[j]][j,:] for j in range(B)])   (B host syncs)
+ * scores [M,B] fp32, candidate-major (the order one scoring call over the
+ *        [M,B,L] candidate tensor produces);
+ * alpha == 0: idx = argmax(softmax(scores)) with first-index ties (reference);
+ * alpha  > 0: idx = gumbel_argmax(softmax(scores/alpha), U_sel) -- build
+ *        decision, the reference's multinomial lines are commented out;
+ *        U_sel [B,M] fp32 or NULL for the Philox stream;
+ * x_out  [B,L] selected rows; idx_out optional int32 [B].
+ */
+int svdd_select_gather(const float* scores, const void* cand, int tok_dtype,
+                       float alpha, const float* U_sel, uint64_t seed, int step,
+                       int64_t row_offset, void* x_out, int32_t* idx_out, int B,
+                       int L, int M, void* stream);
+
+/* ---- argmax of post-SUBS log-probs ----------------------------------------
+ * Replaces the noise-removal step diffusion_gosai.py:1049-1060
+ *   x = forward(x, sigma)[:, :, :-1].argmax(-1)
+ * and the Tweedie x0 estimate diffusion_gosai.py:1415-1419
+ *   argmax(forward(cand, sigma_s), dim=2) combined with carried tokens.
+ * logits [N,L,5] raw backbone output for tokens x [N,L]; out [N,L] in 0..3. */
+int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype, void* out,
+                   int64_t n_rows, int L, void* stream);
+
+/* ---- stage 1: MDLM denoiser (models/dnaconv.py:135-210 CNNModel.forward) ---
+ * Tensors (names relative to the `backbone.` prefix of the Lightning
+ * checkpoint, shapes as in the reference):
+ *   linear.{weight[H,5,9],bias[H]}  convs.i.{weight[H,H,9],bias[H]}
+ *   norms.i.{weight[H],bias[H]}     final_conv.0.{weight[H,H,1],bias[H]}
+ *   final_conv.2.{weight[5,H,1],bias[5]}
+ * H must be 128, n_layers = 5*num_cnn_stacks with dilation groups
+ * [1,1,4,16,64] (models/dnaconv.py:155-160).  The per-layer time bias
+ * time_layers[i](relu(time_embedder(sigma))) is a [n_layers,H] fp32 row block
+ * computed by the host (constant when time_conditioning is False,
+ * diffusion_gosai.py:334-335) and passed to each forward.
+ * Arithmetic: bf16 operands, fp32 accumulation (tcgen05), fp32 LayerNorm. */
+typedef struct svdd_denoiser svdd_denoiser;
+int svdd_denoiser_create(const svdd_tensor* tensors, int n_tensors,
+                         int num_cnn_stacks, void* stream, svdd_denoiser** out);
+void svdd_denoiser_destroy(svdd_denoiser* h);
+size_t svdd_denoiser_workspace_bytes(const svdd_denoiser* h, int64_t n_rows, int L);
+/* tokens [N,L] -> logits [N,L,5] fp32 (raw, pre-SUBS). */
+int svdd_denoiser_forward(svdd_denoiser* h, const void* tokens, int tok_dtype,
+                          const float* time_bias, float* logits, int64_t n_rows,
+                          int L, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- stage 3a: RNA value net / reward oracle (ConvGRU) --------------------
+ * Replaces head(embedding(transform_samples(tokens).float())).squeeze()
+ * (diffusion_gosai.py:1208-1209, 1462-1470) for
+ * ConvGRUTrunk.forward Enformer.py:1411-1426 + ConvHead.forward :2166-2173,
+ * and reward_model(onehot.float().transpose(1,2))[:,0] (diffusion_gosai.py:1430)
+ * for the gReLU ConvGRU oracle (no BN / no residual variant).
+ * Tensors: the trunk's state_dict under its own key names plus the head's
+ * under the prefix "head." (head.channel_transform.conv.layer.{weight,bias}). */
+typedef struct svdd_convgru svdd_convgru;
+int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, void* stream,
+                        svdd_convgru** out);
+void svdd_convgru_destroy(svdd_convgru* h);
+size_t svdd_convgru_workspace_bytes(const svdd_convgru* h, int64_t n_rows, int L);
+/* tokens [N,L] (4 -> all-zero one-hot row) -> scores [N] fp32. */
+int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_dtype,
+                       float* scores, int64_t n_rows, int L, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ---- stage 3b: DNA value net / reward oracle (Enformer-style) -------------
+ * Same call shape as 3a for EnformerTrunk.forward Enformer.py:1326-1334
+ * (conv tower :1807-1884, transformer tower :1887-2007, pointwise :1315-1323)
+ * + ConvHead.  `n_heads` as passed to EnformerTrunk (decode.py:78). */
+typedef struct svdd_enformer svdd_enformer;
+int svdd_enformer_create(const svdd_tensor* tensors, int n_tensors, int n_heads,
+                         void* stream, svdd_enformer** out);
+void svdd_enformer_destroy(svdd_enformer* h);
+size_t svdd_enformer_workspace_bytes(const svdd_enformer* h, int64_t n_rows, int L);
+int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok_dtype,
+                        float* scores, int64_t n_rows, int L, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---- self test of the tcgen05 implicit-GEMM building block ----------------
+ * C[r,n] = sum_{tap,k} A[seq(r), l(r)+(tap-taps/2)*dil, k] * W[tap,n,k]
+ * (zero outside [0,L)) + bias[n], bf16 operands, fp32 accumulate, fp32 out.
+ * A [S,L,K] bf16, W [taps,N,K] bf16, bias [N] fp32, C [S*L,N] fp32.  Used by
+ * tests to check the tensor-core path against a plain CUDA-core kernel. */
+int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16,
+                            const float* bias, float* C, int S, int L, int K,
+                            int N, int taps, int dil, int use_tensor_cores,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDD_B200_H_ */

@@ -1,0 +1,307 @@
+"""ctypes binding of libsvdd_b200.so (the C ABI in include/svdd_b200.h).
+
+PyTorch is used here only as plumbing: device allocations, the current CUDA
+stream and data pointers.  Every compute call is a hand-written sm_100a kernel
+behind the C ABI.  There is NO fallback: if the shared library has not been
+built (``make`` / ``__graft_entry__.build()``) or a tensor is not on a CUDA
+device, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsvdd_b200.so')
+
+SVDD_TOK_I64, SVDD_TOK_U8 = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SvddError(RuntimeError):
+  pass
+
+
+class _Tensor(ctypes.Structure):
+  _fields_ = [('name', ctypes.c_char_p), ('data', ctypes.c_void_p),
+              ('ndim', ctypes.c_int32), ('shape', ctypes.c_int64 * 4)]
+
+
+def _declare(lib):
+  c = ctypes
+  vp, i32, i64, u64, f32 = c.c_void_p, c.c_int, c.c_int64, c.c_uint64, c.c_float
+  lib.svdd_version.restype = i32
+  lib.svdd_last_error.restype = c.c_char_p
+  lib.svdd_device_check.argtypes = [i32]
+  lib.svdd_launch_count.restype = i64
+  lib.svdd_subs_sample.argtypes = [vp, i32, vp, i32, vp, u64, i32, i64, f32, f32,
+                                   vp, vp, i32, i32, i32, vp]
+  lib.svdd_select_gather.argtypes = [vp, vp, i32, f32, vp, u64, i32, i64, vp, vp,
+                                     i32, i32, i32, vp]
+  lib.svdd_x0_argmax.argtypes = [vp, vp, i32, vp, i64, i32, vp]
+  lib.svdd_selftest_conv_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                          i32, i32, vp]
+  tp = c.POINTER(_Tensor)
+  for net, extra in (('denoiser', [i32]), ('convgru', []), ('enformer', [i32])):
+    create = getattr(lib, f'svdd_{net}_create', None)
+    if create is None:
+      continue
+    create.argtypes = [tp, i32] + extra + [vp, c.POINTER(vp)]
+    getattr(lib, f'svdd_{net}_destroy').argtypes = [vp]
+    getattr(lib, f'svdd_{net}_destroy').restype = None
+    ws = getattr(lib, f'svdd_{net}_workspace_bytes')
+    ws.argtypes = [vp, i64, i32]
+    ws.restype = c.c_size_t
+  if hasattr(lib, 'svdd_denoiser_forward'):
+    lib.svdd_denoiser_forward.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp,
+                                          c.c_size_t, vp]
+  for net in ('convgru', 'enformer'):
+    fn = getattr(lib, f'svdd_{net}_score', None)
+    if fn is not None:
+      fn.argtypes = [vp, vp, i32, vp, i64, i32, vp, c.c_size_t, vp]
+
+
+def lib():
+  """Loads the shared library or raises (no CPU fallback)."""
+  global _lib
+  if _lib is None:
+    with _lock:
+      if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+          raise SvddError(
+              f'{LIB_PATH} is missing: build it with `make` (or '
+              '`python -c "import __graft_entry__ as g; g.build()"`). '
+              'svdd_b200 has no CPU / PyTorch fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        _lib = handle
+  return _lib
+
+
+def check(rc):
+  if rc != 0:
+    msg = lib().svdd_last_error()
+    raise SvddError(f'libsvdd_b200 error {rc}: {msg.decode() if msg else ""}')
+
+
+def launch_count():
+  return int(lib().svdd_launch_count())
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise SvddError('svdd_b200 kernels need CUDA tensors (there is no CPU path)')
+
+
+def _ptr(t):
+  return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def tok_dtype(t):
+  if t.dtype == torch.int64:
+    return SVDD_TOK_I64
+  if t.dtype == torch.uint8:
+    return SVDD_TOK_U8
+  raise SvddError(f'token tensors must be int64 or uint8, got {t.dtype}')
+
+
+# -- stage 2 ---------------------------------------------------------------------
+def subs_sample(logits, x, M, mc_t, mc_s, U=None, seed=0, step=0, row_offset=0,
+                is_log_p=False, want_q=False, out=None):
+  """svdd_subs_sample: logits fp32[B,L,5], x [B,L] -> candidates [M,B,L]
+  (+ q_xs fp32[B,L,5] when want_q)."""
+  _require_cuda(logits, x, U)
+  B, L = x.shape
+  assert logits.shape == (B, L, 5) and logits.dtype == torch.float32
+  logits, x = logits.contiguous(), x.contiguous()
+  if U is not None:
+    assert U.shape == (M, B, L, 5) and U.dtype == torch.float32
+    U = U.contiguous()
+  cand = out if out is not None else torch.empty((M, B, L), dtype=x.dtype, device=x.device)
+  q = torch.empty((B, L, 5), dtype=torch.float32, device=x.device) if want_q else None
+  check(lib().svdd_subs_sample(_ptr(logits), int(is_log_p), _ptr(x), tok_dtype(x),
+                               _ptr(U), int(seed), int(step), int(row_offset),
+                               float(mc_t), float(mc_s), _ptr(cand), _ptr(q), B, L, M,
+                               _stream()))
+  return (cand, q) if want_q else cand
+
+
+# -- stage 4 ---------------------------------------------------------------------
+def select_gather(scores, cand, alpha=0.0, U_sel=None, seed=0, step=0,
+                  row_offset=0, want_idx=False, out=None):
+  """svdd_select_gather: scores fp32[M,B], cand [M,B,L] -> x_next [B,L]."""
+  _require_cuda(scores, cand, U_sel)
+  M, B, L = cand.shape
+  assert scores.shape == (M, B) and scores.dtype == torch.float32
+  scores, cand = scores.contiguous(), cand.contiguous()
+  if U_sel is not None:
+    assert U_sel.shape == (B, M) and U_sel.dtype == torch.float32
+    U_sel = U_sel.contiguous()
+  x_out = out if out is not None else torch.empty((B, L), dtype=cand.dtype, device=cand.device)
+  idx = torch.empty((B,), dtype=torch.int32, device=cand.device) if want_idx else None
+  check(lib().svdd_select_gather(_ptr(scores), _ptr(cand), tok_dtype(cand), float(alpha),
+                                 _ptr(U_sel), int(seed), int(step), int(row_offset),
+                                 _ptr(x_out), _ptr(idx), B, L, M, _stream()))
+  return (x_out, idx) if want_idx else x_out
+
+
+def x0_argmax(logits, x, out=None):
+  """svdd_x0_argmax: argmax over the 4 real tokens of SUBS(logits, x)."""
+  _require_cuda(logits, x)
+  L = x.shape[-1]
+  n = x.numel() // L
+  logits, x = logits.contiguous(), x.contiguous()
+  out = out if out is not None else torch.empty_like(x)
+  check(lib().svdd_x0_argmax(_ptr(logits), _ptr(x), tok_dtype(x), _ptr(out), n, L, _stream()))
+  return out
+
+
+def selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=True):
+  """A bf16[S,L,K], W bf16[taps,N,K], bias fp32[N] -> fp32[S*L,N]."""
+  _require_cuda(A, W, bias)
+  S, L, K = A.shape
+  N = W.shape[1]
+  assert W.shape == (taps, N, K) and A.dtype == W.dtype == torch.bfloat16
+  C = torch.empty((S * L, N), dtype=torch.float32, device=A.device)
+  check(lib().svdd_selftest_conv_gemm(_ptr(A.contiguous()), _ptr(W.contiguous()), _ptr(bias),
+                                      _ptr(C), S, L, K, N, taps, dil, int(tensor_cores),
+                                      _stream()))
+  return C
+
+
+# -- network handles ---------------------------------------------------------------
+def _tensor_table(named):
+  """[(name, fp32 CUDA tensor)] -> (ctypes array, keepalive list)."""
+  arr = (_Tensor * len(named))()
+  keep = []
+  for i, (name, t) in enumerate(named):
+    t = t.detach().to(torch.float32).contiguous()
+    _require_cuda(t)
+    keep.append(t)
+    arr[i].name = name.encode()
+    arr[i].data = t.data_ptr()
+    arr[i].ndim = t.dim()
+    for d in range(4):
+      arr[i].shape[d] = t.shape[d] if d < t.dim() else 1
+  return arr, keep
+
+
+class _Handle:
+  """Owns an opaque svdd_* handle plus a grow-only workspace."""
+  _net = None
+
+  def __init__(self):
+    self._h = ctypes.c_void_p()
+    self._ws = None
+
+  def _create(self, named, *extra):
+    arr, keep = _tensor_table(named)
+    fn = getattr(lib(), f'svdd_{self._net}_create')
+    check(fn(arr, len(named), *extra, _stream(), ctypes.byref(self._h)))
+    torch.cuda.current_stream().synchronize()   # packing reads `keep`
+    del keep
+
+  def _workspace(self, n_rows, L, device):
+    need = int(getattr(lib(), f'svdd_{self._net}_workspace_bytes')(self._h, n_rows, L))
+    if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+      self._ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
+    return self._ws, need
+
+  def __del__(self):
+    try:
+      if self._h:
+        getattr(lib(), f'svdd_{self._net}_destroy')(self._h)
+        self._h = ctypes.c_void_p()
+    except Exception:
+      pass
+
+
+class DenoiserHandle(_Handle):
+  """Packed CNN denoiser (svdd_denoiser_*).  Built from a
+  ``svdd_b200.denoiser.CNNModel`` (or any module with the reference's
+  ``CNNModel`` state_dict layout plus ``time_bias``)."""
+  _net = 'denoiser'
+
+  def __init__(self, module):
+    super().__init__()
+    sd = module.state_dict()
+    named = [(k, v) for k, v in sd.items()
+             if not k.startswith('time_') and v.dtype.is_floating_point]
+    dev = next(iter(sd.values())).device
+    if dev.type != 'cuda':
+      raise SvddError('move the model to a CUDA device before running it')
+    stacks = module.num_layers // 5
+    self._create(named, stacks)
+    self._module = module
+    self._tbias_cache = {}
+
+  def time_bias(self, sigma):
+    key = float(sigma)
+    tb = self._tbias_cache.get(key)
+    if tb is None:
+      tb = self._module.time_bias(key).float().contiguous()
+      if len(self._tbias_cache) > 512:
+        self._tbias_cache.clear()
+      self._tbias_cache[key] = tb
+    return tb
+
+  def forward(self, tokens, sigma=0.0, out=None):
+    """tokens int64/uint8 [N,L] (CUDA) -> raw logits fp32 [N,L,5]."""
+    _require_cuda(tokens)
+    tokens = tokens.contiguous()
+    N, L = tokens.shape
+    tb = self.time_bias(sigma)
+    logits = out if out is not None else torch.empty((N, L, 5), dtype=torch.float32,
+                                                     device=tokens.device)
+    ws, need = self._workspace(N, L, tokens.device)
+    check(lib().svdd_denoiser_forward(self._h, _ptr(tokens), tok_dtype(tokens), _ptr(tb),
+                                      _ptr(logits), N, L, _ptr(ws), need, _stream()))
+    return logits
+
+
+class _ScoreHandle(_Handle):
+  def score(self, tokens, out=None):
+    """tokens int64/uint8 [N,L] (CUDA; 4 = mask) -> fp32 [N]."""
+    _require_cuda(tokens)
+    tokens = tokens.contiguous()
+    L = tokens.shape[-1]
+    N = tokens.numel() // L
+    scores = out if out is not None else torch.empty((N,), dtype=torch.float32,
+                                                     device=tokens.device)
+    ws, need = self._workspace(N, L, tokens.device)
+    fn = getattr(lib(), f'svdd_{self._net}_score')
+    check(fn(self._h, _ptr(tokens), tok_dtype(tokens), _ptr(scores), N, L, _ptr(ws), need,
+             _stream()))
+    return scores
+
+
+def _named_with_head(sd_embedding, sd_head):
+  named = [(k, v) for k, v in sd_embedding.items() if v.dtype.is_floating_point]
+  named += [('head.' + k, v) for k, v in sd_head.items() if v.dtype.is_floating_point]
+  if not named or named[0][1].device.type != 'cuda':
+    raise SvddError('move the value network to a CUDA device before scoring')
+  return named
+
+
+class ConvGRUHandle(_ScoreHandle):
+  _net = 'convgru'
+
+  def __init__(self, sd_embedding, sd_head):
+    super().__init__()
+    self._create(_named_with_head(sd_embedding, sd_head))
+
+
+class EnformerHandle(_ScoreHandle):
+  _net = 'enformer'
+
+  def __init__(self, sd_embedding, sd_head, n_heads=8):
+    super().__init__()
+    self._create(_named_with_head(sd_embedding, sd_head), int(n_heads))

@@ -1,0 +1,78 @@
+// Shared host/device helpers for libsvdd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/svdd_b200.h"
+
+namespace svdd {
+
+// ---- error plumbing (thread-local last error, negative return codes) -------
+void set_last_error(const char* fmt, ...);
+
+#define SVDD_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      ::svdd::set_last_error(__VA_ARGS__);                          \
+      return SVDD_ERR_INVALID_ARGUMENT;                             \
+    }                                                               \
+  } while (0)
+
+#define SVDD_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      ::svdd::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,   \
+                             cudaGetErrorString(_e));                        \
+      return SVDD_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+#define SVDD_LAUNCH_CHECK()                                                  \
+  do {                                                                       \
+    cudaError_t _e = cudaGetLastError();                                     \
+    if (_e != cudaSuccess) {                                                 \
+      ::svdd::set_last_error("%s:%d: kernel launch -> %s", __FILE__,         \
+                             __LINE__, cudaGetErrorString(_e));              \
+      return SVDD_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+#define SVDD_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != SVDD_OK) return _rc; \
+  } while (0)
+
+// counts kernel launches issued by this library (bench.py's gpu_launches)
+void count_launch(int n = 1);
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr int kMaskIndex = 4;            // diffusion_gosai.py:85,94-95
+constexpr int kVocab = 5;                // A,C,G,T,MASK
+constexpr float kNegInfinity = -1000000.0f;  // diffusion_gosai.py:156
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// Token tensors cross the ABI as int64 (the reference's dtype) or uint8 (the
+// engine's internal state).  Device-side accessors:
+template <typename Tok>
+__device__ __forceinline__ int load_tok(const Tok* p, size_t i) { return (int)p[i]; }
+template <typename Tok>
+__device__ __forceinline__ void store_tok(Tok* p, size_t i, int v) { p[i] = (Tok)v; }
+
+}  // namespace svdd

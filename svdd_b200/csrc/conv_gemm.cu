@@ -1,0 +1,202 @@
+// Host launcher for the tcgen05 implicit-GEMM (conv_gemm.cuh): builds the TMA
+// tensor maps, picks the N tile and launches one persistent CTA per SM.
+#include <mutex>
+#include <stdlib.h>
+
+#include "conv_gemm.cuh"
+
+namespace svdd {
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    return SVDD_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)",
+                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return SVDD_ERR_CUDA;
+  }
+  return SVDD_OK;
+}
+
+template <int BN, int MODE>
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& g,
+                const EpiParams& ep, cudaStream_t stream) {
+  using C = gemm_detail::Cfg<BN, MODE>;
+  auto kern = gemm_detail::conv_gemm_kernel<BN, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const int64_t tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS) * (g.N / BN);
+  if (tiles == 0) return SVDD_OK;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, gemm_detail::kThreads, C::kSmemBytes, stream>>>(tmA, tmW, g, ep);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
+int pick_bn(const GemmShape& g, int mode) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SVDD_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  const int64_t m_tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS);
+  if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL) return 128;
+  if (mode == EPI_POOL) return (g.N % 128 == 0) ? 128 : 64;
+  if (forced > 0 && g.N % forced == 0) return forced;
+  if (g.N % 256 == 0 && m_tiles * (g.N / 256) >= 2 * (int64_t)num_sms()) return 256;
+  if (g.N % 128 == 0) return 128;
+  return 64;
+}
+
+}  // namespace
+
+void choose_row_tiling(int L, int taps, GemmShape* g) {
+  (void)taps;
+  if (L <= 128) {
+    g->BL = L;
+    g->BS = 128 / L;
+  } else {
+    g->BL = 128;
+    g->BS = 1;
+  }
+}
+
+int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
+                     const EpiParams& ep, cudaStream_t stream) {
+  SVDD_CHECK_ARG(g.K > 0 && g.K % 64 == 0, "conv_gemm: K=%d must be a positive multiple of 64", g.K);
+  SVDD_CHECK_ARG(g.N > 0 && g.N % 64 == 0, "conv_gemm: N=%d must be a positive multiple of 64", g.N);
+  SVDD_CHECK_ARG(g.BL >= 1 && g.BS >= 1 && g.BL * g.BS <= 128, "conv_gemm: bad tile %dx%d", g.BL, g.BS);
+  SVDD_CHECK_ARG(g.BL <= 256 && g.BS <= 256, "conv_gemm: TMA box too large");
+  SVDD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                 "conv_gemm: operands must be 16-byte aligned");
+  if (g.S == 0 || g.L == 0) return SVDD_OK;
+  const int bn = pick_bn(g, mode);
+  SVDD_CHECK_ARG(g.N % bn == 0, "conv_gemm: N=%d not divisible by tile %d", g.N, bn);
+  if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL)
+    SVDD_CHECK_ARG(g.N == 128, "conv_gemm: denoiser epilogues need N == 128 (got %d)", g.N);
+
+  CUtensorMap tmA, tmW;
+  if (mode == EPI_POOL) {
+    SVDD_CHECK_ARG(g.taps == 1, "conv_gemm: pooling epilogue is 1x1 only");
+    const cuuint64_t dims[4] = {(cuuint64_t)g.K, 2, (cuuint64_t)g.L, (cuuint64_t)g.S};
+    const cuuint64_t str[3] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.K * 4, (cuuint64_t)g.L_in * g.K * 2};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+    SVDD_TRY(encode_bf16_map(&tmA, A, 4, dims, str, box));
+  } else {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.L_in, (cuuint64_t)g.S};
+    const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.L_in * g.K * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+    SVDD_TRY(encode_bf16_map(&tmA, A, 3, dims, str, box));
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.N};
+    const cuuint64_t str[1] = {(cuuint64_t)g.K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    SVDD_TRY(encode_bf16_map(&tmW, W, 2, dims, str, box));
+  }
+
+#define CASE(BN_, MODE_) \
+  if (bn == BN_ && mode == MODE_) return launch_impl<BN_, MODE_>(tmA, tmW, g, ep, stream)
+  CASE(64, EPI_GENERIC);
+  CASE(128, EPI_GENERIC);
+  CASE(256, EPI_GENERIC);
+  CASE(128, EPI_DEN_LN);
+  CASE(128, EPI_DEN_FINAL);
+  CASE(64, EPI_POOL);
+  CASE(128, EPI_POOL);
+  CASE(64, EPI_HEADDOT);
+  CASE(128, EPI_HEADDOT);
+  CASE(256, EPI_HEADDOT);
+#undef CASE
+  set_last_error("conv_gemm: no kernel for BN=%d mode=%d", bn, mode);
+  return SVDD_ERR_INTERNAL;
+}
+
+// ---- plain CUDA-core reference of the same contraction (self test only) ----------
+namespace {
+__global__ void naive_conv_gemm_kernel(const __nv_bfloat16* __restrict__ A,
+                                       const __nv_bfloat16* __restrict__ W,
+                                       const float* __restrict__ bias, float* __restrict__ C, int S,
+                                       int L, int K, int N, int taps, int dil) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S * L * N) return;
+  const int n = (int)(idx % N);
+  const int64_t row = idx / N;
+  const int l = (int)(row % L), s = (int)(row / L);
+  float acc = 0.0f;
+  for (int t = 0; t < taps; ++t) {
+    const int li = l + (t - taps / 2) * dil;
+    if (li < 0 || li >= L) continue;
+    const __nv_bfloat16* a = A + ((int64_t)s * L + li) * K;
+    const __nv_bfloat16* w = W + ((int64_t)t * N + n) * K;
+    for (int k = 0; k < K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+  }
+  C[idx] = acc + (bias ? bias[n] : 0.0f);
+}
+}  // namespace
+}  // namespace svdd
+
+using namespace svdd;
+
+extern "C" int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16, const float* bias,
+                                       float* C, int S, int L, int K, int N, int taps, int dil,
+                                       int use_tensor_cores, void* stream) {
+  SVDD_CHECK_ARG(A_bf16 && W_bf16 && C, "selftest: null pointer");
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!use_tensor_cores) {
+    const int64_t total = (int64_t)S * L * N;
+    naive_conv_gemm_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)W_bf16, bias, C, S, L, K, N, taps, dil);
+    count_launch();
+    SVDD_LAUNCH_CHECK();
+    return SVDD_OK;
+  }
+  GemmShape g;
+  g.K = K; g.N = N; g.taps = taps; g.dil = dil;
+  if (taps == 1) {  // plain GEMM: flatten rows
+    g.S = 1; g.L = S * L; g.L_in = S * L; g.BL = 128; g.BS = 1;
+  } else {
+    g.S = S; g.L = L; g.L_in = L;
+    choose_row_tiling(L, taps, &g);
+  }
+  EpiParams ep;
+  ep.bias = bias;
+  ep.out = C; ep.out_dtype = DT_F32; ep.ld_out = N;
+  return launch_conv_gemm(A_bf16, W_bf16, g, EPI_GENERIC, ep, st);
+}

@@ -1,0 +1,477 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for 1-D convolutions and linears.
+//
+//   C[(s,l), n] = epilogue( sum_{tap<T} sum_{k<K} A[s, l + (tap - T/2)*dil, k] * W[tap*N + n, k] )
+//
+// A   : bf16 activations, channels-last [S, L_in, K]  (zero outside [0, L_in))
+// W   : bf16 weights, tap-major [T*N, K]              (K contiguous)
+// acc : fp32 in tensor memory
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer: per (tap, 64-wide K block) one 3-D box of A
+//               (64 ch x BL positions x BS sequences, out-of-range positions are
+//               zero-filled by TMA = the conv's zero padding) and one 2-D box of W,
+//               both 128B-swizzled, into a kStages-deep smem ring;
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma
+//               (M=128, N=BN, K=16) per stage into a double-buffered TMEM
+//               accumulator, tcgen05.commit releases the smem slot / signals the
+//               epilogue;
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time (thread =
+//               output row, so per-row reductions such as LayerNorm are
+//               thread-local), fused bias / BN-affine / activation / residual /
+//               LayerNorm / attention-pool / head-dot, vectorised global stores.
+// Taps whose whole A tile falls in the zero padding are skipped by both the
+// producer and the issuer (dilation-64 taps on 200-long sequences).
+#pragma once
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace svdd {
+
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum DType { DT_NONE = 0, DT_BF16 = 1, DT_F32 = 2 };
+enum EpiMode { EPI_GENERIC = 0, EPI_DEN_LN = 1, EPI_DEN_FINAL = 2, EPI_POOL = 3, EPI_HEADDOT = 4 };
+
+struct EpiParams {
+  // generic chain on v = acc:  v = v*scale + shift ; v += bias ; [act] ; v += res ; [act]
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int act = ACT_NONE;
+  int act_after_res = 0;
+  const void* res = nullptr;
+  int res_dtype = DT_NONE;
+  int64_t ld_res = 0;
+  void* out = nullptr;
+  int out_dtype = DT_NONE;
+  int64_t ld_out = 0;
+  // second output: out2 = act2(v * scale2 + shift2)   (next layer's BN+GELU operand)
+  void* out2 = nullptr;
+  int out2_dtype = DT_NONE;
+  int64_t ld_out2 = 0;
+  const float* scale2 = nullptr;
+  const float* shift2 = nullptr;
+  int act2 = ACT_NONE;
+  // EPI_DEN_LN: out = residual stream (fp32, read+written), out2 = LN'd operand
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  const float* ln_tbias = nullptr;
+  int ln_enable = 0;
+  // EPI_DEN_FINAL: logits[r, j] = b2[j] + sum_c relu(acc+bias)[c] * w2[j, c]
+  const float* w2 = nullptr;
+  const float* b2 = nullptr;
+  // EPI_POOL: values being pooled (bf16 [S*L_in, N])
+  const void* pool_vals = nullptr;
+  // EPI_HEADDOT: partials[r, n_tile] = sum_{n in tile} v[n] * head_w[n]
+  const float* head_w = nullptr;
+  float* partials = nullptr;
+};
+
+struct GemmShape {
+  int S = 0;       // sequences
+  int L = 0;       // output positions per sequence
+  int L_in = 0;    // input positions per sequence (EPI_POOL: 2 inputs per output)
+  int K = 0, N = 0;
+  int taps = 1, dil = 1;
+  int BL = 128, BS = 1;  // tile = BL positions x BS sequences (BL*BS <= 128)
+};
+
+namespace gemm_detail {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN, int MODE>
+struct Cfg {
+  static constexpr int kAcc = (MODE == EPI_POOL) ? 2 : 1;
+  static constexpr int kABytes = kAcc * kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemColsRaw = 2 * kAcc * BN;
+  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64
+                                   : kTmemColsRaw <= 128 ? 128 : kTmemColsRaw <= 256 ? 256 : 512;
+  static constexpr int kExtraBytes = (MODE == EPI_DEN_FINAL) ? (kVocab * 128 + 8) * 4 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kTmemColsRaw <= 512, "accumulators exceed tensor memory");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_GELU) return v / (1.0f + __expf(-1.702f * v));  // x * sigmoid(1.702 x)
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// store / load 32 consecutive channels of one row
+__device__ __forceinline__ void store_row32(void* base, int dtype, int64_t off, const float* v) {
+  if (dtype == DT_BF16) {
+    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      p[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                        pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  } else {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+__device__ __forceinline__ void load_row32(const void* base, int dtype, int64_t off, float* v) {
+  if (dtype == DT_BF16) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = p[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        v[8 * i + 2 * j] = __low2float(h);
+        v[8 * i + 2 * j + 1] = __high2float(h);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 f = p[i];
+      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+  }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const GemmShape g, const EpiParams ep) {
+  using C = Cfg<BN, MODE>;
+  constexpr int kStages = C::kStages;
+  constexpr int kAcc = C::kAcc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint8_t* extra = smem + kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(extra + C::kExtraBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tiles_l = ceil_div(g.L, g.BL);
+  const int tiles_s = ceil_div(g.S, g.BS);
+  const int n_tiles = g.N / BN;
+  const int64_t total_tiles = (int64_t)tiles_l * tiles_s * n_tiles;
+  const int kblocks = g.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        ptx::mbar_init(&full_bar[i], 1);
+        ptx::mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&tfull_bar[i], 1);
+        ptx::mbar_init(&tempty_bar[i], 4);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  if constexpr (MODE == EPI_DEN_FINAL) {
+    float* w2s = reinterpret_cast<float*>(extra);
+    for (int i = threadIdx.x; i < kVocab * 128; i += kThreads) w2s[i] = ep.w2[i];
+    if (threadIdx.x < kVocab) w2s[kVocab * 128 + threadIdx.x] = ep.b2[threadIdx.x];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int64_t t, int& n0, int& s0, int& l0) {
+    const int nt = (int)(t % n_tiles);
+    const int64_t mt = t / n_tiles;
+    n0 = nt * BN;
+    s0 = (int)(mt / tiles_l) * g.BS;
+    l0 = (int)(mt % tiles_l) * g.BL;
+  };
+  auto tap_active = [&](int tap, int l0, int& l_start) {
+    l_start = l0 + (tap - g.taps / 2) * g.dil;
+    return (l_start + g.BL > 0) && (l_start < g.L_in);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(kAcc * g.BL * g.BS * kBK * 2 + C::kBBytes);
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n0, s0, l0;
+        tile_coords(t, n0, s0, l0);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          int l_start;
+          if (MODE != EPI_POOL && !tap_active(tap, l0, l_start)) continue;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stage_base + stage * C::kStageBytes;
+            uint8_t* sb = sa + C::kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            if (MODE == EPI_POOL) {
+              ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBK, 0, l0, s0);
+              ptx::tma_load_4d(sa + kBM * kBK * 2, &tmA, &full_bar[stage], kb * kBK, 1, l0, s0);
+            } else {
+              ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * kBK, l_start, s0);
+            }
+            ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * kBK, tap * g.N + n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+    uint32_t stage = 0, phase = 0;
+    uint32_t acc_stage = 0, acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n0, s0, l0;
+      tile_coords(t, n0, s0, l0);
+      ptx::mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc_stage * (kAcc * BN);
+      uint32_t first = 1;
+      for (int tap = 0; tap < g.taps; ++tap) {
+        int l_start;
+        if (MODE != EPI_POOL && !tap_active(tap, l0, l_start)) continue;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+            const uint32_t sb = sa + C::kABytes;
+            const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+            const uint64_t db = ptx::make_kmajor_sw128_desc(sb);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 B per 16-element K step inside the 128 B swizzle atom
+              ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
+              if (kAcc == 2) {
+                const uint64_t da1 = ptx::make_kmajor_sw128_desc(sa + kBM * kBK * 2);
+                ptx::umma_bf16(tmem_d + BN, da1 + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
+          first = 0;
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (lane == 0) ptx::umma_commit(&tfull_bar[acc_stage]);
+      __syncwarp();
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row of the tile owned by this thread
+    uint32_t acc_stage = 0, acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n0, s0, l0;
+      tile_coords(t, n0, s0, l0);
+      const int s = s0 + r / g.BL, l = l0 + r % g.BL;
+      const bool valid = (r < g.BL * g.BS) && (s < g.S) && (l < g.L);
+      const int64_t row = (int64_t)s * g.L + l;
+      ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * (kAcc * BN);
+
+      if constexpr (MODE == EPI_GENERIC || MODE == EPI_POOL || MODE == EPI_HEADDOT) {
+        float head_acc = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          float v[32];
+          ptx::tmem_ld_32x32(taddr + c0, raw);
+          if constexpr (MODE == EPI_POOL) {
+            uint32_t raw1[32];
+            ptx::tmem_ld_32x32(taddr + BN + c0, raw1);
+            ptx::tmem_ld_wait();
+            if (valid) {
+              const int64_t rin = (int64_t)s * g.L_in + 2 * l;
+              const bool has1 = (2 * l + 1) < g.L_in;
+              float y0[32], y1[32];
+              load_row32(ep.pool_vals, DT_BF16, rin * g.N + n0 + c0, y0);
+              if (has1) load_row32(ep.pool_vals, DT_BF16, (rin + 1) * g.N + n0 + c0, y1);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float a0 = __uint_as_float(raw[i]);
+                if (has1) {
+                  const float a1 = __uint_as_float(raw1[i]);
+                  const float m = fmaxf(a0, a1);
+                  const float e0 = __expf(a0 - m), e1 = __expf(a1 - m);
+                  const float inv = 1.0f / (e0 + e1);
+                  v[i] = y0[i] * (e0 * inv) + y1[i] * (e1 * inv);
+                } else {
+                  v[i] = y0[i];
+                }
+              }
+            }
+          } else {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          }
+          if (valid) {
+            const int n = n0 + c0;
+            if (MODE != EPI_POOL) {
+              if (ep.scale != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = v[i] * __ldg(ep.scale + n + i) + __ldg(ep.shift + n + i);
+              }
+              if (ep.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __ldg(ep.bias + n + i);
+              }
+              if (ep.act != ACT_NONE && !ep.act_after_res) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
+              }
+              if (ep.res != nullptr) {
+                float rr[32];
+                load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, rr);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += rr[i];
+              }
+              if (ep.act != ACT_NONE && ep.act_after_res) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
+              }
+            }
+            if (MODE == EPI_HEADDOT) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) head_acc += v[i] * __ldg(ep.head_w + n + i);
+            }
+            if (ep.out != nullptr) store_row32(ep.out, ep.out_dtype, row * ep.ld_out + n, v);
+            if (ep.out2 != nullptr) {
+              float w[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float x = v[i];
+                if (ep.scale2 != nullptr) x = x * __ldg(ep.scale2 + n + i) + __ldg(ep.shift2 + n + i);
+                w[i] = apply_act(x, ep.act2);
+              }
+              store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n, w);
+            }
+          }
+        }
+        if (MODE == EPI_HEADDOT && valid) ep.partials[row * n_tiles + n0 / BN] = head_acc;
+      } else if constexpr (MODE == EPI_DEN_LN) {
+        // denoiser layer i: feat += relu(conv + bias); h_next = LN_{i+1}(feat + tbias_{i+1})
+        // (models/dnaconv.py:189-200).  BN == N == 128: the whole channel row is in this
+        // thread's TMEM lane.
+        float v[BN];
+        float* feat = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(taddr + c0, raw);
+          ptx::tmem_ld_wait();
+          float rr[32];
+          if (valid) load_row32(feat, DT_F32, row * BN + c0, rr);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[c0 + i] = valid ? rr[i] + fmaxf(__uint_as_float(raw[i]) + __ldg(ep.bias + c0 + i), 0.0f) : 0.0f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) store_row32(feat, DT_F32, row * BN + c0, v + c0);
+          if (ep.ln_enable) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < BN; ++i) {
+              v[i] += __ldg(ep.ln_tbias + i);
+              sum += v[i];
+            }
+            const float mean = sum * (1.0f / BN);
+            float sq = 0.0f;
+#pragma unroll
+            for (int i = 0; i < BN; ++i) {
+              const float dlt = v[i] - mean;
+              sq += dlt * dlt;
+            }
+            const float rstd = rsqrtf(sq * (1.0f / BN) + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < BN; ++i)
+              v[i] = (v[i] - mean) * rstd * __ldg(ep.ln_gamma + i) + __ldg(ep.ln_beta + i);
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) store_row32(ep.out2, DT_BF16, row * BN + c0, v + c0);
+        }
+      } else if constexpr (MODE == EPI_DEN_FINAL) {
+        // final_conv: relu(1x1) then 1x1 to the 5 logits (models/dnaconv.py:163-165,201)
+        const float* w2s = reinterpret_cast<const float*>(extra);
+        float lg[kVocab];
+#pragma unroll
+        for (int j = 0; j < kVocab; ++j) lg[j] = w2s[kVocab * 128 + j];
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(taddr + c0, raw);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float y = fmaxf(__uint_as_float(raw[i]) + __ldg(ep.bias + c0 + i), 0.0f);
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j) lg[j] += y * w2s[j * 128 + c0 + i];
+          }
+        }
+        if (valid) {
+          float* o = reinterpret_cast<float*>(ep.out) + row * kVocab;
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) o[j] = lg[j];
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_stage]);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace gemm_detail
+
+// Host-side launcher (conv_gemm.cu).  A is [S, L_in, K] bf16 (for EPI_POOL the
+// rows 2l, 2l+1 of each sequence feed output row l), W is [taps*N, K] bf16.
+int launch_conv_gemm(const void* A, const void* W, const GemmShape& shape, int mode,
+                     const EpiParams& ep, cudaStream_t stream);
+
+// Picks (BL, BS) for a conv over sequences of length L: whole-sequence tiles when
+// L <= 128 (several sequences per tile), else 128-position tiles.
+void choose_row_tiling(int L, int taps, GemmShape* shape);
+
+}  // namespace svdd

@@ -1,0 +1,371 @@
+// Stage 2 (SUBS + q_xs + Gumbel-max + carry-over), stage 4 (selection + gather)
+// and the post-SUBS argmax.  HBM-bound byte/fp32 work: no tensor cores.
+//
+// Bit-exactness contract: every fp32 operation below is the same IEEE
+// operation, in the same association, as the reference's torch expression
+// (cited per line); transcendental calls are the accurate libdevice logf/expf
+// that ATen's CUDA kernels call.  Explicit __f*_rn intrinsics stop nvcc from
+// contracting mul+add into FMA.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace svdd {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+// Post-SUBS probabilities of one position.
+//   raw logits  : diffusion_gosai.py:289-294  logits[...,4] += -1e6; logits -= logsumexp
+//   logsumexp   : ATen logsumexp = log(sum(exp(x - max))) + max
+//   unmasked row: diffusion_gosai.py:300-303  -1e6 everywhere, 0 at x
+__device__ __forceinline__ void subs_log_p(const float* lg, int tok, bool is_log_p,
+                                           float* logp) {
+  if (is_log_p) {
+#pragma unroll
+    for (int v = 0; v < kVocab; ++v) logp[v] = lg[v];
+    return;
+  }
+  if (tok != kMaskIndex) {
+#pragma unroll
+    for (int v = 0; v < kVocab; ++v) logp[v] = (v == tok) ? 0.0f : kNegInfinity;
+    return;
+  }
+  float l[kVocab];
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) l[v] = lg[v];
+  l[kMaskIndex] = __fadd_rn(l[kMaskIndex], kNegInfinity);
+  float mx = l[0];
+#pragma unroll
+  for (int v = 1; v < kVocab; ++v) mx = fmaxf(mx, l[v]);
+  const float mx_used = (fabsf(mx) == INFINITY) ? 0.0f : mx;
+  float s = 0.0f;
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) s = __fadd_rn(s, expf(__fsub_rn(l[v], mx_used)));
+  const float lse = __fadd_rn(logf(s), mx_used);
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) logp[v] = __fsub_rn(l[v], lse);
+}
+
+// argmax_v q[v] / (1e-10 - log(u[v] + 1e-10)), first index on ties
+// (diffusion_gosai.py:30-34).
+__device__ __forceinline__ int gumbel_argmax5(const float* q, const float* u) {
+  int best = 0;
+  float best_key = 0.0f;
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) {
+    const float g = __fsub_rn(1e-10f, logf(__fadd_rn(u[v], 1e-10f)));
+    const float key = __fdiv_rn(q[v], g);
+    if (v == 0 || key > best_key) { best_key = key; best = v; }
+  }
+  return best;
+}
+
+template <typename Tok, bool kInjected>
+__global__ void __launch_bounds__(kThreads)
+subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
+                   const Tok* __restrict__ x, const float* __restrict__ U,
+                   uint32_t key0, uint32_t key1, uint32_t step, int64_t row_offset,
+                   float mc_t, float mc_s, Tok* __restrict__ cand,
+                   float* __restrict__ q_out, int64_t BL, int L, int M) {
+  __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
+  if (pos0 >= BL) return;
+  const int64_t pos = pos0 + lane;
+  const bool valid = pos < BL;
+  const int64_t n_el = BL * kVocab;
+  float* stage = s_stage[warp];
+
+  // coalesced load of this warp's 32x5 logits, transposed through smem
+  const int64_t e0 = pos0 * kVocab;
+#pragma unroll
+  for (int k = 0; k < kVocab; ++k) {
+    const int64_t e = e0 + k * 32 + lane;
+    stage[k * 32 + lane] = (e < n_el) ? __ldg(logits + e) : 0.0f;
+  }
+  __syncwarp();
+  float lg[kVocab];
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) lg[v] = stage[lane * kVocab + v];
+  __syncwarp();
+
+  const int tok = valid ? load_tok(x, pos) : 0;
+  const bool masked = valid && tok == kMaskIndex;
+
+  // q_xs (diffusion_gosai.py:1194-1196)
+  float logp[kVocab], q[kVocab];
+  subs_log_p(lg, tok, is_log_p != 0, logp);
+  const float d = __fsub_rn(mc_t, mc_s);
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) q[v] = __fmul_rn(expf(logp[v]), d);
+  q[kMaskIndex] = mc_s;
+  if (q_out != nullptr) {
+#pragma unroll
+    for (int v = 0; v < kVocab; ++v) stage[lane * kVocab + v] = q[v];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kVocab; ++k) {
+      const int64_t e = e0 + k * 32 + lane;
+      if (e < n_el) q_out[e] = stage[k * 32 + lane];
+    }
+    __syncwarp();
+  }
+
+  // carry-over: an unmasked token is kept whatever the draw (:1199-1203), so a
+  // warp without masked positions never touches the noise.
+  const unsigned any_masked = __ballot_sync(0xffffffffu, masked);
+  if (any_masked == 0u) {
+    if (valid)
+      for (int m = 0; m < M; ++m) store_tok(cand, (size_t)m * BL + pos, tok);
+    return;
+  }
+
+  if (kInjected) {
+    float pre[kVocab];
+    auto prefetch = [&](int m) {
+      const int64_t b0 = ((int64_t)m * BL + pos0) * kVocab;
+      const int64_t lim = ((int64_t)m + 1) * n_el;
+#pragma unroll
+      for (int k = 0; k < kVocab; ++k) {
+        const int64_t e = b0 + k * 32 + lane;
+        pre[k] = (e < lim) ? __ldg(U + e) : 0.5f;
+      }
+    };
+    prefetch(0);
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+      for (int k = 0; k < kVocab; ++k) stage[k * 32 + lane] = pre[k];
+      __syncwarp();
+      if (m + 1 < M) prefetch(m + 1);
+      float u[kVocab];
+#pragma unroll
+      for (int v = 0; v < kVocab; ++v) u[v] = stage[lane * kVocab + v];
+      __syncwarp();
+      if (valid) {
+        const int draw = masked ? gumbel_argmax5(q, u) : tok;
+        store_tok(cand, (size_t)m * BL + pos, draw);
+      }
+    }
+  } else {
+    const uint32_t row = (uint32_t)(row_offset + pos / L);
+    const uint32_t l = (uint32_t)(pos % L);
+    for (int m = 0; m < M; ++m) {
+      if (!valid) continue;
+      int draw = tok;
+      if (masked) {
+        const Philox4 a = philox4x32_10(l, row, (uint32_t)m, step, key0, key1);
+        const Philox4 e = philox4x32_10(l, row, (uint32_t)m | (1u << 16), step, key0, key1);
+        const float u[kVocab] = {philox_uniform(a.x), philox_uniform(a.y),
+                                 philox_uniform(a.z), philox_uniform(a.w),
+                                 philox_uniform(e.x)};
+        draw = gumbel_argmax5(q, u);
+      }
+      store_tok(cand, (size_t)m * BL + pos, draw);
+    }
+  }
+}
+
+// ---- post-SUBS argmax over the 4 real tokens --------------------------------
+template <typename Tok>
+__global__ void __launch_bounds__(kThreads)
+x0_argmax_kernel(const float* __restrict__ logits, const Tok* __restrict__ x,
+                 Tok* __restrict__ out, int64_t NL) {
+  __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
+  if (pos0 >= NL) return;
+  const int64_t pos = pos0 + lane;
+  float* stage = s_stage[warp];
+  const int64_t n_el = NL * kVocab, e0 = pos0 * kVocab;
+#pragma unroll
+  for (int k = 0; k < kVocab; ++k) {
+    const int64_t e = e0 + k * 32 + lane;
+    stage[k * 32 + lane] = (e < n_el) ? __ldg(logits + e) : 0.0f;
+  }
+  __syncwarp();
+  if (pos >= NL) return;
+  float lg[kVocab], logp[kVocab];
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) lg[v] = stage[lane * kVocab + v];
+  const int tok = load_tok(x, pos);
+  subs_log_p(lg, tok, false, logp);
+  int best = 0;
+#pragma unroll
+  for (int v = 1; v < kMaskIndex; ++v)
+    if (logp[v] > logp[best]) best = v;
+  store_tok(out, pos, best);
+}
+
+// ---- stage 4 -----------------------------------------------------------------
+// One warp per sequence.  The max / sum reductions use the same butterfly
+// (lanes = next_pow2(M) capped at 32, element i on lane i % lanes, xor
+// shuffles from lanes/2 down to 1) as ATen's softmax_warp_forward so that the
+// softmax values -- and hence first-index argmax ties -- are those of
+// torch.softmax(scores, dim=1) on the same device (diffusion_gosai.py:1220,1225).
+constexpr int kMaxIterSel = 8;  // M <= 256
+
+template <typename Tok, bool kInjected>
+__global__ void __launch_bounds__(kThreads)
+select_gather_kernel(const float* __restrict__ scores, const Tok* __restrict__ cand,
+                     float alpha, const float* __restrict__ U_sel, uint32_t key0,
+                     uint32_t key1, uint32_t step, int64_t row_offset,
+                     Tok* __restrict__ x_out, int32_t* __restrict__ idx_out, int B,
+                     int L, int M, int lanes, int iters) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarpsPerBlock + warp;
+  if (b >= B) return;
+  const bool active = lane < lanes;
+  float e[kMaxIterSel];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < kMaxIterSel; ++it) {
+    if (it < iters) {
+      const int m = lane + it * lanes;
+      float s = (active && m < M) ? __ldg(scores + (size_t)m * B + b) : -INFINITY;
+      if (alpha > 0.0f && s != -INFINITY) s = __fdiv_rn(s, alpha);
+      e[it] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  for (int off = lanes >> 1; off > 0; off >>= 1)
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.0f;
+#pragma unroll
+  for (int it = 0; it < kMaxIterSel; ++it) {
+    if (it < iters) {
+      const float v = (e[it] == -INFINITY) ? 0.0f : expf(__fsub_rn(e[it], mx));
+      e[it] = v;
+      sum = __fadd_rn(sum, v);
+    }
+  }
+  for (int off = lanes >> 1; off > 0; off >>= 1)
+    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, off));
+
+  // key per candidate: softmax value (alpha == 0) or Gumbel-max key
+  float best_key = -INFINITY;
+  int best_m = 0x7fffffff;
+#pragma unroll
+  for (int it = 0; it < kMaxIterSel; ++it) {
+    if (it < iters) {
+      const int m = lane + it * lanes;
+      if (active && m < M) {
+        float key = __fdiv_rn(e[it], sum);
+        if (alpha > 0.0f) {
+          float u;
+          if (kInjected) {
+            u = __ldg(U_sel + (size_t)b * M + m);
+          } else {
+            const Philox4 w = philox4x32_10((uint32_t)(m >> 2), (uint32_t)(row_offset + b),
+                                            0u, step | (1u << 24), key0, key1);
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            u = philox_uniform(words[m & 3]);
+          }
+          const float g = __fsub_rn(1e-10f, logf(__fadd_rn(u, 1e-10f)));
+          key = __fdiv_rn(key, g);
+        }
+        if (key > best_key || (key == best_key && m < best_m)) { best_key = key; best_m = m; }
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ok = __shfl_xor_sync(0xffffffffu, best_key, off);
+    const int om = __shfl_xor_sync(0xffffffffu, best_m, off);
+    if (ok > best_key || (ok == best_key && om < best_m)) { best_key = ok; best_m = om; }
+  }
+  if (best_m == 0x7fffffff) best_m = 0;  // all keys NaN / -inf: torch.argmax -> 0
+  if (lane == 0 && idx_out != nullptr) idx_out[b] = best_m;
+  const Tok* src = cand + ((size_t)best_m * B + b) * L;
+  Tok* dst = x_out + (size_t)b * L;
+  for (int l = lane; l < L; l += 32) dst[l] = src[l];
+}
+
+int check_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_last_error("no CUDA device");
+    return SVDD_ERR_CUDA;
+  }
+  return svdd_device_check(dev);
+}
+
+}  // namespace
+}  // namespace svdd
+
+using namespace svdd;
+
+extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
+                                int tok_dtype, const float* U, uint64_t seed, int step,
+                                int64_t row_offset, float mc_t, float mc_s, void* cand,
+                                float* q_out, int B, int L, int M, void* stream) {
+  SVDD_CHECK_ARG(logits && x && cand, "svdd_subs_sample: null pointer");
+  SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_subs_sample: bad shape B=%d L=%d M=%d", B, L, M);
+  SVDD_CHECK_ARG(M < (1 << 16), "svdd_subs_sample: M must be < 65536");
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  SVDD_TRY(check_device());
+  const int64_t BL = (int64_t)B * L;
+  if (BL == 0) return SVDD_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(BL, kThreads);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(Tok, INJ)                                                              \
+  subs_sample_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                            \
+      logits, is_log_p, (const Tok*)x, U, k0, k1, (uint32_t)step, row_offset, mc_t,  \
+      mc_s, (Tok*)cand, q_out, BL, L, M)
+  if (tok_dtype == SVDD_TOK_I64) { if (U) LAUNCH(int64_t, true); else LAUNCH(int64_t, false); }
+  else                           { if (U) LAUNCH(uint8_t, true); else LAUNCH(uint8_t, false); }
+#undef LAUNCH
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
+extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype, void* out,
+                              int64_t n_rows, int L, void* stream) {
+  SVDD_CHECK_ARG(logits && x && out, "svdd_x0_argmax: null pointer");
+  SVDD_CHECK_ARG(n_rows >= 0 && L >= 0, "svdd_x0_argmax: bad shape");
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  SVDD_TRY(check_device());
+  const int64_t NL = n_rows * L;
+  if (NL == 0) return SVDD_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(NL, kThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tok_dtype == SVDD_TOK_I64)
+    x0_argmax_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)x, (int64_t*)out, NL);
+  else
+    x0_argmax_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)x, (uint8_t*)out, NL);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
+extern "C" int svdd_select_gather(const float* scores, const void* cand, int tok_dtype,
+                                  float alpha, const float* U_sel, uint64_t seed, int step,
+                                  int64_t row_offset, void* x_out, int32_t* idx_out, int B,
+                                  int L, int M, void* stream) {
+  SVDD_CHECK_ARG(scores && cand && x_out, "svdd_select_gather: null pointer");
+  SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_select_gather: bad shape");
+  SVDD_CHECK_ARG(M <= 32 * kMaxIterSel, "svdd_select_gather: M=%d exceeds %d", M, 32 * kMaxIterSel);
+  SVDD_CHECK_ARG(alpha >= 0.0f, "svdd_select_gather: alpha must be >= 0");
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  SVDD_TRY(check_device());
+  if (B == 0) return SVDD_OK;
+  int pow2 = 1;
+  while (pow2 < M) pow2 <<= 1;
+  const int lanes = pow2 < 32 ? pow2 : 32;
+  const int iters = pow2 / lanes;
+  const unsigned grid = (unsigned)ceil_div(B, kWarpsPerBlock);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(Tok, INJ)                                                               \
+  select_gather_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                           \
+      scores, (const Tok*)cand, alpha, U_sel, k0, k1, (uint32_t)step, row_offset,     \
+      (Tok*)x_out, idx_out, B, L, M, lanes, iters)
+  const bool inj = U_sel != nullptr;
+  if (tok_dtype == SVDD_TOK_I64) { if (inj) LAUNCH(int64_t, true); else LAUNCH(int64_t, false); }
+  else                           { if (inj) LAUNCH(uint8_t, true); else LAUNCH(uint8_t, false); }
+#undef LAUNCH
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}

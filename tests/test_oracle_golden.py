@@ -1,0 +1,156 @@
+"""The CPU oracle (oracle/) against the golden vectors produced by the
+reference's own code (tests/golden/make_golden.py).  Integer outputs must be
+bit-exact; fp32 outputs bit-exact where the oracle uses the same torch ops."""
+import numpy as np
+import torch
+
+import helpers
+from oracle import nets, svdd
+
+
+def T(a):
+  return torch.from_numpy(np.asarray(a))
+
+
+def test_schedule_matches_reference_expression():
+  g = helpers.load_golden('schedule_128.npz')
+  sched, sigma_last = svdd.move_chances(128, 1e-5)
+  assert sched.dtype == np.float32
+  np.testing.assert_array_equal(sched[:, 1], g['mc_s'])
+  np.testing.assert_array_equal((sched[:, 0] - sched[:, 1]).astype(np.float32),
+                                g['mc_t_minus_mc_s'])
+  assert sigma_last == g['sigma_last']
+  # the low bits differ from the closed form 0.999*t the docstring suggests
+  t = np.linspace(1, 1e-5, 129, dtype=np.float32)[:128]
+  assert np.any(sched[:, 0] != (np.float32(0.999) * t))
+
+
+def _cases():
+  g = helpers.load_golden('stage_kats.npz')
+  for tag in 'abcd':
+    yield tag, {k[2:]: g[k] for k in g.files if k.startswith(tag + '_')}
+
+
+def test_stage2_and_4_known_answers():
+  sched, _ = svdd.move_chances(128, 1e-5)
+  for tag, c in _cases():
+    step = int(c['step'])
+    x, logits, U = T(c['x']), T(c['logits']), T(c['U'])
+    log_p = svdd.subs_parameterization(logits, x)
+    np.testing.assert_array_equal(log_p.numpy(), c['log_p'], err_msg=tag)
+    q = svdd.build_q_xs(log_p, sched[step, 0], sched[step, 1])
+    np.testing.assert_array_equal(q.numpy(), c['q'], err_msg=tag)
+    cand = svdd.draw_candidates(x, q, U)
+    np.testing.assert_array_equal(cand.numpy(), c['cand'], err_msg=tag)
+    idx = svdd.select(T(c['scores']))
+    x_next = svdd.gather_selected(cand, idx)
+    np.testing.assert_array_equal(x_next.numpy(), c['x_next'], err_msg=tag)
+    x0 = log_p[:, :, :-1].argmax(-1)
+    np.testing.assert_array_equal(x0.numpy(), c['x0'], err_msg=tag)
+    # carried tokens never change
+    keep = x != svdd.MASK_INDEX
+    assert torch.equal(x_next[keep], x[keep])
+
+
+def test_analytic_known_answers():
+  # U == 0 -> constant Gumbel denominator -> draw = argmax(q)   
+  x = torch.full((2, 7), 4, dtype=torch.int64)
+  logits = torch.randn(2, 7, 5, generator=torch.Generator().manual_seed(0))
+  q = svdd.build_q_xs(svdd.subs_parameterization(logits, x), 0.9, 0.8)
+  cand = svdd.draw_candidates(x, q, torch.zeros(1, 2, 7, 5))
+  assert torch.equal(cand[0], q.argmax(-1))
+  # M identical scores -> index 0
+  assert torch.equal(svdd.select(torch.ones(3, 6)), torch.zeros(3, dtype=torch.int64))
+  # unmasked rows are exactly one-hot in probability space
+  x2 = torch.tensor([[0, 1, 2, 3, 4]])
+  lp = svdd.subs_parameterization(torch.randn(1, 5, 5), x2)
+  p = lp.exp()
+  assert torch.equal(p[0, :4], torch.eye(5)[:4])
+  assert p[0, 4, 4] == 0 and abs(float(p[0, 4, :4].sum()) - 1) < 1e-6
+
+
+def test_denoiser_matches_reference():
+  g = helpers.load_golden('denoiser_seed44.npz')
+  for L in (50, 200):
+    m = helpers.build_denoiser(44, L)
+    sd = {'backbone.' + k: v for k, v in m.state_dict().items()}
+    np.testing.assert_array_equal(helpers.state_checksum(m.state_dict()), g[f'L{L}_checksum'])
+    x = T(g[f'L{L}_tokens'])
+    with torch.no_grad():
+      logits = nets.denoiser_logits(sd, x)
+    np.testing.assert_allclose(logits.numpy(), g[f'L{L}_logits'], rtol=0, atol=1e-5)
+    log_p = svdd.subs_parameterization(logits, x)
+    np.testing.assert_allclose(log_p.numpy(), g[f'L{L}_log_p'], rtol=0, atol=1e-5)
+    # time bias folded on the host == the reference's per-call computation
+    tb = m.time_bias(0.0)
+    temb = nets.denoiser_time_embedding(sd, torch.zeros(1))
+    for i in range(m.num_layers):
+      ref_row = torch.nn.functional.linear(
+          temb, sd[f'backbone.time_layers.{i}.dense.weight'],
+          sd[f'backbone.time_layers.{i}.dense.bias'])[0]
+      assert torch.allclose(tb[i], ref_row, atol=1e-6)
+
+
+def test_value_nets_match_reference():
+  g = helpers.load_golden('value_nets.npz')
+  with torch.no_grad():
+    emb, head = helpers.build_convgru_value()
+    np.testing.assert_array_equal(helpers.state_checksum(emb.state_dict()), g['convgru_checksum'])
+    oh = svdd.transform_samples(T(g['convgru_tokens'])).float()
+    v = nets.convgru_value(emb.state_dict(), head.state_dict(), oh).squeeze()
+    np.testing.assert_allclose(v.numpy(), g['convgru_values'], rtol=0, atol=1e-6)
+
+    emb, head = helpers.build_convgru_oracle()
+    np.testing.assert_array_equal(helpers.state_checksum(emb.state_dict()), g['rnaoracle_checksum'])
+    v = nets.convgru_value(emb.state_dict(), head.state_dict(), oh.transpose(1, 2)).squeeze()
+    np.testing.assert_allclose(v.numpy(), g['rnaoracle_values'], rtol=0, atol=1e-6)
+
+    emb, head = helpers.build_enformer()
+    np.testing.assert_array_equal(helpers.state_checksum(emb.state_dict()), g['enformer_checksum'])
+    oh = svdd.transform_samples(T(g['enformer_tokens'])).float()
+    v = nets.enformer_value(emb.state_dict(), head.state_dict(), oh, n_heads=8).squeeze()
+    np.testing.assert_allclose(v.numpy(), g['enformer_values'], rtol=1e-5, atol=1e-5)
+    # bf16-operand emulation stays close to fp32 (sanity of the comparison target)
+    vb = nets.enformer_value(emb.state_dict(), head.state_dict(), oh, n_heads=8,
+                             emulate_bf16=True).squeeze()
+    assert float((vb - v).abs().max()) < 0.05 * float(v.abs().max() + 1)
+
+
+def _rna_models():
+  den = helpers.build_denoiser(44, 50)
+  sd = {'backbone.' + k: v for k, v in den.state_dict().items()}
+  denoiser = lambda x: nets.denoiser_logits(sd, x)
+  emb, head = helpers.build_convgru_value()
+  value = lambda tok: nets.convgru_value(emb.state_dict(), head.state_dict(),
+                                         svdd.transform_samples(tok).float()).squeeze()
+  oe, oh = helpers.build_convgru_oracle()
+  reward = lambda tok: nets.convgru_value(
+      oe.state_dict(), oh.state_dict(),
+      svdd.transform_samples(tok).float().transpose(1, 2))[:, 0].squeeze()
+  return denoiser, value, reward
+
+
+def test_trajectories_bit_exact():
+  g = helpers.load_golden('trajectories.npz')
+  denoiser, value, reward = _rna_models()
+  with torch.no_grad():
+    # SVDD-MC: same seed through the oracle's reference-order RNG consumption ...
+    torch.manual_seed(123)
+    x = svdd.controlled_sample(denoiser, value, B=4, L=50, M=3, num_steps=12)
+    np.testing.assert_array_equal(x.numpy(), g['mc_tokens'])
+    # ... and with the recorded uniforms injected
+    x = svdd.controlled_sample(denoiser, value, B=4, L=50, M=3, num_steps=12,
+                               noise=svdd.ArrayNoise(g['mc_U']))
+    np.testing.assert_array_equal(x.numpy(), g['mc_tokens'])
+    # SVDD-PM
+    x = svdd.controlled_sample_tweedie(denoiser, reward, B=4, L=50, M=3, num_steps=6,
+                                       noise=svdd.ArrayNoise(g['pm_U']))
+    np.testing.assert_array_equal(x.numpy(), g['pm_tokens'])
+    # plain ancestral sampler and _sample's mid states
+    x = svdd.decode_sample(denoiser, B=4, L=50, num_steps=16, noise=svdd.ArrayNoise(g['plain_U']))
+    np.testing.assert_array_equal(x.numpy(), g['plain_tokens'])
+    torch.manual_seed(56)
+    x, mid = svdd.sample_with_mid(denoiser, B=2, L=50, num_steps=8)
+    np.testing.assert_array_equal(x.numpy(), g['sample_tokens'])
+    np.testing.assert_array_equal(torch.stack(mid).numpy(), g['sample_mid'])
+  assert int(x.max()) <= 3
