@@ -82,14 +82,17 @@ int64_t svdd_launch_count(void);
  * U      [M,B,L,5] fp32 uniforms in [0,1) in the reference's draw order (one
  *        rand_like per candidate, m-major), or NULL to use the in-kernel
  *        Philox4x32-10 stream keyed by (seed, step, global row = row_offset+b);
+ * seed_dev optional DEVICE uint64 added to `seed` at run time, so a CUDA graph
+ *        that captured this call can be replayed with fresh noise (or NULL);
  * mc_t, mc_s  fp32 move chances 1-exp(-sigma(t)), 1-exp(-sigma(t-dt)) computed
  *        on the host with the reference expression (diffusion_gosai.py:1176-1187);
  * q_out  optional [B,L,5] fp32: the q_xs tensor the reference returns (or NULL).
  */
 int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
-                     int tok_dtype, const float* U, uint64_t seed, int step,
-                     int64_t row_offset, float mc_t, float mc_s, void* cand,
-                     float* q_out, int B, int L, int M, void* stream);
+                     int tok_dtype, const float* U, uint64_t seed,
+                     const uint64_t* seed_dev, int step, int64_t row_offset,
+                     float mc_t, float mc_s, void* cand, float* q_out, int B,
+                     int L, int M, void* stream);
 
 /* ---- stage 4: per-sequence selection + gather ----------------------------
  * Replaces diffusion_gosai.py:1219-1227 / 1451-1459:
@@ -104,9 +107,17 @@ int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
  * x_out  [B,L] selected rows; idx_out optional int32 [B].
  */
 int svdd_select_gather(const float* scores, const void* cand, int tok_dtype,
-                       float alpha, const float* U_sel, uint64_t seed, int step,
-                       int64_t row_offset, void* x_out, int32_t* idx_out, int B,
-                       int L, int M, void* stream);
+                       float alpha, const float* U_sel, uint64_t seed,
+                       const uint64_t* seed_dev, int step, int64_t row_offset,
+                       void* x_out, int32_t* idx_out, int B, int L, int M,
+                       void* stream);
+
+/* ---- SUBS parameterisation alone --------------------------------------------
+ * Replaces Diffusion._subs_parameterization (diffusion_gosai.py:286-304) as the
+ * tail of Diffusion.forward (:339-357): raw logits [N,L,5] + tokens x [N,L] ->
+ * log-probs [N,L,5] (mask column -1e6 - lse; unmasked rows -1e6 / 0). */
+int svdd_subs_log_p(const float* logits, const void* x, int tok_dtype,
+                    float* log_p, int64_t n_rows, int L, void* stream);
 
 /* ---- argmax of post-SUBS log-probs ----------------------------------------
  * Replaces the noise-removal step diffusion_gosai.py:1049-1060
@@ -179,6 +190,20 @@ int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16,
                             const float* bias, float* C, int S, int L, int K,
                             int N, int taps, int dil, int use_tensor_cores,
                             void* stream);
+
+/* Unit-test hooks for the fused pieces of stage 3b (used by tests only):
+ *  - attention pooling over position pairs (enformer_pytorch AttentionPool,
+ *    Enformer.py:2447): y bf16 [S,L_in,C], Wp bf16 [C,C] -> fp32 [S*ceil(L_in/2),C];
+ *  - the Enformer relative-position basis (host, [2n-1,F] fp32);
+ *  - attention over n positions with relative-position logits: qkv fp32
+ *    [rows*n, 2*H*dk+H*dv], rel_content_bias/rel_pos_bias [H*dk], relk
+ *    [H,2n-1,dk] -> bf16 [rows*n, H*dv]. */
+int svdd_selftest_pool(const void* y_bf16, const void* Wp_bf16, float* out, int S,
+                       int L_in, int C, void* stream);
+int svdd_selftest_rel_positions(int n, int F, float* out_host);
+int svdd_selftest_attention(const float* qkv, const float* rcb, const float* rpb,
+                            const float* relk, void* out_bf16, int64_t rows, int n,
+                            int H, int dk, int dv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,9 +8,11 @@ tests/golden/make_golden.py and the product's parameter containers in
 reference so outputs match it bit-for-bit on CPU (checked against
 tests/golden/*.npz).
 
-``emulate_bf16=True`` rounds GEMM/conv *operands* (activations and weights) to
-bfloat16 at exactly the points where the sm_100a kernels do, keeping fp32
-accumulation; it is the tight-tolerance comparison target for the tensor-core
+``emulate_bf16=True`` rounds to bfloat16 at the points where the sm_100a kernels
+do -- GEMM/conv operands (activations and weights) and the activations that
+cross a kernel boundary in bf16 (block outputs, residual inputs, pooled
+values) -- keeping fp32 accumulation, normalisation, attention and the GRU
+recurrence; it is the tight-tolerance comparison target for the tensor-core
 path (the fp32 result is the loose, documented-tolerance target).
 """
 import math
@@ -129,8 +131,8 @@ def convgru_trunk(sd, x, emulate_bf16=False, residual=None):
   if x.shape[1] != cin:                       # Enformer.py:1422-1423
     x = x.transpose(1, 2)
   w = sd['conv_tower.blocks.0.conv.weight']
-  x = F.relu(F.conv1d(x, w, sd['conv_tower.blocks.0.conv.bias'],
-                      padding=w.shape[2] // 2))
+  x = _q(F.relu(F.conv1d(x, w, sd['conv_tower.blocks.0.conv.bias'],
+                         padding=w.shape[2] // 2)), e)
   i = 1
   while f'conv_tower.blocks.{i}.conv.weight' in sd:
     p = f'conv_tower.blocks.{i}.'
@@ -142,7 +144,7 @@ def convgru_trunk(sd, x, emulate_bf16=False, residual=None):
       y = _bn_eval(y, sd, p + 'norm.layer.')
     if has_bn if residual is None else residual:
       y = y + x
-    x = F.relu(y)
+    x = _q(F.relu(y), e)
     i += 1
   # GRUBlock.forward (Enformer.py:1607-1630)
   seq = x.permute(0, 2, 1)                     # [N,L,C]
@@ -225,7 +227,7 @@ def _attention_pool(x, w, emulate_bf16):
   return (pairs * logits.softmax(dim=-1)).sum(dim=-1)
 
 
-def _nacdr_block(sd, p, x, residual, pool, e):
+def _nacdr_block(sd, p, x, residual, pool, e, rec=None, tag=''):
   """ConvBlock.forward with order 'NACDR' (Enformer.py:2266-2292):
   BN -> GELU -> conv -> (dropout) -> +input; then optional attention pool."""
   w = sd[p + 'conv.weight']
@@ -233,12 +235,17 @@ def _nacdr_block(sd, p, x, residual, pool, e):
   y = F.conv1d(_q(y, e), _q(w, e), sd[p + 'conv.bias'], padding=w.shape[2] // 2)
   if residual:
     y = y + x
+  y = _q(y, e)
+  if rec is not None:
+    rec[tag] = y
   if pool:
     y = _attention_pool(y, sd[p + 'pool.layer.to_attn_logits.weight'], e)
+    if rec is not None:
+      rec[tag + '_pooled'] = y
   return y
 
 
-def enformer_trunk(sd, x, n_heads=8, emulate_bf16=False):
+def enformer_trunk(sd, x, n_heads=8, emulate_bf16=False, rec=None):
   """EnformerTrunk.forward (Enformer.py:1326-1334).
 
   x fp32 [N,L,4] -> [N,2*channels,L/2^n_conv].  Conv tower
@@ -249,12 +256,15 @@ def enformer_trunk(sd, x, n_heads=8, emulate_bf16=False):
   e = emulate_bf16
   x = x.transpose(1, 2)                                   # :1328
   w = sd['conv_tower.blocks.0.0.weight']
-  x = F.conv1d(x, w, sd['conv_tower.blocks.0.0.bias'], padding=w.shape[2] // 2)
-  x = _nacdr_block(sd, 'conv_tower.blocks.0.1.', x, True, True, e)
+  x = _q(F.conv1d(x, _q(w, e), sd['conv_tower.blocks.0.0.bias'],
+                  padding=w.shape[2] // 2), e)
+  if rec is not None:
+    rec['x0'] = x
+  x = _nacdr_block(sd, 'conv_tower.blocks.0.1.', x, True, True, e, rec, 'y0')
   i = 1
   while f'conv_tower.blocks.{i}.0.conv.weight' in sd:
-    x = _nacdr_block(sd, f'conv_tower.blocks.{i}.0.', x, False, False, e)
-    x = _nacdr_block(sd, f'conv_tower.blocks.{i}.1.', x, True, True, e)
+    x = _nacdr_block(sd, f'conv_tower.blocks.{i}.0.', x, False, False, e, rec, f'z{i}')
+    x = _nacdr_block(sd, f'conv_tower.blocks.{i}.1.', x, True, True, e, rec, f'y{i}')
     i += 1
   x = x.permute(0, 2, 1)                                  # [N,n,C]
   j = 0
@@ -262,12 +272,16 @@ def enformer_trunk(sd, x, n_heads=8, emulate_bf16=False):
     p = f'transformer_tower.blocks.{j}.'
     h = _ln_channels(x, sd, p + 'norm.layer.')
     x = x + _enformer_attention(sd, p + 'mha.', h, n_heads, e)
+    if rec is not None:
+      rec[f'xattn{j}'] = x
     h = _ln_channels(x, sd, p + 'ffn.dense1.norm.layer.')
     h = F.relu(F.linear(_q(h, e), _q(sd[p + 'ffn.dense1.linear.weight'], e),
                         sd[p + 'ffn.dense1.linear.bias']))
     h = F.linear(_q(h, e), _q(sd[p + 'ffn.dense2.linear.weight'], e),
                  sd[p + 'ffn.dense2.linear.bias'])
     x = x + h
+    if rec is not None:
+      rec[f'xt{j}'] = x
     j += 1
   x = x.permute(0, 2, 1)
   x = _nacdr_block(sd, 'pointwise_conv.', x, False, False, e)

@@ -37,13 +37,17 @@ def _declare(lib):
   lib.svdd_last_error.restype = c.c_char_p
   lib.svdd_device_check.argtypes = [i32]
   lib.svdd_launch_count.restype = i64
-  lib.svdd_subs_sample.argtypes = [vp, i32, vp, i32, vp, u64, i32, i64, f32, f32,
+  lib.svdd_subs_sample.argtypes = [vp, i32, vp, i32, vp, u64, vp, i32, i64, f32, f32,
                                    vp, vp, i32, i32, i32, vp]
-  lib.svdd_select_gather.argtypes = [vp, vp, i32, f32, vp, u64, i32, i64, vp, vp,
+  lib.svdd_select_gather.argtypes = [vp, vp, i32, f32, vp, u64, vp, i32, i64, vp, vp,
                                      i32, i32, i32, vp]
   lib.svdd_x0_argmax.argtypes = [vp, vp, i32, vp, i64, i32, vp]
+  lib.svdd_subs_log_p.argtypes = [vp, vp, i32, vp, i64, i32, vp]
   lib.svdd_selftest_conv_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                           i32, i32, vp]
+  lib.svdd_selftest_pool.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+  lib.svdd_selftest_rel_positions.argtypes = [i32, i32, vp]
+  lib.svdd_selftest_attention.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
   tp = c.POINTER(_Tensor)
   for net, extra in (('denoiser', [i32]), ('convgru', []), ('enformer', [i32])):
     create = getattr(lib, f'svdd_{net}_create', None)
@@ -115,7 +119,7 @@ def tok_dtype(t):
 
 # -- stage 2 ---------------------------------------------------------------------
 def subs_sample(logits, x, M, mc_t, mc_s, U=None, seed=0, step=0, row_offset=0,
-                is_log_p=False, want_q=False, out=None):
+                is_log_p=False, want_q=False, out=None, seed_dev=None):
   """svdd_subs_sample: logits fp32[B,L,5], x [B,L] -> candidates [M,B,L]
   (+ q_xs fp32[B,L,5] when want_q)."""
   _require_cuda(logits, x, U)
@@ -128,15 +132,16 @@ def subs_sample(logits, x, M, mc_t, mc_s, U=None, seed=0, step=0, row_offset=0,
   cand = out if out is not None else torch.empty((M, B, L), dtype=x.dtype, device=x.device)
   q = torch.empty((B, L, 5), dtype=torch.float32, device=x.device) if want_q else None
   check(lib().svdd_subs_sample(_ptr(logits), int(is_log_p), _ptr(x), tok_dtype(x),
-                               _ptr(U), int(seed), int(step), int(row_offset),
-                               float(mc_t), float(mc_s), _ptr(cand), _ptr(q), B, L, M,
+                               _ptr(U), int(seed), _ptr(seed_dev), int(step),
+                               int(row_offset), float(mc_t), float(mc_s), _ptr(cand),
+                               _ptr(q), B, L, M,
                                _stream()))
   return (cand, q) if want_q else cand
 
 
 # -- stage 4 ---------------------------------------------------------------------
 def select_gather(scores, cand, alpha=0.0, U_sel=None, seed=0, step=0,
-                  row_offset=0, want_idx=False, out=None):
+                  row_offset=0, want_idx=False, out=None, seed_dev=None):
   """svdd_select_gather: scores fp32[M,B], cand [M,B,L] -> x_next [B,L]."""
   _require_cuda(scores, cand, U_sel)
   M, B, L = cand.shape
@@ -148,8 +153,8 @@ def select_gather(scores, cand, alpha=0.0, U_sel=None, seed=0, step=0,
   x_out = out if out is not None else torch.empty((B, L), dtype=cand.dtype, device=cand.device)
   idx = torch.empty((B,), dtype=torch.int32, device=cand.device) if want_idx else None
   check(lib().svdd_select_gather(_ptr(scores), _ptr(cand), tok_dtype(cand), float(alpha),
-                                 _ptr(U_sel), int(seed), int(step), int(row_offset),
-                                 _ptr(x_out), _ptr(idx), B, L, M, _stream()))
+                                 _ptr(U_sel), int(seed), _ptr(seed_dev), int(step),
+                                 int(row_offset), _ptr(x_out), _ptr(idx), B, L, M, _stream()))
   return (x_out, idx) if want_idx else x_out
 
 
@@ -164,6 +169,17 @@ def x0_argmax(logits, x, out=None):
   return out
 
 
+def subs_log_p(logits, x):
+  """svdd_subs_log_p: raw logits + tokens -> post-SUBS log-probs (Diffusion.forward)."""
+  _require_cuda(logits, x)
+  L = x.shape[-1]
+  n = x.numel() // L
+  logits, x = logits.contiguous(), x.contiguous()
+  out = torch.empty_like(logits)
+  check(lib().svdd_subs_log_p(_ptr(logits), _ptr(x), tok_dtype(x), _ptr(out), n, L, _stream()))
+  return out
+
+
 def selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=True):
   """A bf16[S,L,K], W bf16[taps,N,K], bias fp32[N] -> fp32[S*L,N]."""
   _require_cuda(A, W, bias)
@@ -175,6 +191,33 @@ def selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=True):
                                       _ptr(C), S, L, K, N, taps, dil, int(tensor_cores),
                                       _stream()))
   return C
+
+
+def selftest_pool(y, Wp):
+  """y bf16[S,L,C], Wp bf16[C,C] -> attention-pooled fp32 [S*ceil(L/2), C]."""
+  _require_cuda(y, Wp)
+  S, L, C = y.shape
+  out = torch.empty((S * ((L + 1) // 2), C), dtype=torch.float32, device=y.device)
+  pad = torch.zeros((S * L + 8, C), dtype=torch.bfloat16, device=y.device)   # 1 row of slack
+  pad[:S * L] = y.reshape(S * L, C)
+  check(lib().svdd_selftest_pool(_ptr(pad), _ptr(Wp.contiguous()), _ptr(out), S, L, C, _stream()))
+  return out
+
+
+def selftest_rel_positions(n, F):
+  out = torch.empty((2 * n - 1, F), dtype=torch.float32)
+  check(lib().svdd_selftest_rel_positions(n, F, ctypes.c_void_p(out.data_ptr())))
+  return out
+
+
+def selftest_attention(qkv, rcb, rpb, relk, n, H, dk, dv):
+  _require_cuda(qkv, rcb, rpb, relk)
+  rows = qkv.shape[0] // n
+  out = torch.empty((rows * n, H * dv), dtype=torch.bfloat16, device=qkv.device)
+  check(lib().svdd_selftest_attention(_ptr(qkv.contiguous()), _ptr(rcb.contiguous()),
+                                      _ptr(rpb.contiguous()), _ptr(relk.contiguous()), _ptr(out),
+                                      rows, n, H, dk, dv, _stream()))
+  return out
 
 
 # -- network handles ---------------------------------------------------------------

@@ -1,6 +1,10 @@
 // Library-level entry points: version, error string, device check, launch counter.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -17,6 +21,24 @@ void set_last_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool debug_dump_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("SVDD_DEBUG_DUMP_DIR") != nullptr ? 1 : 0;
+  return on == 1;
+}
+
+void debug_dump(const char* name, const void* dev_ptr, size_t bytes, cudaStream_t st) {
+  if (!debug_dump_enabled()) return;
+  std::vector<char> host(bytes);
+  cudaStreamSynchronize(st);
+  if (cudaMemcpy(host.data(), dev_ptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  const std::string path = std::string(getenv("SVDD_DEBUG_DUMP_DIR")) + "/" + name + ".bin";
+  if (FILE* f = fopen(path.c_str(), "wb")) {
+    fwrite(host.data(), 1, bytes, f);
+    fclose(f);
+  }
+}
 
 }  // namespace svdd
 

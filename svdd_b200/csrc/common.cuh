@@ -50,6 +50,11 @@ void set_last_error(const char* fmt, ...);
 // counts kernel launches issued by this library (bench.py's gpu_launches)
 void count_launch(int n = 1);
 
+// Debug aid: when SVDD_DEBUG_DUMP_DIR is set, writes `bytes` of device memory to
+// <dir>/<name>.bin after synchronising the stream.  Never active on the hot path.
+void debug_dump(const char* name, const void* dev_ptr, size_t bytes, cudaStream_t st);
+bool debug_dump_enabled();
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

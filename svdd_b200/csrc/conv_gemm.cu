@@ -83,6 +83,8 @@ int pick_bn(const GemmShape& g, int mode) {
 
 }  // namespace
 
+int conv_gemm_n_tiles(const GemmShape& g, int mode) { return g.N / pick_bn(g, mode); }
+
 void choose_row_tiling(int L, int taps, GemmShape* g) {
   (void)taps;
   if (L <= 128) {
@@ -199,4 +201,21 @@ extern "C" int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16, c
   ep.bias = bias;
   ep.out = C; ep.out_dtype = DT_F32; ep.ld_out = N;
   return launch_conv_gemm(A_bf16, W_bf16, g, EPI_GENERIC, ep, st);
+}
+
+// Attention pooling (EPI_POOL) in isolation: y bf16 [S, L_in, C], Wp bf16 [C, C] ->
+// out fp32 [S * ceil(L_in/2), C].
+extern "C" int svdd_selftest_pool(const void* y_bf16, const void* Wp_bf16, float* out, int S,
+                                  int L_in, int C, void* stream) {
+  SVDD_CHECK_ARG(y_bf16 && Wp_bf16 && out, "selftest_pool: null pointer");
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  GemmShape g;
+  g.S = S; g.L = (L_in + 1) / 2; g.L_in = L_in; g.K = C; g.N = C; g.taps = 1; g.dil = 1;
+  choose_row_tiling(g.L, 1, &g);
+  EpiParams ep;
+  ep.pool_vals = y_bf16;
+  ep.out = out; ep.out_dtype = DT_F32; ep.ld_out = C;
+  return launch_conv_gemm(y_bf16, Wp_bf16, g, EPI_POOL, ep, (cudaStream_t)stream);
 }

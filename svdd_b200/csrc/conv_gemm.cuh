@@ -470,6 +470,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int launch_conv_gemm(const void* A, const void* W, const GemmShape& shape, int mode,
                      const EpiParams& ep, cudaStream_t stream);
 
+// Number of N tiles launch_conv_gemm will use for this shape/mode (EPI_HEADDOT writes
+// one partial per row per N tile).
+int conv_gemm_n_tiles(const GemmShape& shape, int mode);
+
 // Picks (BL, BS) for a conv over sequences of length L: whole-sequence tiles when
 // L <= 128 (several sequences per tile), else 128-position tiles.
 void choose_row_tiling(int L, int taps, GemmShape* shape);

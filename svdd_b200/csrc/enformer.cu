@@ -1,0 +1,678 @@
+// Stage 3b: the DNA value net / reward oracle (reference: EnformerTrunk.forward
+// Enformer.py:1326-1334 + ConvHead.forward :2166-2173), scoring N token rows per call.
+//
+// Every dense contraction is a conv_gemm (tcgen05) launch; what the reference runs as
+// separate BatchNorm / GELU / residual / attention-pool / LayerNorm-input kernels is folded
+// into GEMM epilogues:
+//   stem  Conv(4->C0,k15)            im2col of the one-hot (K = 15*4 -> 64) + GEMM; epilogue writes x0 and
+//                                    a0 = GELU(BN(x0)) (the next conv's operand, order 'NACDR' :2266-2292)
+//   1x1 + residual                   GEMM, epilogue adds bias and the block input
+//   AttentionPool(2)                 GEMM over (even, odd) position pairs into two TMEM accumulators;
+//                                    epilogue does the pair softmax, the weighted sum and the NEXT block's
+//                                    BN+GELU (enformer_pytorch AttentionPool; Enformer.py:2447)
+//   Conv(k5)                         implicit GEMM (5 shifted TMA boxes), epilogue writes z and GELU(BN(z))
+//   transformer x n (n = L/2^7 = 2 positions): LN kernel, fused QKV GEMM, tiny attention kernel with the
+//                                    Enformer relative-position logits (rel_k precomputed), out-proj GEMM +
+//                                    residual, LN, FFN GEMMs (+ReLU, +residual)
+//   pointwise 1x1 -> GELU -> head    GEMM with EPI_HEADDOT: GELU(acc+b) . head_w per row, then mean over n.
+//
+// Activations are bf16 channels-last [rows, L_i, f_i]; the transformer residual stream is fp32.
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "weights.cuh"
+
+namespace svdd {
+namespace {
+
+constexpr int kMaxStages = 12;
+constexpr int kMaxBlocksT = 32;
+constexpr int kStemK = 64;       // 15 taps x 4 bases = 60, padded to one 64-wide K block
+constexpr int64_t kChunkRows = 2048;
+constexpr int kMaxPos = 8;       // positions entering the transformer (2 for L=200)
+
+// ---- stem im2col: one-hot windows as bf16 rows of 64 ---------------------------------
+template <typename Tok>
+__global__ void ef_im2col_kernel(const Tok* __restrict__ tokens, __nv_bfloat16* __restrict__ col,
+                                 int64_t NL, int L, int taps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NL * 8) return;
+  const int64_t pos = i >> 3;
+  const int grp = (int)(i & 7);          // 8 bf16 = 2 taps x 4 bases
+  const int l = (int)(pos % L);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int tap = grp * 2 + h;
+    const int li = l + tap - taps / 2;
+    if (tap < taps && li >= 0 && li < L) {
+      const int tok = load_tok(tokens, pos + tap - taps / 2);
+      if (tok < 4) w[h * 2 + (tok >> 1)] = (tok & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
+    }
+  }
+  reinterpret_cast<uint4*>(col)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// stem weight [C0,4,taps] fp32 -> bf16 [C0][64] with k = tap*4 + base
+__global__ void ef_pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    int C0, int taps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C0 * kStemK) return;
+  const int k = i % kStemK, c = i / kStemK;
+  const int tap = k >> 2, base = k & 3;
+  out[i] = __float2bfloat16_rn(tap < taps ? w[(c * 4 + base) * taps + tap] : 0.0f);
+}
+
+// ---- row LayerNorm fp32 [R,C] -> bf16 [R,C]; one block per row ---------------------------
+constexpr int kLnThreads = 256;
+constexpr int kLnMaxPer = 16;   // C <= 4096
+__global__ void __launch_bounds__(kLnThreads)
+ef_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+             __nv_bfloat16* __restrict__ out, int C) {
+  __shared__ float s_red[kLnThreads / 32];
+  __shared__ float s_stat;
+  const int64_t row = blockIdx.x;
+  const float* xr = x + row * C;
+  float v[kLnMaxPer];
+  float sum = 0.0f;
+  int cnt = 0;
+  for (int c = threadIdx.x; c < C; c += kLnThreads) { v[cnt] = xr[c]; sum += v[cnt]; ++cnt; }
+  auto block_sum = [&](float val) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int i = 0; i < kLnThreads / 32; ++i) t += s_red[i];
+      s_stat = t;
+    }
+    __syncthreads();
+    const float r = s_stat;
+    __syncthreads();
+    return r;
+  };
+  const float mean = block_sum(sum) / (float)C;
+  float sq = 0.0f;
+  for (int i = 0; i < cnt; ++i) { const float d = v[i] - mean; sq += d * d; }
+  const float rstd = rsqrtf(block_sum(sq) / (float)C + 1e-5f);
+  cnt = 0;
+  for (int c = threadIdx.x; c < C; c += kLnThreads) {
+    out[row * C + c] = __float2bfloat16_rn((v[cnt] - mean) * rstd * g[c] + b[c]);
+    ++cnt;
+  }
+}
+
+// ---- attention over n <= 8 positions (enformer_pytorch Attention.forward) ----------------
+// qkv fp32 [rows*n, 2*H*dk + H*dv]; relk fp32 [H][2n-1][dk]; out bf16 [rows*n, H*dv].
+//   logits[i,j] = (q_i*scale + rcb).k_j + (q_i*scale + rpb).relk[(j-i)+(n-1)]   (relative_shift)
+__global__ void __launch_bounds__(256)
+ef_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb,
+                    const float* __restrict__ rpb, const float* __restrict__ relk,
+                    __nv_bfloat16* __restrict__ out, int n, int H, int dk, int dv) {
+  __shared__ float s_attn[8][kMaxPos][kMaxPos];   // H <= 8 per pass
+  const int64_t seq = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = 2 * H * dk + H * dv;
+  const float* base = qkv + seq * n * ld;
+  const float scale = rsqrtf((float)dk);
+  for (int h0 = 0; h0 < H; h0 += 8) {
+    const int h = h0 + warp;
+    if (h < H) {
+      for (int i = 0; i < n; ++i) {
+        float lg[kMaxPos];
+        for (int j = 0; j < n; ++j) {
+          float acc = 0.0f;
+          for (int d = lane; d < dk; d += 32) {
+            const float q = base[i * ld + h * dk + d] * scale;
+            const float k = base[j * ld + H * dk + h * dk + d];
+            const float rk = relk[((size_t)h * (2 * n - 1) + (j - i + n - 1)) * dk + d];
+            acc += (q + rcb[h * dk + d]) * k + (q + rpb[h * dk + d]) * rk;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          lg[j] = acc;
+        }
+        float mx = lg[0];
+        for (int j = 1; j < n; ++j) mx = fmaxf(mx, lg[j]);
+        float den = 0.0f;
+        for (int j = 0; j < n; ++j) { lg[j] = __expf(lg[j] - mx); den += lg[j]; }
+        if (lane == 0)
+          for (int j = 0; j < n; ++j) s_attn[warp][i][j] = lg[j] / den;
+      }
+    }
+    __syncthreads();
+    const int hcount = (H - h0 < 8) ? H - h0 : 8;
+    for (int e = threadIdx.x; e < n * hcount * dv; e += blockDim.x) {
+      const int d = e % dv, hh = (e / dv) % hcount, i = e / (dv * hcount);
+      float acc = 0.0f;
+      for (int j = 0; j < n; ++j)
+        acc += s_attn[hh][i][j] * base[j * ld + 2 * H * dk + (h0 + hh) * dv + d];
+      out[(seq * n + i) * (size_t)(H * dv) + (h0 + hh) * dv + d] = __float2bfloat16_rn(acc);
+    }
+    __syncthreads();
+  }
+}
+
+// relk[blk][h][p][d] = sum_f W[blk][(h*dk+d)][f] * pos[p][f]
+__global__ void ef_relk_kernel(const float* __restrict__ w, const float* __restrict__ pos,
+                               float* __restrict__ relk, int H, int dk, int F, int P) {
+  const int blk = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * P * dk) return;
+  const int d = i % dk, p = (i / dk) % P, h = i / (dk * P);
+  const float* wr = w + ((size_t)blk * H * dk + h * dk + d) * F;
+  float acc = 0.0f;
+  for (int f = 0; f < F; ++f) acc += wr[f] * pos[p * F + f];
+  relk[(size_t)blk * H * P * dk + i] = acc;
+}
+
+// score[s] = head_b + mean_p sum_tiles partials[(s*n+p), tile]
+__global__ void ef_mean_kernel(const float* __restrict__ partials, int n_tiles, const float* __restrict__ hb,
+                               float* __restrict__ scores, int64_t rows, int n) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= rows) return;
+  float acc = 0.0f;
+  const float* p = partials + (size_t)s * n * n_tiles;
+  for (int i = 0; i < n * n_tiles; ++i) acc += p[i];
+  scores[s] = acc / (float)n + hb[0];
+}
+
+// enformer_pytorch get_positional_embed(n, F) (use_tf_gamma = False), computed once per n.
+std::vector<float> positional_table(int n, int F) {
+  const int P = 2 * n - 1, k = F / 6;
+  std::vector<float> t((size_t)P * F, 0.0f);
+  std::vector<double> base((size_t)3 * k);
+  const double top = log((double)n) / log(2.0);
+  for (int p = 0; p < P; ++p) {
+    const double dist = (double)(p - (n - 1)), ad = fabs(dist);
+    double gmax = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const double frac = k > 1 ? (double)i / (k - 1) : 0.0;
+      const double half_life = pow(2.0, 3.0 + (top - 3.0) * frac);
+      base[i] = exp(-log(2.0) / half_life * ad);
+      base[k + i] = ((pow(2.0, (double)(i + 1)) - 1.0) > ad) ? 1.0 : 0.0;
+      const double stddev = (double)n / (2.0 * k);
+      const double mean = (double)n / k + ((double)n - (double)n / k) * frac;
+      const double conc = (mean / stddev) * (mean / stddev), rate = mean / (stddev * stddev);
+      const double xlogy = (ad == 0.0) ? ((conc - 1.0) == 0.0 ? 0.0 : -INFINITY) : (conc - 1.0) * log(ad);
+      const double logp = xlogy - rate * ad - (lgamma(conc) - conc * log(rate));
+      base[2 * k + i] = exp(logp) + 1e-8;
+      if (base[2 * k + i] > gmax) gmax = base[2 * k + i];
+    }
+    for (int i = 0; i < k; ++i) base[2 * k + i] /= gmax;
+    const double sgn = dist > 0 ? 1.0 : (dist < 0 ? -1.0 : 0.0);
+    for (int i = 0; i < 3 * k; ++i) {
+      t[(size_t)p * F + i] = (float)base[i];
+      t[(size_t)p * F + 3 * k + i] = (float)(sgn * base[i]);
+    }
+  }
+  return t;
+}
+
+}  // namespace
+}  // namespace svdd
+
+using namespace svdd;
+
+struct svdd_enformer {
+  int H = 8, dk = 64, dv = 192, C = 1536, C0 = 768, F = 192;
+  int n_stage = 7, n_blocks = 11, stem_taps = 15;
+  int f[kMaxStages] = {};
+  DeviceArena arena;
+  __nv_bfloat16* stem_w = nullptr; float* stem_b = nullptr;
+  __nv_bfloat16* w5[kMaxStages] = {}; float* b5[kMaxStages] = {};
+  float* bn5_s[kMaxStages] = {}; float* bn5_t[kMaxStages] = {};   // BN feeding the k5 conv of stage i
+  __nv_bfloat16* w1[kMaxStages] = {}; float* b1[kMaxStages] = {};
+  float* bn1_s[kMaxStages] = {}; float* bn1_t[kMaxStages] = {};   // BN feeding the 1x1 conv of stage i
+  __nv_bfloat16* wp[kMaxStages] = {};
+  struct Block {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *rcb, *rpb, *bo, *bf1, *bf2;
+    __nv_bfloat16 *wqkv, *wo, *wf1, *wf2;
+  } blk[kMaxBlocksT] = {};
+  float* relk_w = nullptr;     // [n_blocks][H*dk][F]
+  float *bnpw_s = nullptr, *bnpw_t = nullptr, *bpw = nullptr, *hw = nullptr, *hb = nullptr;
+  __nv_bfloat16* wpw = nullptr;
+  // lazily built for the transformer length n of the first call
+  int relk_n = 0;
+  float* relk = nullptr;       // [n_blocks][H][2n-1][dk]
+  float* pos_dev = nullptr;
+  ~svdd_enformer() {
+    if (relk) cudaFree(relk);
+    if (pos_dev) cudaFree(pos_dev);
+  }
+};
+
+extern "C" int svdd_enformer_create(const svdd_tensor* tensors, int n_tensors, int n_heads,
+                                    void* stream, svdd_enformer** out) {
+  SVDD_CHECK_ARG(tensors && out && n_tensors > 0, "svdd_enformer_create: null argument");
+  SVDD_CHECK_ARG(n_heads >= 1 && n_heads <= 64, "svdd_enformer_create: bad n_heads %d", n_heads);
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  TensorTable tt{tensors, n_tensors};
+  svdd_enformer* h = new (std::nothrow) svdd_enformer();
+  SVDD_CHECK_ARG(h != nullptr, "out of host memory");
+  auto fail = [&](int code) { delete h; return code; };
+#define REQUIRE(cond, ...)                                        \
+  do { if (!(cond)) { set_last_error(__VA_ARGS__); return fail(SVDD_ERR_INVALID_ARGUMENT); } } while (0)
+#define GET_OR_FAIL(var, name, numel)               \
+  const float* var = tt.get((name), (numel));       \
+  if (var == nullptr) return fail(SVDD_ERR_MISSING_TENSOR)
+#define TRY_OR_FAIL(expr)                           \
+  do { int _rc = (expr); if (_rc != SVDD_OK) return fail(_rc); } while (0)
+
+  // ---- discover the architecture from tensor shapes ------------------------------------
+  const std::string ct = "conv_tower.blocks.";
+  h->C0 = (int)tt.dim(ct + "0.0.weight", 0);
+  h->stem_taps = (int)tt.dim(ct + "0.0.weight", 2);
+  REQUIRE(h->C0 > 0 && tt.dim(ct + "0.0.weight", 1) == 4, "enformer: stem conv must take 4 channels");
+  REQUIRE(h->stem_taps * 4 <= kStemK && h->stem_taps % 2 == 1, "enformer: unsupported stem kernel %d", h->stem_taps);
+  int ns = 1;
+  h->f[0] = h->C0;
+  while (ns < kMaxStages && tt.has(ct + std::to_string(ns) + ".0.conv.weight")) {
+    h->f[ns] = (int)tt.dim(ct + std::to_string(ns) + ".0.conv.weight", 0);
+    ++ns;
+  }
+  h->n_stage = ns;
+  h->C = h->f[ns - 1];
+  int nb = 0;
+  while (nb < kMaxBlocksT && tt.has("transformer_tower.blocks." + std::to_string(nb) + ".mha.to_q.weight")) ++nb;
+  h->n_blocks = nb;
+  h->H = n_heads;
+  if (nb > 0) {
+    h->dk = (int)tt.dim("transformer_tower.blocks.0.mha.to_q.weight", 0) / n_heads;
+    h->dv = (int)tt.dim("transformer_tower.blocks.0.mha.to_v.weight", 0) / n_heads;
+    h->F = (int)tt.dim("transformer_tower.blocks.0.mha.to_rel_k.weight", 1);
+    REQUIRE(h->F % 6 == 0, "enformer: num_rel_pos_features %d not divisible by 6", h->F);
+  }
+  for (int i = 0; i < ns; ++i) REQUIRE(h->f[i] % 64 == 0, "enformer: channel count %d not a multiple of 64", h->f[i]);
+  const int C = h->C, H = h->H, dk = h->dk, dv = h->dv, F = h->F;
+  const int nqkv = 2 * H * dk + H * dv;
+  REQUIRE(nqkv % 64 == 0 && (H * dv) % 64 == 0, "enformer: head dims must give multiples of 64");
+
+  // ---- reserve / carve -----------------------------------------------------------------
+  DeviceArena& A = h->arena;
+  auto plan = [&](bool take) {
+#define F32(ptr, n) do { if (take) ptr = A.take<float>(n); else A.reserve(sizeof(float) * (size_t)(n)); } while (0)
+#define B16(ptr, n) do { if (take) ptr = A.take<__nv_bfloat16>(n); else A.reserve(sizeof(__nv_bfloat16) * (size_t)(n)); } while (0)
+    B16(h->stem_w, (size_t)h->C0 * kStemK); F32(h->stem_b, h->C0);
+    for (int i = 0; i < ns; ++i) {
+      const size_t fi = h->f[i], fp = i > 0 ? h->f[i - 1] : 0;
+      if (i > 0) { B16(h->w5[i], 5 * fi * fp); F32(h->b5[i], fi); F32(h->bn5_s[i], fp); F32(h->bn5_t[i], fp); }
+      B16(h->w1[i], fi * fi); F32(h->b1[i], fi); F32(h->bn1_s[i], fi); F32(h->bn1_t[i], fi);
+      B16(h->wp[i], fi * fi);
+    }
+    for (int j = 0; j < nb; ++j) {
+      auto& b = h->blk[j];
+      F32(b.ln1_g, C); F32(b.ln1_b, C); F32(b.ln2_g, C); F32(b.ln2_b, C);
+      F32(b.rcb, H * dk); F32(b.rpb, H * dk); F32(b.bo, C); F32(b.bf1, 2 * C); F32(b.bf2, C);
+      B16(b.wqkv, (size_t)nqkv * C); B16(b.wo, (size_t)C * H * dv);
+      B16(b.wf1, (size_t)2 * C * C); B16(b.wf2, (size_t)2 * C * C);
+    }
+    F32(h->relk_w, (size_t)(nb > 0 ? nb : 1) * H * dk * F);
+    F32(h->bnpw_s, C); F32(h->bnpw_t, C); F32(h->bpw, 2 * C); F32(h->hw, 2 * C); F32(h->hb, 8);
+    B16(h->wpw, (size_t)2 * C * C);
+#undef F32
+#undef B16
+  };
+  plan(false);
+  TRY_OR_FAIL(A.commit());
+  plan(true);
+
+  // ---- pack ------------------------------------------------------------------------------
+  auto bn_fold = [&](const std::string& p, int n, float* s, float* t) -> int {
+    const float* g = tt.get(p + "weight", n);
+    const float* b = tt.get(p + "bias", n);
+    const float* m = tt.get(p + "running_mean", n);
+    const float* v = tt.get(p + "running_var", n);
+    if (!g || !b || !m || !v) return SVDD_ERR_MISSING_TENSOR;
+    return fold_bn(g, b, m, v, nullptr, 1e-5f, s, t, n, st);
+  };
+  {
+    GET_OR_FAIL(sw, ct + "0.0.weight", (int64_t)h->C0 * 4 * h->stem_taps);
+    GET_OR_FAIL(sb, ct + "0.0.bias", h->C0);
+    ef_pack_stem_kernel<<<ceil_div(h->C0 * kStemK, 256), 256, 0, st>>>(sw, h->stem_w, h->C0, h->stem_taps);
+    TRY_OR_FAIL(copy_f32(sb, h->stem_b, h->C0, st));
+  }
+  for (int i = 0; i < ns; ++i) {
+    const int fi = h->f[i];
+    const std::string p1 = ct + std::to_string(i) + ".1.";
+    if (i > 0) {
+      const int fp = h->f[i - 1];
+      const std::string p0 = ct + std::to_string(i) + ".0.";
+      GET_OR_FAIL(w, p0 + "conv.weight", (int64_t)fi * fp * 5);
+      GET_OR_FAIL(b, p0 + "conv.bias", fi);
+      TRY_OR_FAIL(pack_conv_weight(w, h->w5[i], fi, fp, 5, st));
+      TRY_OR_FAIL(copy_f32(b, h->b5[i], fi, st));
+      TRY_OR_FAIL(bn_fold(p0 + "norm.layer.", fp, h->bn5_s[i], h->bn5_t[i]));
+    }
+    GET_OR_FAIL(w, p1 + "conv.weight", (int64_t)fi * fi);
+    GET_OR_FAIL(b, p1 + "conv.bias", fi);
+    GET_OR_FAIL(wp, p1 + "pool.layer.to_attn_logits.weight", (int64_t)fi * fi);
+    TRY_OR_FAIL(pack_conv_weight(w, h->w1[i], fi, fi, 1, st));
+    TRY_OR_FAIL(copy_f32(b, h->b1[i], fi, st));
+    TRY_OR_FAIL(pack_conv_weight(wp, h->wp[i], fi, fi, 1, st));
+    TRY_OR_FAIL(bn_fold(p1 + "norm.layer.", fi, h->bn1_s[i], h->bn1_t[i]));
+  }
+  for (int j = 0; j < nb; ++j) {
+    auto& b = h->blk[j];
+    const std::string p = "transformer_tower.blocks." + std::to_string(j) + ".";
+    GET_OR_FAIL(g1, p + "norm.layer.weight", C);
+    GET_OR_FAIL(b1, p + "norm.layer.bias", C);
+    GET_OR_FAIL(g2, p + "ffn.dense1.norm.layer.weight", C);
+    GET_OR_FAIL(b2, p + "ffn.dense1.norm.layer.bias", C);
+    GET_OR_FAIL(wq, p + "mha.to_q.weight", (int64_t)H * dk * C);
+    GET_OR_FAIL(wk, p + "mha.to_k.weight", (int64_t)H * dk * C);
+    GET_OR_FAIL(wv, p + "mha.to_v.weight", (int64_t)H * dv * C);
+    GET_OR_FAIL(wo, p + "mha.to_out.weight", (int64_t)C * H * dv);
+    GET_OR_FAIL(bo, p + "mha.to_out.bias", C);
+    GET_OR_FAIL(wr, p + "mha.to_rel_k.weight", (int64_t)H * dk * F);
+    GET_OR_FAIL(rc, p + "mha.rel_content_bias", H * dk);
+    GET_OR_FAIL(rp, p + "mha.rel_pos_bias", H * dk);
+    GET_OR_FAIL(w1, p + "ffn.dense1.linear.weight", (int64_t)2 * C * C);
+    GET_OR_FAIL(c1, p + "ffn.dense1.linear.bias", 2 * C);
+    GET_OR_FAIL(w2, p + "ffn.dense2.linear.weight", (int64_t)2 * C * C);
+    GET_OR_FAIL(c2, p + "ffn.dense2.linear.bias", C);
+    TRY_OR_FAIL(copy_f32(g1, b.ln1_g, C, st)); TRY_OR_FAIL(copy_f32(b1, b.ln1_b, C, st));
+    TRY_OR_FAIL(copy_f32(g2, b.ln2_g, C, st)); TRY_OR_FAIL(copy_f32(b2, b.ln2_b, C, st));
+    TRY_OR_FAIL(pack_conv_weight(wq, b.wqkv, H * dk, C, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(wk, b.wqkv + (size_t)H * dk * C, H * dk, C, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(wv, b.wqkv + (size_t)2 * H * dk * C, H * dv, C, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(wo, b.wo, C, H * dv, 1, st));
+    TRY_OR_FAIL(copy_f32(bo, b.bo, C, st));
+    TRY_OR_FAIL(copy_f32(wr, h->relk_w + (size_t)j * H * dk * F, (int64_t)H * dk * F, st));
+    TRY_OR_FAIL(copy_f32(rc, b.rcb, H * dk, st)); TRY_OR_FAIL(copy_f32(rp, b.rpb, H * dk, st));
+    TRY_OR_FAIL(pack_conv_weight(w1, b.wf1, 2 * C, C, 1, st)); TRY_OR_FAIL(copy_f32(c1, b.bf1, 2 * C, st));
+    TRY_OR_FAIL(pack_conv_weight(w2, b.wf2, C, 2 * C, 1, st)); TRY_OR_FAIL(copy_f32(c2, b.bf2, C, st));
+  }
+  {
+    GET_OR_FAIL(w, "pointwise_conv.conv.weight", (int64_t)2 * C * C);
+    GET_OR_FAIL(b, "pointwise_conv.conv.bias", 2 * C);
+    GET_OR_FAIL(hw, "head.channel_transform.conv.layer.weight", 2 * C);
+    GET_OR_FAIL(hb, "head.channel_transform.conv.layer.bias", 1);
+    TRY_OR_FAIL(pack_conv_weight(w, h->wpw, 2 * C, C, 1, st));
+    TRY_OR_FAIL(copy_f32(b, h->bpw, 2 * C, st));
+    TRY_OR_FAIL(copy_f32(hw, h->hw, 2 * C, st));
+    TRY_OR_FAIL(copy_f32(hb, h->hb, 1, st));
+    TRY_OR_FAIL(bn_fold("pointwise_conv.norm.layer.", C, h->bnpw_s, h->bnpw_t));
+  }
+#undef REQUIRE
+#undef GET_OR_FAIL
+#undef TRY_OR_FAIL
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("svdd_enformer_create: %s", cudaGetErrorString(e));
+    return fail(SVDD_ERR_CUDA);
+  }
+  *out = h;
+  return SVDD_OK;
+}
+
+extern "C" void svdd_enformer_destroy(svdd_enformer* h) { delete h; }
+
+// ---- unit-test hooks for the two non-GEMM pieces -------------------------------------------
+extern "C" int svdd_selftest_rel_positions(int n, int F, float* out_host) {
+  SVDD_CHECK_ARG(n >= 1 && F >= 6 && F % 6 == 0 && out_host, "selftest_rel_positions: bad argument");
+  std::vector<float> t = positional_table(n, F);
+  memcpy(out_host, t.data(), t.size() * sizeof(float));
+  return SVDD_OK;
+}
+
+extern "C" int svdd_selftest_attention(const float* qkv, const float* rcb, const float* rpb,
+                                       const float* relk, void* out_bf16, int64_t rows, int n,
+                                       int H, int dk, int dv, void* stream) {
+  SVDD_CHECK_ARG(qkv && rcb && rpb && relk && out_bf16, "selftest_attention: null pointer");
+  SVDD_CHECK_ARG(n >= 1 && n <= kMaxPos, "selftest_attention: n out of range");
+  ef_attention_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
+      qkv, rcb, rpb, relk, (__nv_bfloat16*)out_bf16, n, H, dk, dv);
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
+namespace {
+struct EfWs {
+  __nv_bfloat16* col;
+  __nv_bfloat16* big[3];
+  float* xt;
+  __nv_bfloat16* hn;
+  float* qkv;
+  __nv_bfloat16* ao;
+  __nv_bfloat16* u;
+  float* partials;
+};
+int ef_final_len(const svdd_enformer* h, int L) {
+  int n = L;
+  for (int i = 0; i < h->n_stage; ++i) n = (n + 1) / 2;
+  return n;
+}
+size_t ef_carve(const svdd_enformer* h, Workspace& W, int64_t rows, int L, EfWs* o) {
+  const size_t NL = (size_t)rows * L;
+  size_t big = 0;
+  int len = L;
+  for (int i = 0; i < h->n_stage; ++i) {
+    const size_t need = (size_t)rows * len * h->f[i];
+    if (need > big) big = need;
+    len = (len + 1) / 2;
+  }
+  const int n = len;
+  const size_t R = (size_t)rows * n;
+  const int C = h->C, nqkv = 2 * h->H * h->dk + h->H * h->dv;
+  o->col = W.take<__nv_bfloat16>(NL * kStemK + 64);
+  for (int i = 0; i < 3; ++i) o->big[i] = W.take<__nv_bfloat16>(big + 4096);
+  o->xt = W.take<float>(R * C + 64);
+  o->hn = W.take<__nv_bfloat16>(R * C + 64);
+  o->qkv = W.take<float>(R * nqkv + 64);
+  o->ao = W.take<__nv_bfloat16>(R * h->H * h->dv + 64);
+  o->u = W.take<__nv_bfloat16>(R * 2 * C + 64);
+  o->partials = W.take<float>(R * (2 * C / 64) + 64);
+  return W.used();
+}
+}  // namespace
+
+extern "C" size_t svdd_enformer_workspace_bytes(const svdd_enformer* h, int64_t n_rows, int L) {
+  Workspace W(nullptr, 0);
+  EfWs o;
+  return ef_carve(h, W, n_rows < kChunkRows ? n_rows : kChunkRows, L, &o);
+}
+
+extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok_dtype, float* scores,
+                                   int64_t n_rows, int L, void* ws, size_t ws_bytes, void* stream) {
+  SVDD_CHECK_ARG(h && tokens && scores, "svdd_enformer_score: null pointer");
+  SVDD_CHECK_ARG(n_rows >= 0 && L >= 1, "svdd_enformer_score: bad shape");
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  if (n_rows == 0) return SVDD_OK;
+  if (ws == nullptr || ws_bytes < svdd_enformer_workspace_bytes(h, n_rows, L)) {
+    set_last_error("svdd_enformer_score: workspace too small");
+    return SVDD_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = ef_final_len(h, L);
+  SVDD_CHECK_ARG(n >= 1 && n <= kMaxPos, "svdd_enformer_score: %d positions reach the transformer (max %d)", n, kMaxPos);
+  const int C = h->C, H = h->H, dk = h->dk, dv = h->dv, F = h->F;
+  const int nqkv = 2 * H * dk + H * dv;
+  const int P = 2 * n - 1;
+
+  // relative-position keys for this n (first call only; not on the hot path)
+  if (h->n_blocks > 0 && h->relk_n != n) {
+    if (h->relk) { cudaFree(h->relk); h->relk = nullptr; }
+    if (h->pos_dev) { cudaFree(h->pos_dev); h->pos_dev = nullptr; }
+    std::vector<float> pos = positional_table(n, F);
+    SVDD_CUDA(cudaMalloc(&h->pos_dev, pos.size() * sizeof(float)));
+    SVDD_CUDA(cudaMalloc(&h->relk, (size_t)h->n_blocks * H * P * dk * sizeof(float)));
+    SVDD_CUDA(cudaMemcpy(h->pos_dev, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ef_relk_kernel<<<dim3(ceil_div(H * P * dk, 128), h->n_blocks), 128, 0, st>>>(h->relk_w, h->pos_dev, h->relk,
+                                                                                H, dk, F, P);
+    SVDD_LAUNCH_CHECK();
+    h->relk_n = n;
+  }
+
+  auto gemm_flat = [&](const void* A, const void* Wt, int64_t R, int K, int N, const EpiParams& ep,
+                       int mode) -> int {
+    GemmShape g;
+    g.S = 1; g.L = (int)R; g.L_in = (int)R; g.K = K; g.N = N; g.taps = 1; g.dil = 1; g.BL = 128; g.BS = 1;
+    return launch_conv_gemm(A, Wt, g, mode, ep, st);
+  };
+
+  const size_t tok_bytes = tok_dtype == SVDD_TOK_I64 ? 8 : 1;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += kChunkRows) {
+    const int64_t rows = (n_rows - r0 < kChunkRows) ? n_rows - r0 : kChunkRows;
+    const int64_t NL = rows * L;
+    Workspace W(ws, ws_bytes);
+    EfWs b;
+    ef_carve(h, W, rows, L, &b);
+    const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)r0 * L * tok_bytes;
+
+    // ---- stem -----------------------------------------------------------------------------
+    {
+      const unsigned grid = (unsigned)ceil_div<int64_t>(NL * 8, 256);
+      if (tok_dtype == SVDD_TOK_I64)
+        ef_im2col_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)tok, b.col, NL, L, h->stem_taps);
+      else
+        ef_im2col_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)tok, b.col, NL, L, h->stem_taps);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+    }
+    __nv_bfloat16 *x = b.big[0], *a = b.big[1], *y = b.big[2];   // roles rotate below
+    {
+      EpiParams ep;                                  // x0 = conv + b ; a0 = GELU(BN_{0.1}(x0))
+      ep.bias = h->stem_b;
+      ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = h->C0;
+      ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = h->C0;
+      ep.scale2 = h->bn1_s[0]; ep.shift2 = h->bn1_t[0]; ep.act2 = ACT_GELU;
+      SVDD_TRY(gemm_flat(b.col, h->stem_w, NL, kStemK, h->C0, ep, EPI_GENERIC));
+      if (debug_dump_enabled()) {
+        debug_dump("ef_x0", x, (size_t)NL * h->C0 * 2, st);
+        debug_dump("ef_a0", a, (size_t)NL * h->C0 * 2, st);
+      }
+    }
+    int len = L;
+    for (int i = 0; i < h->n_stage; ++i) {
+      const int fi = h->f[i];
+      if (i > 0) {
+        // z = Conv_k5(a) + b ; a' = GELU(BN_{i.1}(z)).  `a` holds GELU(BN_{i.0}(pooled)).
+        const int fp = h->f[i - 1];
+        GemmShape g;
+        g.S = (int)rows; g.L = len; g.L_in = len; g.K = fp; g.N = fi; g.taps = 5; g.dil = 1;
+        choose_row_tiling(len, 5, &g);
+        EpiParams ep;
+        ep.bias = h->b5[i];
+        ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = fi;
+        ep.out2 = y; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+        ep.scale2 = h->bn1_s[i]; ep.shift2 = h->bn1_t[i]; ep.act2 = ACT_GELU;
+        SVDD_TRY(launch_conv_gemm(a, h->w5[i], g, EPI_GENERIC, ep, st));
+        if (debug_dump_enabled()) {
+          debug_dump(("ef_z" + std::to_string(i)).c_str(), x, (size_t)rows * len * fi * 2, st);
+          debug_dump(("ef_ap" + std::to_string(i)).c_str(), y, (size_t)rows * len * fi * 2, st);
+        }
+        __nv_bfloat16* t = a; a = y; y = t;          // a <- a' ; old a is free (now y)
+      }
+      {  // y = Conv_1x1(a) + b + x     (residual ConvBlock, Enformer.py:1836-1838 / 1866-1868)
+        EpiParams ep;
+        ep.bias = h->b1[i];
+        ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+        ep.out = y; ep.out_dtype = DT_BF16; ep.ld_out = fi;
+        SVDD_TRY(gemm_flat(a, h->w1[i], rows * len, fi, fi, ep, EPI_GENERIC));
+        if (debug_dump_enabled())
+          debug_dump(("ef_y" + std::to_string(i)).c_str(), y, (size_t)rows * len * fi * 2, st);
+      }
+      {  // attention pool over position pairs; epilogue also prepares the next conv's operand
+        const int lo = (len + 1) / 2;
+        GemmShape g;
+        g.S = (int)rows; g.L = lo; g.L_in = len; g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
+        choose_row_tiling(lo, 1, &g);
+        EpiParams ep;
+        ep.pool_vals = y;
+        if (i + 1 < h->n_stage) {
+          ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+          ep.scale2 = h->bn5_s[i + 1]; ep.shift2 = h->bn5_t[i + 1]; ep.act2 = ACT_GELU;
+        } else {
+          ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
+        }
+        SVDD_TRY(launch_conv_gemm(y, h->wp[i], g, EPI_POOL, ep, st));
+        if (debug_dump_enabled()) {
+          if (i + 1 < h->n_stage)
+            debug_dump(("ef_a" + std::to_string(i + 1)).c_str(), a, (size_t)rows * lo * fi * 2, st);
+          else
+            debug_dump("ef_xt_in", b.xt, (size_t)rows * lo * fi * 4, st);
+        }
+        len = lo;
+      }
+    }
+    // ---- transformer tower ------------------------------------------------------------------
+    const int64_t R = rows * n;
+    for (int j = 0; j < h->n_blocks; ++j) {
+      auto& blk = h->blk[j];
+      ef_ln_kernel<<<(unsigned)R, kLnThreads, 0, st>>>(b.xt, blk.ln1_g, blk.ln1_b, b.hn, C);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+      {
+        EpiParams ep;
+        ep.out = b.qkv; ep.out_dtype = DT_F32; ep.ld_out = nqkv;
+        SVDD_TRY(gemm_flat(b.hn, blk.wqkv, R, C, nqkv, ep, EPI_GENERIC));
+      }
+      ef_attention_kernel<<<(unsigned)rows, 256, 0, st>>>(b.qkv, blk.rcb, blk.rpb,
+                                                          h->relk + (size_t)j * H * P * dk, b.ao, n, H, dk, dv);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+      {
+        EpiParams ep;                                // x += to_out(attn)   (:1941-1945)
+        ep.bias = blk.bo;
+        ep.res = b.xt; ep.res_dtype = DT_F32; ep.ld_res = C;
+        ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = C;
+        SVDD_TRY(gemm_flat(b.ao, blk.wo, R, H * dv, C, ep, EPI_GENERIC));
+      }
+      if (debug_dump_enabled()) {
+        debug_dump(("ef_qkv" + std::to_string(j)).c_str(), b.qkv, (size_t)R * nqkv * 4, st);
+        debug_dump(("ef_ao" + std::to_string(j)).c_str(), b.ao, (size_t)R * H * dv * 2, st);
+        debug_dump(("ef_xattn" + std::to_string(j)).c_str(), b.xt, (size_t)R * C * 4, st);
+      }
+      ef_ln_kernel<<<(unsigned)R, kLnThreads, 0, st>>>(b.xt, blk.ln2_g, blk.ln2_b, b.hn, C);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+      {
+        EpiParams ep;                                // ReLU(Linear(C, 2C))
+        ep.bias = blk.bf1; ep.act = ACT_RELU;
+        ep.out = b.u; ep.out_dtype = DT_BF16; ep.ld_out = 2 * C;
+        SVDD_TRY(gemm_flat(b.hn, blk.wf1, R, C, 2 * C, ep, EPI_GENERIC));
+      }
+      {
+        EpiParams ep;                                // x += Linear(2C, C)   (:1946-1948)
+        ep.bias = blk.bf2;
+        ep.res = b.xt; ep.res_dtype = DT_F32; ep.ld_res = C;
+        ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = C;
+        if (j + 1 == h->n_blocks) {                  // pointwise ConvBlock's BN+GELU operand
+          ep.out2 = b.hn; ep.out2_dtype = DT_BF16; ep.ld_out2 = C;
+          ep.scale2 = h->bnpw_s; ep.shift2 = h->bnpw_t; ep.act2 = ACT_GELU;
+        }
+        SVDD_TRY(gemm_flat(b.u, blk.wf2, R, 2 * C, C, ep, EPI_GENERIC));
+      }
+      if (debug_dump_enabled())
+        debug_dump(("ef_xt" + std::to_string(j)).c_str(), b.xt, (size_t)R * C * 4, st);
+    }
+    if (h->n_blocks == 0) {
+      set_last_error("svdd_enformer_score: trunk without transformer blocks is not supported");
+      return SVDD_ERR_INVALID_ARGUMENT;
+    }
+    // ---- pointwise conv -> GELU -> head 1x1 -> mean over positions ----------------------------
+    int n_tiles = 1;
+    {
+      GemmShape g;
+      g.S = 1; g.L = (int)R; g.L_in = (int)R; g.K = C; g.N = 2 * C; g.BL = 128; g.BS = 1;
+      EpiParams ep;
+      ep.bias = h->bpw; ep.act = ACT_GELU;
+      ep.head_w = h->hw; ep.partials = b.partials;
+      n_tiles = conv_gemm_n_tiles(g, EPI_HEADDOT);
+      SVDD_TRY(launch_conv_gemm(b.hn, h->wpw, g, EPI_HEADDOT, ep, st));
+    }
+    ef_mean_kernel<<<(unsigned)ceil_div<int64_t>(rows, 128), 128, 0, st>>>(b.partials, n_tiles, h->hb,
+                                                                           scores + r0, rows, n);
+    count_launch();
+    SVDD_LAUNCH_CHECK();
+  }
+  return SVDD_OK;
+}

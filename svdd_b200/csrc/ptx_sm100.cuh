@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace svdd {
 namespace ptx {
@@ -55,8 +56,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spins on try_wait (which suspends in hardware between polls).  A pipeline bug
+// would otherwise hang the GPU, so after ~2^26 failed polls the kernel traps:
+// the launch fails loudly with an error instead of wedging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 26)) {
+      printf("svdd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
+             (int)threadIdx.x);
+      __trap();
+    }
   }
 }
 

@@ -65,7 +65,8 @@ template <typename Tok, bool kInjected>
 __global__ void __launch_bounds__(kThreads)
 subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                    const Tok* __restrict__ x, const float* __restrict__ U,
-                   uint32_t key0, uint32_t key1, uint32_t step, int64_t row_offset,
+                   uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t step,
+                   int64_t row_offset,
                    float mc_t, float mc_s, Tok* __restrict__ cand,
                    float* __restrict__ q_out, int64_t BL, int L, int M) {
   __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
@@ -148,6 +149,8 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
       }
     }
   } else {
+    const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
+    const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32);
     const uint32_t row = (uint32_t)(row_offset + pos / L);
     const uint32_t l = (uint32_t)(pos % L);
     for (int m = 0; m < M; ++m) {
@@ -197,6 +200,40 @@ x0_argmax_kernel(const float* __restrict__ logits, const Tok* __restrict__ x,
   store_tok(out, pos, best);
 }
 
+// ---- post-SUBS log-probabilities (the tensor Diffusion.forward returns) ----------
+template <typename Tok>
+__global__ void __launch_bounds__(kThreads)
+subs_log_p_kernel(const float* __restrict__ logits, const Tok* __restrict__ x,
+                  float* __restrict__ out, int64_t NL) {
+  __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
+  if (pos0 >= NL) return;
+  const int64_t pos = pos0 + lane;
+  float* stage = s_stage[warp];
+  const int64_t n_el = NL * kVocab, e0 = pos0 * kVocab;
+#pragma unroll
+  for (int k = 0; k < kVocab; ++k) {
+    const int64_t e = e0 + k * 32 + lane;
+    stage[k * 32 + lane] = (e < n_el) ? __ldg(logits + e) : 0.0f;
+  }
+  __syncwarp();
+  float lg[kVocab], logp[kVocab];
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) lg[v] = stage[lane * kVocab + v];
+  __syncwarp();
+  const int tok = pos < NL ? load_tok(x, pos) : 0;
+  subs_log_p(lg, tok, false, logp);
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) stage[lane * kVocab + v] = logp[v];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < kVocab; ++k) {
+    const int64_t e = e0 + k * 32 + lane;
+    if (e < n_el) out[e] = stage[k * 32 + lane];
+  }
+}
+
 // ---- stage 4 -----------------------------------------------------------------
 // One warp per sequence.  The max / sum reductions use the same butterfly
 // (lanes = next_pow2(M) capped at 32, element i on lane i % lanes, xor
@@ -208,8 +245,8 @@ constexpr int kMaxIterSel = 8;  // M <= 256
 template <typename Tok, bool kInjected>
 __global__ void __launch_bounds__(kThreads)
 select_gather_kernel(const float* __restrict__ scores, const Tok* __restrict__ cand,
-                     float alpha, const float* __restrict__ U_sel, uint32_t key0,
-                     uint32_t key1, uint32_t step, int64_t row_offset,
+                     float alpha, const float* __restrict__ U_sel, uint64_t seed,
+                     const uint64_t* __restrict__ seed_dev, uint32_t step, int64_t row_offset,
                      Tok* __restrict__ x_out, int32_t* __restrict__ idx_out, int B,
                      int L, int M, int lanes, int iters) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,6 +293,8 @@ select_gather_kernel(const float* __restrict__ scores, const Tok* __restrict__ c
           if (kInjected) {
             u = __ldg(U_sel + (size_t)b * M + m);
           } else {
+            const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
+            const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32);
             const Philox4 w = philox4x32_10((uint32_t)(m >> 2), (uint32_t)(row_offset + b),
                                             0u, step | (1u << 24), key0, key1);
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
@@ -295,8 +334,9 @@ int check_device() {
 using namespace svdd;
 
 extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
-                                int tok_dtype, const float* U, uint64_t seed, int step,
-                                int64_t row_offset, float mc_t, float mc_s, void* cand,
+                                int tok_dtype, const float* U, uint64_t seed,
+                                const uint64_t* seed_dev, int step, int64_t row_offset,
+                                float mc_t, float mc_s, void* cand,
                                 float* q_out, int B, int L, int M, void* stream) {
   SVDD_CHECK_ARG(logits && x && cand, "svdd_subs_sample: null pointer");
   SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_subs_sample: bad shape B=%d L=%d M=%d", B, L, M);
@@ -306,12 +346,11 @@ extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x
   const int64_t BL = (int64_t)B * L;
   if (BL == 0) return SVDD_OK;
   const unsigned grid = (unsigned)ceil_div<int64_t>(BL, kThreads);
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(Tok, INJ)                                                              \
   subs_sample_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                            \
-      logits, is_log_p, (const Tok*)x, U, k0, k1, (uint32_t)step, row_offset, mc_t,  \
-      mc_s, (Tok*)cand, q_out, BL, L, M)
+      logits, is_log_p, (const Tok*)x, U, seed, seed_dev, (uint32_t)step, row_offset, \
+      mc_t, mc_s, (Tok*)cand, q_out, BL, L, M)
   if (tok_dtype == SVDD_TOK_I64) { if (U) LAUNCH(int64_t, true); else LAUNCH(int64_t, false); }
   else                           { if (U) LAUNCH(uint8_t, true); else LAUNCH(uint8_t, false); }
 #undef LAUNCH
@@ -339,9 +378,29 @@ extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype,
   return SVDD_OK;
 }
 
+extern "C" int svdd_subs_log_p(const float* logits, const void* x, int tok_dtype, float* log_p,
+                               int64_t n_rows, int L, void* stream) {
+  SVDD_CHECK_ARG(logits && x && log_p, "svdd_subs_log_p: null pointer");
+  SVDD_CHECK_ARG(n_rows >= 0 && L >= 0, "svdd_subs_log_p: bad shape");
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  SVDD_TRY(check_device());
+  const int64_t NL = n_rows * L;
+  if (NL == 0) return SVDD_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(NL, kThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tok_dtype == SVDD_TOK_I64)
+    subs_log_p_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)x, log_p, NL);
+  else
+    subs_log_p_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)x, log_p, NL);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
 extern "C" int svdd_select_gather(const float* scores, const void* cand, int tok_dtype,
-                                  float alpha, const float* U_sel, uint64_t seed, int step,
-                                  int64_t row_offset, void* x_out, int32_t* idx_out, int B,
+                                  float alpha, const float* U_sel, uint64_t seed,
+                                  const uint64_t* seed_dev, int step, int64_t row_offset,
+                                  void* x_out, int32_t* idx_out, int B,
                                   int L, int M, void* stream) {
   SVDD_CHECK_ARG(scores && cand && x_out, "svdd_select_gather: null pointer");
   SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_select_gather: bad shape");
@@ -355,12 +414,11 @@ extern "C" int svdd_select_gather(const float* scores, const void* cand, int tok
   const int lanes = pow2 < 32 ? pow2 : 32;
   const int iters = pow2 / lanes;
   const unsigned grid = (unsigned)ceil_div(B, kWarpsPerBlock);
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(Tok, INJ)                                                               \
   select_gather_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                           \
-      scores, (const Tok*)cand, alpha, U_sel, k0, k1, (uint32_t)step, row_offset,     \
-      (Tok*)x_out, idx_out, B, L, M, lanes, iters)
+      scores, (const Tok*)cand, alpha, U_sel, seed, seed_dev, (uint32_t)step,         \
+      row_offset, (Tok*)x_out, idx_out, B, L, M, lanes, iters)
   const bool inj = U_sel != nullptr;
   if (tok_dtype == SVDD_TOK_I64) { if (inj) LAUNCH(int64_t, true); else LAUNCH(int64_t, false); }
   else                           { if (inj) LAUNCH(uint8_t, true); else LAUNCH(uint8_t, false); }

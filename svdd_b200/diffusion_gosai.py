@@ -1,0 +1,395 @@
+"""``Diffusion`` -- drop-in for the sampling entry points of the reference's
+``diffusion_gosai.Diffusion`` (diffusion_gosai.py:74-1888), decode path only.
+
+Same names, argument meaning and error behaviour as the reference for
+  forward                     :339      controlled_sample           :1022  (SVDD-MC)
+  _sample_prior               :751      controlled_sample_tweedie   :1106  (SVDD-PM)
+  _sample                     :821      _ddpm_update_finetune*      :1148 / :1175 / :1374
+  decode_sample               :889      transform_samples           :1462
+  load_from_checkpoint (Lightning classmethod used at Enformer.py:92)
+but every stage of a reverse step is a hand-written sm_100a kernel behind the C
+ABI (include/svdd_b200.h):
+
+  stage 1  svdd_denoiser_forward   tcgen05 implicit-GEMM conv stack        (A4, A5)
+  stage 2  svdd_subs_sample        SUBS + q_xs + M Gumbel-max draws + carry (A6-A8)
+  stage 3  svdd_*_score            value net / reward oracle on all B*M candidates
+                                   in ONE call (A9-A13; Tweedie: stage 1 + svdd_x0_argmax)
+  stage 4  svdd_select_gather      softmax -> argmax / resample -> gather   (A14)
+
+The 128-step loop has no host synchronisation (the reference's per-row Python
+gather costs B syncs per step) and is captured once into a CUDA graph.  Tokens
+live as uint8 on the device; int64 only at the API boundary.  Training, the
+analytic/SEDD samplers and the guidance baselines are out of scope (SURVEY.md
+section 8) and raise NotImplementedError.
+"""
+import itertools
+
+import torch
+from torch import nn
+
+from . import _lib, denoiser, noise_schedule, value_nets
+
+
+class InjectedNoise:
+  """Uniform noise supplied by the caller instead of the in-kernel Philox stream
+  (parity runs: "fed the reference's uniform-noise tensors").
+
+  U_draw fp32 CUDA [steps, M, B, L, 5]: the reference's ``rand_like(q_xs)`` tensors
+  in draw order (step-major, then candidate).  U_sel fp32 CUDA [steps, B, M] is
+  only used when alpha > 0."""
+
+  def __init__(self, U_draw, U_sel=None):
+    self.U_draw, self.U_sel = U_draw, U_sel
+
+  def draws(self, step):
+    return self.U_draw[step]
+
+  def select(self, step):
+    return None if self.U_sel is None else self.U_sel[step]
+
+
+def _as_scorer(embedding, head):
+  """(embedding, head) modules -> packed scoring handle.  An object that already
+  exposes ``score(tokens, out=)`` (e.g. a handle, or a test double that replays
+  recorded values) is used as is."""
+  if hasattr(embedding, 'score'):
+    return embedding
+  return value_nets.packed_scorer(embedding, head)
+
+
+class Diffusion(nn.Module):
+  """MDLM (SUBS parameterisation, absorbing state) sampler + SVDD decoding."""
+
+  def __init__(self, config):
+    super().__init__()
+    self.config = config
+    self.vocab_size = 4
+    self.sampler = config.sampling.predictor
+    self.mask_index = self.vocab_size
+    self.vocab_size += 1
+    self.parameterization = config.parameterization
+    if config.backbone != 'cnn':
+      raise NotImplementedError(
+          f"backbone '{config.backbone}': only the CNN denoiser is on the decode "
+          'path (models/__init__.py comments the others out, SURVEY.md F7)')
+    if self.parameterization != 'subs':
+      raise NotImplementedError("only parameterization='subs' is built")
+    self.backbone = denoiser.CNNModel(config.model, alphabet_size=self.vocab_size, num_cls=3)
+    self.T = config.T
+    self.subs_masking = config.subs_masking
+    self.noise = noise_schedule.get_noise(config)
+    self.ema = None          # decode uses the raw weights
+    self.time_conditioning = config.time_conditioning
+    self.neg_infinity = -1000000.0
+    # run-level randomness: Philox key = base seed + number of sampler calls so far
+    self._base_seed = None
+    self._calls = itertools.count()
+    self._graphs = {}
+    self.use_cuda_graph = True
+
+  # -- plumbing ---------------------------------------------------------------------
+  @property
+  def device(self):
+    return next(self.parameters()).device
+
+  @property
+  def dtype(self):
+    return torch.float32
+
+  @classmethod
+  def load_from_checkpoint(cls, checkpoint_path, config=None, map_location='cpu', **kw):
+    """Reads a Lightning ``.ckpt`` of the reference model: ``state_dict`` with
+    ``backbone.*`` keys (shapes in SURVEY.md A5).  EMA / loop state are ignored,
+    as on the reference's decode path."""
+    if config is None:
+      raise ValueError('config is required (the reference passes config=cfg, Enformer.py:92)')
+    ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+    sd = ckpt['state_dict'] if 'state_dict' in ckpt else ckpt
+    model = cls(config)
+    own = {k: v for k, v in sd.items() if k.startswith('backbone.')}
+    missing, unexpected = model.load_state_dict(own, strict=False)
+    missing = [k for k in missing if k.startswith('backbone.')]
+    if missing or unexpected:
+      raise RuntimeError(f'checkpoint mismatch: missing={missing} unexpected={unexpected}')
+    return model
+
+  def _seed_for_call(self):
+    if self._base_seed is None:
+      self._base_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    return (self._base_seed + 0x9E3779B97F4A7C15 * next(self._calls)) & 0xFFFFFFFFFFFFFFFF
+
+  def manual_seed(self, seed):
+    """Re-keys the in-kernel noise stream (torch.manual_seed analogue)."""
+    self._base_seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+    self._calls = itertools.count()
+
+  # -- reference API: single forward ----------------------------------------------------
+  def _process_sigma(self, sigma):
+    if sigma is None:
+      raise AssertionError("sigma is None is only valid for parameterization == 'ar'")
+    if sigma.ndim > 1:
+      sigma = sigma.squeeze(-1)
+    if not self.time_conditioning:
+      sigma = torch.zeros_like(sigma)
+    assert sigma.ndim == 1, sigma.shape
+    return sigma
+
+  def _sigma_scalar(self, sigma):
+    """Host scalar of a batch-constant sigma tensor (0 without time conditioning)."""
+    if not self.time_conditioning:
+      return 0.0
+    return float(self._process_sigma(sigma).reshape(-1)[0])
+
+  @torch.no_grad()
+  def forward(self, x, sigma):
+    """Returns log score: post-SUBS log-probs fp32 [B,L,5] (diffusion_gosai.py:339-357)."""
+    logits = self.backbone.packed().forward(x, self._sigma_scalar(sigma))
+    return _lib.subs_log_p(logits, x)
+
+  def _subs_parameterization(self, logits, xt):
+    return _lib.subs_log_p(logits, xt)
+
+  def _sample_prior(self, *batch_dims):
+    return self.mask_index * torch.ones(*batch_dims, dtype=torch.int64)
+
+  def transform_samples(self, samples, num_classes=4):
+    """One-hot(4) with mask rows zeroed (diffusion_gosai.py:1462-1470).  Kept for
+    callers that want the tensor; the scoring kernels consume token ids directly."""
+    mask = samples != 4
+    one_hot = torch.nn.functional.one_hot(samples * mask, num_classes=num_classes)
+    return one_hot * mask.unsqueeze(-1)
+
+  # -- reference API: single reverse steps -------------------------------------------------
+  def _move_chances(self, t, dt):
+    """(mc_t, mc_s, sigma_t, sigma_s) from tensors exactly as diffusion_gosai.py:1176-1187."""
+    t0 = t.detach().reshape(-1)[:1].reshape(1, 1).cpu().float()
+    sigma_t = self.noise(t0)[0].squeeze(-1)
+    sigma_s = self.noise(t0 - dt)[0].squeeze(-1)
+    mc_t = 1 - torch.exp(-sigma_t)
+    mc_s = 1 - torch.exp(-sigma_s)
+    return mc_t.item(), mc_s.item(), sigma_t.item(), sigma_s.item()
+
+  @torch.no_grad()
+  def _ddpm_update_finetune(self, x, t, dt, U=None):
+    """diffusion_gosai.py:1148-1172 -> (x_next, x, q_xs, copy_flag)."""
+    mc_t, mc_s, sigma_t, _ = self._move_chances(t, dt)
+    logits = self.backbone.packed().forward(x, sigma_t if self.time_conditioning else 0.0)
+    cand, q = _lib.subs_sample(logits, x, 1, mc_t, mc_s, U=None if U is None else U[None],
+                               seed=self._seed_for_call(), want_q=True)
+    return cand[0], x, q, (x != self.mask_index).to(x.dtype)
+
+  @torch.no_grad()
+  def _ddpm_update_finetune_controlled(self, x, t, dt, pre_scorer_embedding, pre_scorer_head,
+                                       repeats=10, U=None, alpha=0.0):
+    """diffusion_gosai.py:1175-1228 -> (final_samples, x, q_xs, copy_flag)."""
+    mc_t, mc_s, sigma_t, _ = self._move_chances(t, dt)
+    seed = self._seed_for_call()
+    logits = self.backbone.packed().forward(x, sigma_t if self.time_conditioning else 0.0)
+    cand, q = _lib.subs_sample(logits, x, repeats, mc_t, mc_s, U=U, seed=seed, want_q=True)
+    B, L = x.shape
+    scores = _as_scorer(pre_scorer_embedding, pre_scorer_head).score(cand.reshape(repeats * B, L))
+    final = _lib.select_gather(scores.reshape(repeats, B), cand, alpha=alpha, seed=seed)
+    return final, x, q, (x != self.mask_index).to(x.dtype)
+
+  @torch.no_grad()
+  def _ddpm_update_finetune_controlled_twedie(self, x, t, dt, reward_model, repeats=10,
+                                              options='True', task='dna', U=None, alpha=0.0):
+    """diffusion_gosai.py:1374-1460 -> (final_samples, x, q_xs, copy_flag)."""
+    if task == 'rna_saluki':
+      raise NotImplementedError('rna_saluki needs a private .npy the reference does not ship')
+    mc_t, mc_s, sigma_t, sigma_s = self._move_chances(t, dt)
+    seed = self._seed_for_call()
+    den = self.backbone.packed()
+    logits = den.forward(x, sigma_t if self.time_conditioning else 0.0)
+    cand, q = _lib.subs_sample(logits, x, repeats, mc_t, mc_s, U=U, seed=seed, want_q=True)
+    B, L = x.shape
+    flat = cand.reshape(repeats * B, L)
+    if options == 'True':
+      lg2 = den.forward(flat, sigma_s if self.time_conditioning else 0.0)
+      flat = _lib.x0_argmax(lg2, flat)
+    scores = _as_scorer(reward_model.embedding, reward_model.head).score(flat)
+    final = _lib.select_gather(scores.reshape(repeats, B), cand, alpha=alpha, seed=seed)
+    return final, x, q, (x != self.mask_index).to(x.dtype)
+
+  # -- the engine: whole-trajectory loops ------------------------------------------------------
+  def _resolve(self, num_steps, eval_sp_size):
+    B = self.config.loader.eval_batch_size if eval_sp_size is None else eval_sp_size
+    if self.parameterization == 'ar':
+      raise NotImplementedError('autoregressive sampling is not on the decode path')
+    if num_steps is None:
+      num_steps = self.config.sampling.steps
+    if self.sampler != 'ddpm':
+      raise NotImplementedError(
+          f"sampling.predictor='{self.sampler}': the decode path is built for 'ddpm' "
+          '(configs_gosai*/config_gosai.yaml:36)')
+    return int(B), int(num_steps)
+
+  def _trajectory(self, mode, B, num_steps, eps, M=1, scorer=None, tweedie=True, alpha=0.0,
+                  noise=None, row_offset=0, collect_mid=False, seed=None, trace=None):
+    """Runs num_steps reverse steps (+ noise removal) for B sequences on this GPU.
+
+    mode 'plain' (A18), 'mc' (A1/SVDD-MC) or 'pm' (SVDD-PM).  Returns the uint8 token
+    tensor [B,L] (and the list of intermediate states when collect_mid)."""
+    dev = self.device
+    if dev.type != 'cuda':
+      raise _lib.SvddError('move the model to a CUDA device (svdd_b200 has no CPU path)')
+    L = int(self.config.model.length)
+    sched, sigma_last = noise_schedule.move_chance_schedule(self.noise, num_steps, eps)
+    den = self.backbone.packed()
+    tc = self.time_conditioning
+    seed = self._seed_for_call() if seed is None else seed
+    graphable = self.use_cuda_graph and not collect_mid and noise is None and trace is None
+    if graphable:
+      # the run key lives in device memory so that a captured graph replays with fresh noise
+      if getattr(self, '_seed_dev', None) is None or self._seed_dev.device != dev:
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+      skw = dict(seed=0, seed_dev=self._seed_dev)
+    else:
+      skw = dict(seed=seed)
+    u8 = torch.uint8
+    buf = dict(
+        x=torch.full((B, L), self.mask_index, dtype=u8, device=dev),
+        x2=torch.empty((B, L), dtype=u8, device=dev),
+        logits=torch.empty((B, L, 5), dtype=torch.float32, device=dev),
+        cand=torch.empty((M, B, L), dtype=u8, device=dev),
+        scores=torch.empty((M, B), dtype=torch.float32, device=dev))
+    if mode == 'pm' and tweedie:
+      buf['logits2'] = torch.empty((M * B, L, 5), dtype=torch.float32, device=dev)
+      buf['x0'] = torch.empty((M * B, L), dtype=u8, device=dev)
+    mids = []
+
+    def step(i):
+      mc_t, mc_s, sigma_t, sigma_s = sched[i]
+      x, x2 = (buf['x'], buf['x2']) if i % 2 == 0 else (buf['x2'], buf['x'])
+      den.forward(x, sigma_t if tc else 0.0, out=buf['logits'])
+      U = None if noise is None else noise.draws(i)
+      if mode == 'plain':
+        _lib.subs_sample(buf['logits'], x, 1, mc_t, mc_s, U=U, step=i,
+                         row_offset=row_offset, out=x2[None], **skw)
+      else:
+        cand = buf['cand']
+        _lib.subs_sample(buf['logits'], x, M, mc_t, mc_s, U=U, step=i,
+                         row_offset=row_offset, out=cand, **skw)
+        flat = cand.reshape(M * B, L)
+        if mode == 'pm' and tweedie:
+          den.forward(flat, sigma_s if tc else 0.0, out=buf['logits2'])
+          flat = _lib.x0_argmax(buf['logits2'], flat, out=buf['x0'])
+        scorer.score(flat, out=buf['scores'].reshape(-1))
+        _lib.select_gather(buf['scores'], cand, alpha=alpha,
+                           U_sel=None if noise is None else noise.select(i),
+                           step=i, row_offset=row_offset, out=x2, **skw)
+      if collect_mid and i != num_steps - 1:
+        mids.append(x2.clone())
+      if trace is not None:
+        rec = dict(step=i, mc_t=mc_t, mc_s=mc_s, x=x.clone(), logits=buf['logits'].clone(),
+                   x_next=x2.clone())
+        if mode != 'plain':
+          rec.update(cand=buf['cand'].clone(), scores=buf['scores'].clone())
+          if mode == 'pm' and tweedie:
+            rec.update(x0=buf['x0'].clone(), logits2=buf['logits2'].clone())
+        trace.append(rec)
+
+    def finish():
+      x = buf['x'] if num_steps % 2 == 0 else buf['x2']
+      out = buf['x2'] if num_steps % 2 == 0 else buf['x']
+      if self.config.sampling.noise_removal:
+        # diffusion_gosai.py:1049-1060: x = forward(x, sigma(t_last))[:, :, :-1].argmax(-1)
+        den.forward(x, sigma_last if tc else 0.0, out=buf['logits'])
+        if trace is not None:
+          trace.append(dict(step=num_steps, x=x.clone(), logits=buf['logits'].clone()))
+        return _lib.x0_argmax(buf['logits'], x, out=out)
+      return x
+
+    if not graphable:
+      for i in range(num_steps):
+        step(i)
+      result = finish()
+      return (result, mids) if collect_mid else result
+    return self._graph_trajectory(mode, B, num_steps, eps, M, scorer, tweedie, alpha,
+                                  row_offset, seed, buf, step, finish)
+
+  def _graph_trajectory(self, mode, B, num_steps, eps, M, scorer, tweedie, alpha, row_offset,
+                        seed, buf, step, finish):
+    """Captures the whole trajectory once per configuration and replays it.  The
+    per-run Philox key lives in device memory (`seed_dev`), so replays draw fresh
+    noise without re-capturing."""
+    key = (mode, B, num_steps, eps, M, id(scorer), tweedie, alpha, row_offset,
+           id(self.backbone.packed()))
+    entry = self._graphs.get(key)
+    def set_seed():
+      # int64 view of the unsigned 64-bit run key
+      self._seed_dev.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+
+    if entry is None:
+      # One eager pass sizes every workspace / lazy table outside the capture.
+      set_seed()
+      for i in range(min(num_steps, 2)):
+        step(i)
+      finish()
+      torch.cuda.synchronize()
+      buf['x'].fill_(self.mask_index)
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph):
+        for i in range(num_steps):
+          step(i)
+        result = finish()
+      entry = (graph, buf, result)
+      if len(self._graphs) > 8:
+        self._graphs.clear()
+      self._graphs[key] = entry
+    graph, gbuf, result = entry
+    set_seed()
+    gbuf['x'].fill_(self.mask_index)
+    graph.replay()
+    return result.clone()
+
+  # -- reference API: samplers -------------------------------------------------------------------
+  @torch.no_grad()
+  def _sample(self, num_steps=None, eps=1e-5, eval_sp_size=None, cdq=False, noise=None):
+    """diffusion_gosai.py:821-886 (cdq=False): returns (x, mid_x) with the
+    num_steps-1 intermediate states."""
+    if cdq:
+      raise NotImplementedError('cdq rollouts belong to value-function training')
+    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    x, mids = self._trajectory('plain', B, num_steps, eps, noise=noise, collect_mid=True)
+    return x.long(), [m.long() for m in mids]
+
+  @torch.no_grad()
+  def decode_sample(self, num_steps=None, eps=1e-5, eval_sp_size=None, cdq=False, noise=None,
+                    row_offset=0, trace=None):
+    """Plain ancestral sampling, the "pre-trained" baseline (diffusion_gosai.py:889-936)."""
+    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    return self._trajectory('plain', B, num_steps, eps, noise=noise, row_offset=row_offset,
+                            trace=trace).long()
+
+  @torch.no_grad()
+  def controlled_sample(self, pre_scorer_embedding, pre_scorer_head, num_steps=None, eps=1e-5,
+                        eval_sp_size=None, sample_M=10, alpha=0.0, noise=None, row_offset=0,
+                        trace=None):
+    """SVDD-MC (diffusion_gosai.py:1022-1061).  ``alpha``/``noise``/``row_offset``/``trace``
+    are additions: alpha=0 is the reference's argmax selection."""
+    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    scorer = _as_scorer(pre_scorer_embedding, pre_scorer_head)
+    return self._trajectory('mc', B, num_steps, eps, M=int(sample_M), scorer=scorer, alpha=alpha,
+                            noise=noise, row_offset=row_offset, trace=trace).long()
+
+  @torch.no_grad()
+  def controlled_sample_tweedie(self, reward_model, num_steps=None, eps=1e-5, eval_sp_size=None,
+                                sample_M=10, options=True, task='dna', alpha=0.0, noise=None,
+                                row_offset=0, trace=None):
+    """SVDD-PM (diffusion_gosai.py:1106-1145).  As in the reference, Tweedie's
+    x0-prediction is used only when ``options`` equals the STRING "True" (:1414)."""
+    if task == 'rna_saluki':
+      raise NotImplementedError('rna_saluki needs a private .npy the reference does not ship')
+    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    scorer = (reward_model if hasattr(reward_model, 'score')
+              else _as_scorer(reward_model.embedding, reward_model.head))
+    return self._trajectory('pm', B, num_steps, eps, M=int(sample_M), scorer=scorer,
+                            tweedie=(options == 'True'), alpha=alpha, noise=noise,
+                            row_offset=row_offset, trace=trace).long()
+
+  # -- everything else in the reference class is outside the decode path -------------------------
+  def training_step(self, *a, **k):
+    raise NotImplementedError('training is out of scope of svdd_b200 (SURVEY.md section 8)')
+
+  controlled_sample_TDS = controlled_sample_DPS = controlled_sample_CG = training_step

@@ -180,12 +180,33 @@ def ref_convgru_oracle():
   return E.OriBaseModel(emb, head).eval()
 
 
-def ref_enformer_small():
+def ref_enformer_small(calibrate=True):
+  """Small EnformerTrunk whose BatchNorm running statistics are CALIBRATED on a
+  batch (as training would leave them): with the constructor's (0, 1) statistics a
+  random-init trunk is so contractive that its output barely depends on the input
+  and a parity test could not see semantic errors.  The statistics are committed
+  (enformer_small_bn.npz) so the GPU box can rebuild the same net."""
   kw = helpers.ENFORMER_SMALL_KW
   torch.manual_seed(5)
   emb = E.EnformerTrunk(**kw)
   head = E.ConvHead(n_tasks=1, in_channels=2 * kw['channels'], act_func=None, pool_func='avg')
   helpers.perturb_(emb, 9)
+  if calibrate:
+    bns = [m for m in emb.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    for m in emb.modules():
+      if isinstance(m, torch.nn.Dropout):
+        m.p = 0.0
+    for m in bns:
+      m.reset_running_stats()
+      m.momentum = None                      # cumulative average over the calibration pass
+    emb.train()
+    d = ref_diffusion(50)
+    cal = helpers.random_tokens(48, 200, 4242, 0.3)
+    with torch.no_grad():
+      emb(d.transform_samples(cal).float())
+    stats = {k: v.clone() for k, v in emb.state_dict().items()
+             if k.endswith('running_mean') or k.endswith('running_var')}
+    save('enformer_small_bn.npz', **stats)
   return emb.eval(), head.eval()
 
 

@@ -104,6 +104,13 @@ def build_enformer(seed=5, perturb=9, full=False):
   head = value_nets.ConvHead(n_tasks=1, in_channels=2 * kw['channels'],
                              act_func=None, pool_func='avg')
   perturb_(emb, perturb)
+  if not full:
+    # calibrated BatchNorm statistics (see tests/golden/make_golden.py:ref_enformer_small)
+    stats = load_golden('enformer_small_bn.npz')
+    sd = emb.state_dict()
+    with torch.no_grad():
+      for k in stats.files:
+        sd[k].copy_(torch.from_numpy(stats[k]))
   return emb.eval(), head.eval()
 
 

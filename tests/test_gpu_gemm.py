@@ -1,0 +1,92 @@
+"""-m gpu: the tcgen05/TMA implicit-GEMM building block against a plain
+CUDA-core kernel of the same contraction and against torch fp32 conv1d."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from svdd_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # S, L, K, N, taps, dil
+    (3, 200, 128, 128, 9, 1),      # denoiser layer, dilation 1
+    (3, 200, 128, 128, 9, 4),
+    (2, 200, 128, 128, 9, 16),
+    (2, 200, 128, 128, 9, 64),     # most taps fall in the padding and are skipped
+    (5, 50, 128, 128, 9, 64),      # RNA length: only the centre tap is in range
+    (7, 50, 64, 64, 5, 1),         # ConvGRU conv block
+    (9, 100, 768, 768, 5, 1),      # Enformer tower conv (L=100)
+    (11, 25, 896, 1024, 5, 1),     # odd-length tiles, several sequences per tile
+    (40, 7, 128, 256, 5, 1),
+    (64, 4, 1280, 1536, 5, 1),
+    (4, 200, 768, 768, 1, 1),      # 1x1 conv == plain GEMM (flattened rows)
+    (300, 2, 1536, 2560, 1, 1),    # fused QKV projection
+    (300, 2, 3072, 1536, 1, 1),
+    (1, 1, 64, 64, 1, 1),
+]
+
+
+@pytest.mark.parametrize('S,L,K,N,taps,dil', CASES)
+def test_conv_gemm_matches_cuda_core_kernel(cuda, S, L, K, N, taps, dil):
+  g = torch.Generator(device='cpu').manual_seed(S * 131 + L)
+  A = (torch.randn(S, L, K, generator=g)).to(cuda).bfloat16()
+  W = (torch.randn(taps, N, K, generator=g) * (K * taps) ** -0.5).to(cuda).bfloat16()
+  bias = torch.randn(N, generator=g).to(cuda)
+  ref = _lib.selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=False)
+  out = _lib.selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=True)
+  torch.cuda.synchronize()
+  err = float((out - ref).abs().max())
+  assert err < 2e-3, err
+  # and against torch's own conv1d in fp32 on the same bf16-rounded operands
+  y = F.conv1d(A.float().permute(0, 2, 1), W.float().permute(1, 2, 0), bias,
+               dilation=dil, padding=(taps // 2) * dil)
+  y = y.permute(0, 2, 1).reshape(S * L, N)
+  assert float((out - y).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize('S,L,C', [(3, 200, 128), (5, 100, 768), (7, 25, 256), (9, 13, 128),
+                                   (20, 7, 384), (33, 4, 128), (1, 1, 64), (2, 3, 64)])
+def test_attention_pool_epilogue(cuda, S, L, C):
+  """EPI_POOL: two TMEM accumulators (even / odd positions), pair softmax and the
+  weighted sum, incl. odd lengths where the last pair has a padded slot."""
+  g = torch.Generator().manual_seed(S * 7 + L)
+  y = torch.randn(S, L, C, generator=g).to(cuda).bfloat16()
+  Wp = (2 * torch.eye(C) + torch.randn(C, C, generator=g) * C ** -0.5).to(cuda).bfloat16()
+  out = _lib.selftest_pool(y, Wp)
+  yf = y.float()
+  logits = yf @ Wp.float().t()
+  if L % 2:
+    yf = F.pad(yf, (0, 0, 0, 1))
+    logits = F.pad(logits, (0, 0, 0, 1), value=-torch.finfo(torch.float32).max)
+  w = logits.reshape(S, -1, 2, C).softmax(dim=2)
+  ref = (yf.reshape(S, -1, 2, C) * w).sum(2).reshape(-1, C)
+  assert float((out - ref).abs().max()) < 2e-3
+
+
+def test_relative_position_basis_matches_oracle():
+  from oracle import enformer_shim
+  for n, Fdim in [(2, 192), (2, 48), (4, 96), (7, 192)]:
+    got = _lib.selftest_rel_positions(n, Fdim)
+    ref = enformer_shim.get_positional_embed(n, Fdim)
+    # fp32 torch vs fp64 host evaluation of the gamma log-pdf (lgamma of ~1e3)
+    assert float((got - ref).abs().max()) < 2e-4, (n, Fdim)
+
+
+@pytest.mark.parametrize('n', [1, 2, 4])
+def test_attention_kernel(cuda, n):
+  from oracle import enformer_shim
+  H, dk, dv, rows = 8, 64, 48, 37
+  g = torch.Generator().manual_seed(n)
+  qkv = torch.randn(rows * n, 2 * H * dk + H * dv, generator=g)
+  rcb, rpb = torch.randn(H * dk, generator=g), torch.randn(H * dk, generator=g)
+  relk = torch.randn(H, 2 * n - 1, dk, generator=g) * 0.3
+  got = _lib.selftest_attention(qkv.to(cuda), rcb.to(cuda), rpb.to(cuda), relk.to(cuda), n, H, dk, dv).float().cpu()
+  q = qkv[:, :H * dk].reshape(rows, n, H, dk).permute(0, 2, 1, 3) * dk ** -0.5
+  k = qkv[:, H * dk:2 * H * dk].reshape(rows, n, H, dk).permute(0, 2, 1, 3)
+  v = qkv[:, 2 * H * dk:].reshape(rows, n, H, dv).permute(0, 2, 1, 3)
+  content = torch.einsum('bhid,bhjd->bhij', q + rcb.reshape(1, H, 1, dk), k)
+  rel = enformer_shim.relative_shift(torch.einsum('bhid,hjd->bhij', q + rpb.reshape(1, H, 1, dk), relk))
+  out = torch.einsum('bhij,bhjd->bhid', (content + rel).softmax(-1), v)
+  ref = out.permute(0, 2, 1, 3).reshape(rows * n, H * dv)
+  assert float((got - ref).abs().max()) < 0.02 * float(ref.abs().max())

@@ -1,0 +1,158 @@
+"""-m gpu: the tensor-core networks (through the C ABI) against the reference
+goldens (fp32) and the oracle's bf16-operand emulation.
+
+Stated tolerances (north_star: "network logits and values agree within a stated
+bf16/fp32 tolerance"):
+  * vs the oracle with bf16-rounded GEMM operands (same rounding points, fp32
+    accumulate): max |d| <= TIGHT * scale  -- catches semantic errors;
+  * vs the reference's fp32 output: max |d| <= LOOSE * scale -- the bf16 budget.
+scale = max |reference output| over the batch."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import nets, svdd
+from svdd_b200 import _lib, value_nets
+
+pytestmark = pytest.mark.gpu
+
+TIGHT, LOOSE = 4e-3, 3e-2
+# value nets: random-init nets emit near-constant scores much smaller than their
+# internal activations (O(1)), so the error is stated as absolute for |v| <= 1 and
+# relative beyond: |d| <= tol * max(1, max|v|).
+V_TIGHT, V_LOOSE = 2e-3, 1e-2
+
+
+def T(a):
+  return torch.from_numpy(np.asarray(a))
+
+
+def _report(name, got, emu, ref, floor=0.0):
+  scale = max(float(ref.abs().max()), floor)
+  e_emu = float((got - emu).abs().max()) / scale
+  e_ref = float((got - ref).abs().max()) / scale
+  print(f'\n[{name}] scale={scale:.4g} rel.err vs bf16-emulating oracle={e_emu:.3e} vs fp32 reference={e_ref:.3e}')
+  return e_emu, e_ref
+
+
+@pytest.mark.parametrize('L', [50, 200])
+@pytest.mark.parametrize('tok_dtype', [torch.int64, torch.uint8])
+def test_denoiser_logits(cuda, L, tok_dtype):
+  g = helpers.load_golden('denoiser_seed44.npz')
+  m = helpers.build_denoiser(44, L)
+  sd = {'backbone.' + k: v for k, v in m.state_dict().items()}
+  x = T(g[f'L{L}_tokens'])
+  ref = T(g[f'L{L}_logits'])
+  with torch.no_grad():
+    emu = nets.denoiser_logits(sd, x, emulate_bf16=True)
+  m = m.to(cuda)
+  got = m.packed().forward(x.to(cuda).to(tok_dtype), 0.0).cpu()
+  e_emu, e_ref = _report(f'denoiser L={L}', got, emu, ref)
+  assert e_emu < TIGHT and e_ref < LOOSE
+  # the distribution the sampler sees: max |d log p| over real tokens of masked rows
+  lp_got = svdd.subs_parameterization(got, x)[x == 4][:, :4]
+  lp_ref = T(g[f'L{L}_log_p'])[x == 4][:, :4]
+  assert float((lp_got - lp_ref).abs().max()) < 0.05
+  # argmax tokens (noise removal / Tweedie) agree except where the top-2 gap is tiny
+  a_got = _lib.x0_argmax(got.to(cuda), x.to(cuda)).cpu()
+  a_ref = svdd.subs_parameterization(ref, x)[:, :, :4].argmax(-1)
+  gap = svdd.subs_parameterization(ref, x)[:, :, :4].topk(2, -1).values
+  bad = a_got != a_ref
+  assert float((gap[..., 0] - gap[..., 1])[bad].max() if bad.any() else 0.0) < 0.05
+
+
+def test_denoiser_batch_shapes(cuda):
+  """Ragged batch sizes (tiles that straddle sequences / partial last tile) give
+  the same per-sequence logits as a batch of one."""
+  for L in (50, 200):
+    m = helpers.build_denoiser(44, L).to(cuda)
+    x = helpers.random_tokens(7, L, 3, 0.6).to(cuda)
+    full = m.packed().forward(x, 0.0)
+    for n in (1, 2, 5):
+      part = m.packed().forward(x[:n].contiguous(), 0.0)
+      assert torch.equal(part, full[:n]), (L, n)
+
+
+def test_convgru_value(cuda):
+  g = helpers.load_golden('value_nets.npz')
+  tok = T(g['convgru_tokens'])
+  oh = svdd.transform_samples(tok).float()
+  for name, build, key, tr in (('value', helpers.build_convgru_value, 'convgru_values', False),
+                               ('oracle', helpers.build_convgru_oracle, 'rnaoracle_values', True)):
+    emb, head = build()
+    inp = oh.transpose(1, 2) if tr else oh
+    with torch.no_grad():
+      emu = nets.convgru_value(emb.state_dict(), head.state_dict(), inp, emulate_bf16=True).reshape(-1)
+    ref = T(g[key])
+    emb, head = emb.to(cuda), head.to(cuda)
+    got = value_nets.score_tokens(emb, head, tok.to(cuda)).cpu()
+    e_emu, e_ref = _report(f'convgru {name}', got, emu, ref, floor=1.0)
+    assert e_emu < V_TIGHT and e_ref < V_LOOSE
+    got8 = value_nets.score_tokens(emb, head, tok.to(cuda).to(torch.uint8)).cpu()
+    assert torch.equal(got8, got)
+
+
+def test_convgru_many_rows(cuda):
+  """More rows than one chunk / one GRU block: per-row results do not depend on
+  batch composition."""
+  emb, head = helpers.build_convgru_value()
+  emb, head = emb.to(cuda), head.to(cuda)
+  tok = helpers.random_tokens(1000, 50, 21, 0.5).to(cuda)
+  full = value_nets.score_tokens(emb, head, tok)
+  part = value_nets.score_tokens(emb, head, tok[137:150].contiguous())
+  assert torch.allclose(part, full[137:150], rtol=0, atol=1e-6)
+  assert torch.isfinite(full).all()
+
+
+def test_enformer_value(cuda):
+  g = helpers.load_golden('value_nets.npz')
+  tok = T(g['enformer_tokens'])
+  oh = svdd.transform_samples(tok).float()
+  emb, head = helpers.build_enformer()
+  with torch.no_grad():
+    emu = nets.enformer_value(emb.state_dict(), head.state_dict(), oh, n_heads=8,
+                              emulate_bf16=True).reshape(-1)
+  ref = T(g['enformer_values'])
+  emb, head = emb.to(cuda), head.to(cuda)
+  got = value_nets.score_tokens(emb, head, tok.to(cuda)).cpu()
+  print('\n got', got.numpy(), '\n emu', emu.numpy(), '\n ref', ref.numpy())
+  # The trunk is ~45 bf16-operand layers deep; with calibrated BatchNorm the rounding
+  # noise reaches ~0.7% of the activation scale at the trunk output (measured stage by
+  # stage with tools/debug_enformer.py: the kernels track the fp32 reference slightly
+  # BETTER than the CPU bf16 emulation does, and no stage shows a jump).  Stated
+  # tolerance: 10% of the score spread over the batch, against both targets.
+  spread = float(ref.max() - ref.min())
+  e_emu, e_ref = _report('enformer (384ch, 2 blocks)', got, emu, ref, floor=spread)
+  assert e_emu < 0.1 and e_ref < 0.1
+  assert torch.equal(got.argsort(), ref.argsort())
+  got8 = value_nets.score_tokens(emb, head, tok.to(cuda).to(torch.uint8)).cpu()
+  assert torch.equal(got8, got)
+
+
+def test_enformer_batch_independence(cuda):
+  emb, head = helpers.build_enformer()
+  emb, head = emb.to(cuda), head.to(cuda)
+  tok = helpers.random_tokens(70, 200, 33, 0.5).to(cuda)
+  full = value_nets.score_tokens(emb, head, tok)
+  part = value_nets.score_tokens(emb, head, tok[11:14].contiguous())
+  assert torch.allclose(part, full[11:14], rtol=0, atol=1e-5)
+  assert torch.isfinite(full).all()
+
+
+def test_value_rank_agreement(cuda):
+  """What selection needs: the candidate the fp32 oracle prefers is (nearly always)
+  the one the bf16 tensor-core net prefers.  Reported, with a weak bound."""
+  emb, head = helpers.build_convgru_value()
+  x = helpers.random_tokens(64, 50, 5, 0.5)
+  cand = torch.stack([torch.where(x == 4, torch.randint(0, 5, x.shape,
+                      generator=torch.Generator().manual_seed(m)), x) for m in range(10)])
+  with torch.no_grad():
+    ref = nets.convgru_value(emb.state_dict(), head.state_dict(),
+                             svdd.transform_samples(cand.reshape(-1, 50)).float()).reshape(10, 64)
+  got = value_nets.score_tokens(emb.to(cuda), head.to(cuda), cand.reshape(-1, 50).to(cuda)).cpu().reshape(10, 64)
+  agree = float((got.argmax(0) == ref.argmax(0)).float().mean())
+  regret = float((ref.max(0).values - ref.gather(0, got.argmax(0)[None])[0]).max())
+  spread = float((ref.max(0).values - ref.min(0).values).mean())
+  print(f'\n[rank] argmax agreement={agree:.3f} worst regret={regret:.2e} mean spread={spread:.2e}')
+  assert agree >= 0.8 and regret <= 0.25 * spread
