@@ -1,0 +1,349 @@
+"""bench.py -- SVDD decoding throughput on B200 (the metric of BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One bench "step" = one complete SVDD-MC decode of one batch through the hot path:
+128 reverse steps (denoiser -> fused SUBS/Gumbel draw of M candidates -> value net on
+all B*M candidates -> select+gather) plus the noise-removal forward, i.e. one call of
+``Diffusion.controlled_sample``.  Workload = BASELINE.json configs[1]: DNA enhancer
+HepG2 SVDD-MC, L=200, M=10, batch 128 per GPU, random-init CNN denoiser and
+Enformer-style value net, synthetic (all-mask prior + counter-based noise).
+
+  value     decoded sequences / s, device-timed (CUDA events) over K replays of the
+            captured trajectory, state resident in HBM; max over ranks; whole-job
+            aggregate (weak scaling: every GPU decodes its own 128-sequence shard,
+            no data-path collective; the only exchange is the final NCCL all_gather of
+            the tokens, which is inside the timed region).
+  e2e       the same metric through the public API with HOST buffers: the start state
+            is copied from pinned host memory and the decoded tokens are read back to
+            host every step; wall clock with synchronisation on both sides.
+  roofline  the tensor-core GEMM kernel (conv_gemm_kernel, >95% of the step): summed
+            nominal dense FLOPs / summed CUDA-event launch time of one instrumented
+            value-net + denoiser pass, against the MEASURED sustained bf16 peak.
+  cpu_baseline  the CPU oracle (a port of the reference's algorithm, oracle/) timed on
+            this box's host cores on a bounded sample; reported, not a target.
+
+--impl reference times that CPU port alone (the reference itself is Python that cannot
+travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+WORKLOAD = ('c2: DNA enhancer HepG2 SVDD-MC (decode.py --task dna --sample_M 10), L=200, M=10, '
+            'batch 128 per GPU, 128 denoise steps + noise removal, random-init CNN denoiser + '
+            'Enformer-style value net (7 conv / 1536 ch / 11 transformer blocks)')
+B_PER_GPU, M, L, NUM_STEPS = 128, 10, 200, 128
+F_DEN = 2 * L * (5 * 128 * 9 + 20 * 128 * 128 * 9 + 128 * 128 + 128 * 5)
+F_VAL = 3.362e9
+
+
+def peaks():
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+      p = json.load(f)
+    return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'],
+                src='measured (MEASURED_PEAKS.json)')
+  except Exception:
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+  """nvidia-smi sampling of SM clocks / throttle reasons during the timed region."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.idx, self.proc, self.path = gpu_index, None, None
+
+  def start(self):
+    try:
+      fd, self.path = tempfile.mkstemp(suffix='.csv')
+      os.close(fd)
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+           '-i', str(self.idx)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons, power = [], [], set(), []
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    try:
+      for line in open(self.path):
+        f = [x.strip() for x in line.split(',')]
+        if len(f) < 9:
+          continue
+        sm.append(float(f[1])); mx.append(float(f[2]))
+        try:
+          power.append(float(f[3]))
+        except ValueError:
+          pass
+        for n, v in zip(names, f[5:9]):
+          if v.lower().startswith('active'):
+            reasons.add(n)
+      os.unlink(self.path)
+    except Exception:
+      pass
+    if sm:
+      out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                 samples=len(sm), power_w_max=max(power) if power else None)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+def build_models(device, seed=44):
+  import helpers
+  from svdd_b200 import config, diffusion_gosai, value_nets
+  cfg = config.load_config('dna')
+  torch.manual_seed(seed)                       # decode.py's default --seed
+  model = diffusion_gosai.Diffusion(cfg).eval()
+  emb = value_nets.EnformerTrunk(**helpers.ENFORMER_FULL_KW)          # decode.py:78
+  head = value_nets.ConvHead(n_tasks=1, in_channels=2 * 1536, act_func=None, pool_func='avg')
+  # zero-initialised attention output projections would make the attention path vacuous
+  helpers.perturb_(emb, 9)
+  return cfg, model.to(device), emb.to(device).eval(), head.to(device).eval()
+
+
+def cpu_port_sample(cfg_model, emb, head, n_seq=2, n_steps=2, threads=None):
+  """Times the CPU oracle (port of the reference) on a bounded sample of the workload:
+  n_steps reverse SVDD-MC steps for n_seq sequences x M candidates, full-size networks.
+  Returns (decoded seq/s extrapolated to 128 steps + noise removal, description, cores)."""
+  from oracle import nets, svdd
+  threads = threads or os.cpu_count()
+  torch.set_num_threads(threads)
+  sd = {'backbone.' + k: v.detach().float().cpu() for k, v in cfg_model.backbone.state_dict().items()}
+  esd = {k: v.detach().float().cpu() for k, v in emb.state_dict().items()}
+  hsd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+  denoiser = lambda x: nets.denoiser_logits(sd, x)
+  value = lambda tok: nets.enformer_value(esd, hsd, svdd.transform_samples(tok).float()).reshape(-1)
+  sched, _ = svdd.move_chances(NUM_STEPS, 1e-5)
+  x = torch.full((n_seq, L), 4, dtype=torch.int64)
+  g = torch.Generator().manual_seed(0)
+  with torch.no_grad():
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+      U = torch.rand(M, n_seq, L, 5, generator=g)
+      x = svdd.step_mc(denoiser, value, x, float(sched[i, 0]), float(sched[i, 1]), U)
+    t_step = (time.perf_counter() - t0) / n_steps
+    t0 = time.perf_counter()
+    svdd.noise_removal(denoiser, x)
+    t_den = time.perf_counter() - t0
+  total = t_step * NUM_STEPS + t_den
+  desc = (f'{n_steps} reverse steps of the workload for {n_seq} sequences x M={M} candidates '
+          f'(full-size nets, torch CPU fp32, {threads} threads): {t_step:.2f} s/step; extrapolated '
+          f'x{NUM_STEPS} steps + 1 denoiser forward = {total:.1f} s per {n_seq} sequences')
+  return n_seq / total, desc, threads, t_step
+
+
+def run_reference(args, rank, world):
+  """--impl reference: the reference's CPU implementation of the path.  The reference is
+  Python/PyTorch that cannot travel to the GPU box, so this is its port (oracle/)."""
+  if rank != 0:
+    return
+  cfg, model, emb, head = build_models(torch.device('cpu'))
+  vals, desc, cores, t_steps = [], '', 0, []
+  for i in range(args.warmup + args.steps):
+    v, desc, cores, t_step = cpu_port_sample(model, emb, head, n_seq=2, n_steps=1)
+    if i >= args.warmup:
+      vals.append(v)
+      t_steps.append(t_step)
+  value = statistics.mean(vals)
+  print(json.dumps({
+      'impl': 'reference', 'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s',
+      'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': 1000.0 * 2 / value, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'B_per_gpu': B_PER_GPU, 'M': M, 'L': L,
+                 'denoise_steps': NUM_STEPS},
+      'cpu_baseline': {'value': value, 'unit': 'seq/s', 'cores': cores, 'kind': 'port',
+                       'sample': desc},
+      'e2e': {'value': value, 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'ms_per_denoise_step_cpu_sample': 1000.0 * statistics.mean(t_steps)}))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  rank = int(os.environ.get('RANK', 0))
+  world = int(os.environ.get('WORLD_SIZE', 1))
+  local = int(os.environ.get('LOCAL_RANK', 0))
+  if args.impl == 'reference':
+    run_reference(args, rank, world)
+    return
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device: svdd_b200 has no CPU path '
+                     '(use --impl reference for the CPU port)')
+  import torch.distributed as dist
+  torch.cuda.set_device(local)
+  device = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=device)
+  assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+
+  from svdd_b200 import _lib
+  cfg, model, emb, head = build_models(device)
+  B = B_PER_GPU
+  row_offset = rank * B
+  gathered = [torch.empty((B, L), dtype=torch.int64, device=device) for _ in range(world)]
+
+  def one_run(x_init=None):
+    x = model.controlled_sample(emb, head, eval_sp_size=B, sample_M=M, row_offset=row_offset,
+                                x_init=x_init)
+    if world > 1:
+      dist.all_gather(gathered, x)       # the path's only exchange: final gather of sequences
+    return x
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(args.warmup):            # includes graph capture
+    x = one_run()
+  barrier()
+  assert x.shape == (B, L) and int(x.max()) <= 3 and int(x.min()) >= 0
+  launches_per_run = int(getattr(model, 'launches_per_trajectory', 0))
+
+  # ---- device-timed region -----------------------------------------------------------------
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    one_run()
+  e1.record()
+  barrier()
+  dev_ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+  if world > 1:
+    dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
+  ms_per_step = float(dev_ms) / args.steps
+  value = world * B / (ms_per_step / 1000.0)
+
+  # ---- end to end through the public API with host buffers ------------------------------------
+  host_in = torch.full((B, L), 4, dtype=torch.int64).pin_memory()
+  host_out = torch.empty((B, L), dtype=torch.int64).pin_memory()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    x_dev = host_in.to(device, non_blocking=True)
+    x = one_run(x_init=x_dev)
+    host_out.copy_(x, non_blocking=True)
+    torch.cuda.synchronize()
+  barrier()
+  e2e_s = torch.tensor([time.perf_counter() - t0], device=device)
+  if world > 1:
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  e2e_value = world * B * args.steps / float(e2e_s)
+  clocks = sampler.stop() if rank == 0 else {}
+
+  # ---- roofline leg: one instrumented eager pass of the dominant kernel family -----------------
+  roofline, stage_rooflines = None, {}
+  if rank == 0:
+    pk = peaks()
+    cand = torch.randint(0, 4, (M * B, L), device=device, dtype=torch.uint8)
+    from svdd_b200 import value_nets
+    scorer = value_nets.packed_scorer(emb, head)
+    den = model.backbone.packed()
+    scorer.score(cand); den.forward(cand[:B], 0.0)
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    scorer.score(cand)
+    den.forward(cand[:B], 0.0)
+    torch.cuda.synchronize()
+    gemm_ms, gemm_n, gemm_flops = _lib.profile_end()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    step_ms = ms_per_step / NUM_STEPS       # one reverse step (the +1 denoiser forward is <0.1%)
+    roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one '
+                'reverse step: value net on B*M candidates + denoiser on B',
+                'achieved': achieved, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tf_sust'], 'traffic': None, 'peak_source': pk['src'] + ', sustained',
+                'launches': gemm_n, 'flops_per_step': gemm_flops, 'gemm_ms_per_step': gemm_ms,
+                'share_of_step': gemm_ms / step_ms if step_ms > 0 else None}
+    # HBM-bound stages at the per-GPU size of BASELINE config 4 (B=4096/8, M=20): algorithmic bytes
+    sched_mc = (0.5, 0.49)
+    Bc, Mc = 512, 20
+    lg = torch.randn(Bc, L, 5, device=device)
+    xs = torch.full((Bc, L), 4, dtype=torch.int64, device=device)
+    U = torch.rand(Mc, Bc, L, 5, device=device)
+    sc = torch.randn(Mc, Bc, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def timed(fn, reps=10):
+      ts = []
+      for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+      return statistics.median(ts)
+    cand64 = _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U)
+    t2 = timed(lambda: _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U, out=cand64))
+    bytes2 = Bc * L * (28 + 28 * Mc)
+    t4 = timed(lambda: _lib.select_gather(sc, cand64))
+    bytes4 = Bc * (4 * Mc + 16 * L)
+    for name, t, nb in (('stage2_subs_sample', t2, bytes2), ('stage4_select_gather', t4, bytes4)):
+      ach = nb / (t * 1e-3) / 1e9
+      stage_rooflines[name] = {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
+                               'frac': ach / pk['hbm'], 'algorithmic_bytes': nb, 'ms': t,
+                               'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 flushed'}
+    del flush, U, lg
+
+  # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    v, desc, cores, _ = cpu_port_sample(model, emb, head, n_seq=4, n_steps=3)
+    cpu = {'value': v, 'unit': 'seq/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+
+  if rank == 0:
+    print(json.dumps({
+        'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'B_per_gpu': B, 'global_batch': B * world, 'M': M, 'L': L,
+                   'denoise_steps': NUM_STEPS, 'parallelism': f'batch-sharded x{world}',
+                   'l2': 'per-step working set (0.5 GB bf16 weights + >1 GB activations) >> 126 MB L2; no flush',
+                   'noise': 'in-kernel Philox4x32-10', 'cuda_graph': bool(model.use_cuda_graph)},
+        'ms_per_denoise_step': ms_per_step / NUM_STEPS,
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'seq/s', 'h2d_bytes_per_step': B * L * 8,
+                'd2h_bytes_per_step': B * L * 8},
+        'gpu_launches': launches_per_run * args.steps,
+        'roofline': roofline, 'stage_rooflines': stage_rooflines, 'cpu_baseline': cpu}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -69,6 +69,13 @@ int svdd_device_check(int device);
  * bench.py reports the delta over the timed region as "gpu_launches". */
 int64_t svdd_launch_count(void);
 
+/* Per-launch CUDA-event timing of the tensor-core GEMM kernel (measurement aid for
+ * bench.py's roofline leg; adds two event records per launch, so it is only
+ * enabled around a dedicated pass).  svdd_profile_end returns the summed device
+ * time, the number of launches and their nominal dense FLOPs. */
+int svdd_profile_begin(void);
+int svdd_profile_end(double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+
 /* ---- stage 2: SUBS + move-chance mixing + Gumbel-max draw + carry-over ----
  * Replaces, fused into one kernel:
  *   Diffusion._subs_parameterization          diffusion_gosai.py:286-304

@@ -95,6 +95,17 @@ def launch_count():
   return int(lib().svdd_launch_count())
 
 
+def profile_begin():
+  check(lib().svdd_profile_begin())
+
+
+def profile_end():
+  """-> (ms summed over conv_gemm launches, number of launches, nominal dense FLOPs)."""
+  ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+  check(lib().svdd_profile_end(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+  return ms.value, n.value, fl.value
+
+
 def _stream():
   return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -3,6 +3,8 @@
 #include <mutex>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "conv_gemm.cuh"
 
 namespace svdd {
@@ -47,6 +49,18 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64
   return SVDD_OK;
 }
 
+// ---- optional per-launch timing (bench.py's roofline leg; off on the hot path) --------
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // start/stop pairs
+  double flops = 0.0;
+  std::mutex mu;
+};
+ProfState& prof() {
+  static ProfState p;
+  return p;
+}
+
 template <int BN, int MODE>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& g,
                 const EpiParams& ep, cudaStream_t stream) {
@@ -60,9 +74,24 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape&
   const int64_t tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS) * (g.N / BN);
   if (tiles == 0) return SVDD_OK;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  ProfState& P = prof();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (P.on) {
+    SVDD_CUDA(cudaEventCreate(&e0));
+    SVDD_CUDA(cudaEventCreate(&e1));
+    SVDD_CUDA(cudaEventRecord(e0, stream));
+  }
   kern<<<grid, gemm_detail::kThreads, C::kSmemBytes, stream>>>(tmA, tmW, g, ep);
   count_launch();
   SVDD_LAUNCH_CHECK();
+  if (P.on) {
+    SVDD_CUDA(cudaEventRecord(e1, stream));
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.ev.push_back(e0);
+    P.ev.push_back(e1);
+    // nominal dense count (padding taps included), the figure SURVEY.md section 8(d) uses
+    P.flops += 2.0 * (double)g.S * g.L * (C::kAcc) * (double)g.N * g.K * g.taps;
+  }
   return SVDD_OK;
 }
 
@@ -147,6 +176,37 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   return SVDD_ERR_INTERNAL;
 }
 
+}  // namespace svdd
+
+extern "C" int svdd_profile_begin(void) {
+  svdd::ProfState& P = svdd::prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (cudaEvent_t e : P.ev) cudaEventDestroy(e);
+  P.ev.clear();
+  P.flops = 0.0;
+  P.on = true;
+  return SVDD_OK;
+}
+
+extern "C" int svdd_profile_end(double* gemm_ms, int64_t* gemm_launches, double* gemm_flops) {
+  svdd::ProfState& P = svdd::prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.on = false;
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < P.ev.size(); i += 2) {
+    if (cudaEventSynchronize(P.ev[i + 1]) != cudaSuccess) break;
+    float t = 0.0f;
+    if (cudaEventElapsedTime(&t, P.ev[i], P.ev[i + 1]) == cudaSuccess) ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_launches) *gemm_launches = (int64_t)(P.ev.size() / 2);
+  if (gemm_flops) *gemm_flops = P.flops;
+  for (cudaEvent_t e : P.ev) cudaEventDestroy(e);
+  P.ev.clear();
+  return SVDD_OK;
+}
+
+namespace svdd {
 // ---- plain CUDA-core reference of the same contraction (self test only) ----------
 namespace {
 __global__ void naive_conv_gemm_kernel(const __nv_bfloat16* __restrict__ A,

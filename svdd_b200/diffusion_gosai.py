@@ -225,7 +225,8 @@ class Diffusion(nn.Module):
     return int(B), int(num_steps)
 
   def _trajectory(self, mode, B, num_steps, eps, M=1, scorer=None, tweedie=True, alpha=0.0,
-                  noise=None, row_offset=0, collect_mid=False, seed=None, trace=None):
+                  noise=None, row_offset=0, collect_mid=False, seed=None, trace=None,
+                  x_init=None):
     """Runs num_steps reverse steps (+ noise removal) for B sequences on this GPU.
 
     mode 'plain' (A18), 'mc' (A1/SVDD-MC) or 'pm' (SVDD-PM).  Returns the uint8 token
@@ -256,6 +257,8 @@ class Diffusion(nn.Module):
     if mode == 'pm' and tweedie:
       buf['logits2'] = torch.empty((M * B, L, 5), dtype=torch.float32, device=dev)
       buf['x0'] = torch.empty((M * B, L), dtype=u8, device=dev)
+    if x_init is not None:       # start from caller-supplied tokens instead of the all-mask prior
+      buf['x'].copy_(x_init.to(dev).reshape(B, L))
     mids = []
 
     def step(i):
@@ -306,10 +309,10 @@ class Diffusion(nn.Module):
       result = finish()
       return (result, mids) if collect_mid else result
     return self._graph_trajectory(mode, B, num_steps, eps, M, scorer, tweedie, alpha,
-                                  row_offset, seed, buf, step, finish)
+                                  row_offset, seed, buf, step, finish, x_init)
 
   def _graph_trajectory(self, mode, B, num_steps, eps, M, scorer, tweedie, alpha, row_offset,
-                        seed, buf, step, finish):
+                        seed, buf, step, finish, x_init=None):
     """Captures the whole trajectory once per configuration and replays it.  The
     per-run Philox key lives in device memory (`seed_dev`), so replays draw fresh
     noise without re-capturing."""
@@ -320,6 +323,12 @@ class Diffusion(nn.Module):
       # int64 view of the unsigned 64-bit run key
       self._seed_dev.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
 
+    def reset_state(b):
+      if x_init is None:
+        b['x'].fill_(self.mask_index)
+      else:
+        b['x'].copy_(x_init.to(b['x'].device).reshape(b['x'].shape))
+
     if entry is None:
       # One eager pass sizes every workspace / lazy table outside the capture.
       set_seed()
@@ -327,19 +336,21 @@ class Diffusion(nn.Module):
         step(i)
       finish()
       torch.cuda.synchronize()
-      buf['x'].fill_(self.mask_index)
+      reset_state(buf)
+      before = _lib.launch_count()
       graph = torch.cuda.CUDAGraph()
       with torch.cuda.graph(graph):
         for i in range(num_steps):
           step(i)
         result = finish()
+      self.launches_per_trajectory = _lib.launch_count() - before
       entry = (graph, buf, result)
       if len(self._graphs) > 8:
         self._graphs.clear()
       self._graphs[key] = entry
     graph, gbuf, result = entry
     set_seed()
-    gbuf['x'].fill_(self.mask_index)
+    reset_state(gbuf)
     graph.replay()
     return result.clone()
 
@@ -365,13 +376,13 @@ class Diffusion(nn.Module):
   @torch.no_grad()
   def controlled_sample(self, pre_scorer_embedding, pre_scorer_head, num_steps=None, eps=1e-5,
                         eval_sp_size=None, sample_M=10, alpha=0.0, noise=None, row_offset=0,
-                        trace=None):
+                        trace=None, x_init=None):
     """SVDD-MC (diffusion_gosai.py:1022-1061).  ``alpha``/``noise``/``row_offset``/``trace``
     are additions: alpha=0 is the reference's argmax selection."""
     B, num_steps = self._resolve(num_steps, eval_sp_size)
     scorer = _as_scorer(pre_scorer_embedding, pre_scorer_head)
     return self._trajectory('mc', B, num_steps, eps, M=int(sample_M), scorer=scorer, alpha=alpha,
-                            noise=noise, row_offset=row_offset, trace=trace).long()
+                            noise=noise, row_offset=row_offset, trace=trace, x_init=x_init).long()
 
   @torch.no_grad()
   def controlled_sample_tweedie(self, reward_model, num_steps=None, eps=1e-5, eval_sp_size=None,
