@@ -112,7 +112,7 @@ int pick_bn(const GemmShape& g, int mode) {
 
 }  // namespace
 
-int conv_gemm_n_tiles(const GemmShape& g, int mode) { return g.N / pick_bn(g, mode); }
+int conv_gemm_n_tiles(const GemmShape& g, int mode) { return 2 * (g.N / pick_bn(g, mode)); }
 
 void choose_row_tiling(int L, int taps, GemmShape* g) {
   (void)taps;

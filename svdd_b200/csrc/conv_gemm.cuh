@@ -6,7 +6,7 @@
 // W   : bf16 weights, tap-major [T*N, K]              (K contiguous)
 // acc : fp32 in tensor memory
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer: per (tap, 64-wide K block) one 3-D box of A
 //               (64 ch x BL positions x BS sequences, out-of-range positions are
 //               zero-filled by TMA = the conv's zero padding) and one 2-D box of W,
@@ -15,10 +15,13 @@
 //               (M=128, N=BN, K=16) per stage into a double-buffered TMEM
 //               accumulator, tcgen05.commit releases the smem slot / signals the
 //               epilogue;
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time (thread =
-//               output row, so per-row reductions such as LayerNorm are
-//               thread-local), fused bias / BN-affine / activation / residual /
-//               LayerNorm / attention-pool / head-dot, vectorised global stores.
+//   warps 2-9   epilogue: thread = (output row, column half); tcgen05.ld 32 lanes x
+//               32 columns at a time, software-pipelined against the math; the
+//               per-column vectors of the tile (bias, BN scale/shift, head weights)
+//               are staged in shared memory once per tile; fused bias / BN-affine /
+//               activation / residual / LayerNorm (row partials exchanged between
+//               the two halves through smem) / attention-pool / head-dot,
+//               vectorised global stores.
 // Taps whose whole A tile falls in the zero padding are skipped by both the
 // producer and the issuer (dilation-64 taps on 200-long sequences).
 #pragma once
@@ -61,7 +64,7 @@ struct EpiParams {
   const float* b2 = nullptr;
   // EPI_POOL: values being pooled (bf16 [S*L_in, N])
   const void* pool_vals = nullptr;
-  // EPI_HEADDOT: partials[r, n_tile] = sum_{n in tile} v[n] * head_w[n]
+  // EPI_HEADDOT: partials[r, 2*n_tile + half] = sum_{n in that half tile} v[n] * head_w[n]
   const float* head_w = nullptr;
   float* partials = nullptr;
 };
@@ -79,8 +82,13 @@ namespace gemm_detail {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quadrant (column halves)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;         // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int kSmemBudget = 196 * 1024;            // operand ring
+constexpr int kParamVecs = 6;                      // bias, scale, shift, scale2, shift2, head_w per tile
+enum ParamSlot { P_BIAS = 0, P_SCALE = 1, P_SHIFT = 2, P_SCALE2 = 3, P_SHIFT2 = 4, P_HEADW = 5,
+                 P_LN_TBIAS = 1, P_LN_GAMMA = 2, P_LN_BETA = 3 };
 
 template <int BN, int MODE>
 struct Cfg {
@@ -93,21 +101,33 @@ struct Cfg {
   static constexpr int kTmemColsRaw = 2 * kAcc * BN;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64
                                    : kTmemColsRaw <= 128 ? 128 : kTmemColsRaw <= 256 ? 256 : 512;
-  static constexpr int kExtraBytes = (MODE == EPI_DEN_FINAL) ? (kVocab * 128 + 8) * 4 : 0;
+  static constexpr int kHalf = BN / 2;             // columns per epilogue thread
+  static constexpr int kChunks = kHalf / 32;       // tcgen05.ld 32x32b.x32 per thread per accumulator
+  static constexpr int kParamBytes = 2 * kParamVecs * BN * 4;          // double-buffered per tile
+  static constexpr int kXchBytes = 2 * kBM * 8 * 4;                    // half <-> half exchange
+  static constexpr int kW2Bytes = (MODE == EPI_DEN_FINAL) ? (kVocab * 128 + 8) * 4 : 0;
+  static constexpr int kExtraBytes = kParamBytes + kXchBytes + kW2Bytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kTmemColsRaw <= 512, "accumulators exceed tensor memory");
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "N tile must be 64, 128 or 256");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
+
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_GELU) return v / (1.0f + __expf(-1.702f * v));  // x * sigmoid(1.702 x)
+  if (act == ACT_GELU) return v * fast_rcp(1.0f + __expf(-1.702f * v));  // x * sigmoid(1.702 x)
   return v;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 // store / load 32 consecutive channels of one row
@@ -147,6 +167,15 @@ __device__ __forceinline__ void load_row32(const void* base, int dtype, int64_t 
     }
   }
 }
+// 32 consecutive per-column parameters from shared memory (warp-uniform address -> broadcast)
+__device__ __forceinline__ void load_param32(const float* p, float* v) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 f = q[i];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -155,10 +184,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using C = Cfg<BN, MODE>;
   constexpr int kStages = C::kStages;
   constexpr int kAcc = C::kAcc;
+  constexpr int kHalf = C::kHalf;
+  constexpr int kChunks = C::kChunks;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   uint8_t* extra = smem + kStages * C::kStageBytes;
+  float* s_param = reinterpret_cast<float*>(extra);                                  // [2][kParamVecs][BN]
+  float* s_xch = reinterpret_cast<float*>(extra + C::kParamBytes);                   // [2][128][8]
+  float* s_w2 = reinterpret_cast<float*>(extra + C::kParamBytes + C::kXchBytes);     // DEN_FINAL only
   uint64_t* bars = reinterpret_cast<uint64_t*>(extra + C::kExtraBytes);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
@@ -186,7 +220,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull_bar[i], 1);
-        ptx::mbar_init(&tempty_bar[i], 4);
+        ptx::mbar_init(&tempty_bar[i], kEpiWarps);
       }
       ptx::fence_barrier_init();
     }
@@ -195,9 +229,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::tmem_relinquish();
   }
   if constexpr (MODE == EPI_DEN_FINAL) {
-    float* w2s = reinterpret_cast<float*>(extra);
-    for (int i = threadIdx.x; i < kVocab * 128; i += kThreads) w2s[i] = ep.w2[i];
-    if (threadIdx.x < kVocab) w2s[kVocab * 128 + threadIdx.x] = ep.b2[threadIdx.x];
+    for (int i = threadIdx.x; i < kVocab * 128; i += kThreads) s_w2[i] = ep.w2[i];
+    if (threadIdx.x < kVocab) s_w2[kVocab * 128 + threadIdx.x] = ep.b2[threadIdx.x];
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -288,9 +321,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row of the tile owned by this thread
+    // ===================== epilogue: 8 warps, thread = (row, column half) =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;            // which half of the tile's columns
+    const int etid = threadIdx.x - 64;
+    const int r = quad * 32 + lane;      // row of the tile owned by this thread
+    float* xch_mine = s_xch + (half * kBM + r) * 8;
+    const float* xch_other = s_xch + ((half ^ 1) * kBM + r) * 8;
     uint32_t acc_stage = 0, acc_phase = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n0, s0, l0;
@@ -298,35 +336,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int s = s0 + r / g.BL, l = l0 + r % g.BL;
       const bool valid = (r < g.BL * g.BS) && (s < g.S) && (l < g.L);
       const int64_t row = (int64_t)s * g.L + l;
+
+      // per-column parameters of this N tile -> shared memory (double-buffered with the accumulator)
+      float* P = s_param + acc_stage * (kParamVecs * BN);
+      for (int i = etid; i < BN; i += kEpiThreads) {
+        if constexpr (MODE == EPI_DEN_LN) {
+          P[P_BIAS * BN + i] = ep.bias[i];
+          if (ep.ln_enable) {
+            P[P_LN_TBIAS * BN + i] = ep.ln_tbias[i];
+            P[P_LN_GAMMA * BN + i] = ep.ln_gamma[i];
+            P[P_LN_BETA * BN + i] = ep.ln_beta[i];
+          }
+        } else {
+          if (ep.bias) P[P_BIAS * BN + i] = ep.bias[n0 + i];
+          if (ep.scale) { P[P_SCALE * BN + i] = ep.scale[n0 + i]; P[P_SHIFT * BN + i] = ep.shift[n0 + i]; }
+          if (ep.scale2) { P[P_SCALE2 * BN + i] = ep.scale2[n0 + i]; P[P_SHIFT2 * BN + i] = ep.shift2[n0 + i]; }
+          if (MODE == EPI_HEADDOT) P[P_HEADW * BN + i] = ep.head_w[n0 + i];
+        }
+      }
+      epi_bar_sync();
+
       ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * (kAcc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * (kAcc * BN) + half * kHalf;
+      const int cbase = half * kHalf;    // first column (within the tile) of this thread
 
       if constexpr (MODE == EPI_GENERIC || MODE == EPI_POOL || MODE == EPI_HEADDOT) {
         float head_acc = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t raw[32];
+        uint32_t raw[2][32];
+        if constexpr (MODE != EPI_POOL) ptx::tmem_ld_32x32(taddr, raw[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int c0 = cbase + c * 32;   // column within the tile
+          const int n = n0 + c0;           // global column
           float v[32];
-          ptx::tmem_ld_32x32(taddr + c0, raw);
           if constexpr (MODE == EPI_POOL) {
-            uint32_t raw1[32];
-            ptx::tmem_ld_32x32(taddr + BN + c0, raw1);
+            ptx::tmem_ld_32x32(taddr + c * 32, raw[0]);
+            ptx::tmem_ld_32x32(taddr + BN + c * 32, raw[1]);
             ptx::tmem_ld_wait();
             if (valid) {
               const int64_t rin = (int64_t)s * g.L_in + 2 * l;
               const bool has1 = (2 * l + 1) < g.L_in;
               float y0[32], y1[32];
-              load_row32(ep.pool_vals, DT_BF16, rin * g.N + n0 + c0, y0);
-              if (has1) load_row32(ep.pool_vals, DT_BF16, (rin + 1) * g.N + n0 + c0, y1);
+              load_row32(ep.pool_vals, DT_BF16, rin * g.N + n, y0);
+              if (has1) load_row32(ep.pool_vals, DT_BF16, (rin + 1) * g.N + n, y1);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float a0 = __uint_as_float(raw[i]);
+                const float a0 = __uint_as_float(raw[0][i]);
                 if (has1) {
-                  const float a1 = __uint_as_float(raw1[i]);
+                  const float a1 = __uint_as_float(raw[1][i]);
                   const float m = fmaxf(a0, a1);
                   const float e0 = __expf(a0 - m), e1 = __expf(a1 - m);
-                  const float inv = 1.0f / (e0 + e1);
+                  const float inv = fast_rcp(e0 + e1);
                   v[i] = y0[i] * (e0 * inv) + y1[i] * (e1 * inv);
                 } else {
                   v[i] = y0[i];
@@ -335,117 +396,143 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else {
             ptx::tmem_ld_wait();
+            if (c + 1 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
           }
           if (valid) {
-            const int n = n0 + c0;
-            if (MODE != EPI_POOL) {
+            float pv[32];
+            if constexpr (MODE != EPI_POOL) {
               if (ep.scale != nullptr) {
+                float ps[32];
+                load_param32(P + P_SCALE * BN + c0, ps);
+                load_param32(P + P_SHIFT * BN + c0, pv);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = v[i] * __ldg(ep.scale + n + i) + __ldg(ep.shift + n + i);
+                for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
               }
               if (ep.bias != nullptr) {
+                load_param32(P + P_BIAS * BN + c0, pv);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(ep.bias + n + i);
+                for (int i = 0; i < 32; ++i) v[i] += pv[i];
               }
               if (ep.act != ACT_NONE && !ep.act_after_res) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
               }
               if (ep.res != nullptr) {
-                float rr[32];
-                load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, rr);
+                load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, pv);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += rr[i];
+                for (int i = 0; i < 32; ++i) v[i] += pv[i];
               }
               if (ep.act != ACT_NONE && ep.act_after_res) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
               }
             }
-            if (MODE == EPI_HEADDOT) {
+            if constexpr (MODE == EPI_HEADDOT) {
+              load_param32(P + P_HEADW * BN + c0, pv);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) head_acc += v[i] * __ldg(ep.head_w + n + i);
+              for (int i = 0; i < 32; ++i) head_acc += v[i] * pv[i];
             }
             if (ep.out != nullptr) store_row32(ep.out, ep.out_dtype, row * ep.ld_out + n, v);
             if (ep.out2 != nullptr) {
-              float w[32];
+              if (ep.scale2 != nullptr) {
+                float ps[32];
+                load_param32(P + P_SCALE2 * BN + c0, ps);
+                load_param32(P + P_SHIFT2 * BN + c0, pv);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = v[i];
-                if (ep.scale2 != nullptr) x = x * __ldg(ep.scale2 + n + i) + __ldg(ep.shift2 + n + i);
-                w[i] = apply_act(x, ep.act2);
+                for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
               }
-              store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n, w);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act2);
+              store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n, v);
             }
           }
         }
-        if (MODE == EPI_HEADDOT && valid) ep.partials[row * n_tiles + n0 / BN] = head_acc;
+        if (MODE == EPI_HEADDOT && valid)
+          ep.partials[row * (2 * n_tiles) + 2 * (n0 / BN) + half] = head_acc;
       } else if constexpr (MODE == EPI_DEN_LN) {
         // denoiser layer i: feat += relu(conv + bias); h_next = LN_{i+1}(feat + tbias_{i+1})
-        // (models/dnaconv.py:189-200).  BN == N == 128: the whole channel row is in this
-        // thread's TMEM lane.
-        float v[BN];
+        // (models/dnaconv.py:189-200).  BN == N == 128; the two threads that share a row
+        // (column halves) combine their LayerNorm partial sums through shared memory.
+        float v[kHalf];
         float* feat = reinterpret_cast<float*>(ep.out);
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c = 0; c < kChunks; ++c) {
           uint32_t raw[32];
-          ptx::tmem_ld_32x32(taddr + c0, raw);
+          ptx::tmem_ld_32x32(taddr + c * 32, raw);
           ptx::tmem_ld_wait();
-          float rr[32];
-          if (valid) load_row32(feat, DT_F32, row * BN + c0, rr);
+          float rr[32], pb[32];
+          load_param32(P + P_BIAS * BN + cbase + c * 32, pb);
+          if (valid) load_row32(feat, DT_F32, row * BN + cbase + c * 32, rr);
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            v[c0 + i] = valid ? rr[i] + fmaxf(__uint_as_float(raw[i]) + __ldg(ep.bias + c0 + i), 0.0f) : 0.0f;
+            v[c * 32 + i] = valid ? rr[i] + fmaxf(__uint_as_float(raw[i]) + pb[i], 0.0f) : 0.0f;
         }
         if (valid) {
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) store_row32(feat, DT_F32, row * BN + c0, v + c0);
-          if (ep.ln_enable) {
-            float sum = 0.0f;
+          for (int c = 0; c < kChunks; ++c) store_row32(feat, DT_F32, row * BN + cbase + c * 32, v + c * 32);
+        }
+        if (ep.ln_enable) {            // block-uniform
+          float sum = 0.0f;
 #pragma unroll
-            for (int i = 0; i < BN; ++i) {
-              v[i] += __ldg(ep.ln_tbias + i);
-              sum += v[i];
-            }
-            const float mean = sum * (1.0f / BN);
-            float sq = 0.0f;
+          for (int c = 0; c < kChunks; ++c) {
+            float pt[32];
+            load_param32(P + P_LN_TBIAS * BN + cbase + c * 32, pt);
 #pragma unroll
-            for (int i = 0; i < BN; ++i) {
-              const float dlt = v[i] - mean;
-              sq += dlt * dlt;
-            }
-            const float rstd = rsqrtf(sq * (1.0f / BN) + 1e-5f);
-#pragma unroll
-            for (int i = 0; i < BN; ++i)
-              v[i] = (v[i] - mean) * rstd * __ldg(ep.ln_gamma + i) + __ldg(ep.ln_beta + i);
+            for (int i = 0; i < 32; ++i) { v[c * 32 + i] += pt[i]; sum += v[c * 32 + i]; }
           }
+          xch_mine[0] = sum;
+          epi_bar_sync();
+          const float mean = (sum + xch_other[0]) * (1.0f / BN);
+          float sq = 0.0f;
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) store_row32(ep.out2, DT_BF16, row * BN + c0, v + c0);
+          for (int i = 0; i < kHalf; ++i) { const float d = v[i] - mean; sq += d * d; }
+          xch_mine[1] = sq;
+          epi_bar_sync();
+          const float rstd = rsqrtf((sq + xch_other[1]) * (1.0f / BN) + 1e-5f);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            float pg[32], pbt[32];
+            load_param32(P + P_LN_GAMMA * BN + cbase + c * 32, pg);
+            load_param32(P + P_LN_BETA * BN + cbase + c * 32, pbt);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[c * 32 + i] = (v[c * 32 + i] - mean) * rstd * pg[i] + pbt[i];
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c)
+            store_row32(ep.out2, DT_BF16, row * BN + cbase + c * 32, v + c * 32);
         }
       } else if constexpr (MODE == EPI_DEN_FINAL) {
         // final_conv: relu(1x1) then 1x1 to the 5 logits (models/dnaconv.py:163-165,201)
-        const float* w2s = reinterpret_cast<const float*>(extra);
         float lg[kVocab];
 #pragma unroll
-        for (int j = 0; j < kVocab; ++j) lg[j] = w2s[kVocab * 128 + j];
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int j = 0; j < kVocab; ++j) lg[j] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
           uint32_t raw[32];
-          ptx::tmem_ld_32x32(taddr + c0, raw);
+          ptx::tmem_ld_32x32(taddr + c * 32, raw);
           ptx::tmem_ld_wait();
+          float pb[32];
+          load_param32(P + P_BIAS * BN + cbase + c * 32, pb);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float y = fmaxf(__uint_as_float(raw[i]) + __ldg(ep.bias + c0 + i), 0.0f);
+            const float y = fmaxf(__uint_as_float(raw[i]) + pb[i], 0.0f);
 #pragma unroll
-            for (int j = 0; j < kVocab; ++j) lg[j] += y * w2s[j * 128 + c0 + i];
+            for (int j = 0; j < kVocab; ++j) lg[j] += y * s_w2[j * 128 + cbase + c * 32 + i];
           }
         }
-        if (valid) {
+        if (half == 1) {
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) xch_mine[j] = lg[j];
+        }
+        epi_bar_sync();
+        if (half == 0 && valid) {
           float* o = reinterpret_cast<float*>(ep.out) + row * kVocab;
 #pragma unroll
-          for (int j = 0; j < kVocab; ++j) o[j] = lg[j];
+          for (int j = 0; j < kVocab; ++j) o[j] = lg[j] + xch_other[j] + s_w2[kVocab * 128 + j];
         }
       }
       ptx::tc_fence_before();
@@ -470,8 +557,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int launch_conv_gemm(const void* A, const void* W, const GemmShape& shape, int mode,
                      const EpiParams& ep, cudaStream_t stream);
 
-// Number of N tiles launch_conv_gemm will use for this shape/mode (EPI_HEADDOT writes
-// one partial per row per N tile).
+// Number of partials per row that EPI_HEADDOT writes for this shape (2 per N tile: one per
+// column half).
 int conv_gemm_n_tiles(const GemmShape& shape, int mode);
 
 // Picks (BL, BS) for a conv over sequences of length L: whole-sequence tiles when
