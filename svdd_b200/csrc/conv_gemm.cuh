@@ -113,12 +113,31 @@ struct Cfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_GELU) return v * fast_rcp(1.0f + __expf(-1.702f * v));  // x * sigmoid(1.702 x)
-  return v;
+// single-instruction MUFU approximations (2 ulp): enough for activations that are rounded
+// to bf16 right after
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// enformer GELU: x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 * log2(e) * x))
+__device__ __forceinline__ float gelu_enformer(float v) {
+  return v * fast_rcp(1.0f + fast_ex2(-2.4554669595930157f * v));
+}
+// activation over a 32-column chunk; the kind is tested once per chunk, not per element
+__device__ __forceinline__ void apply_act32(float* v, int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_enformer(v[i]);
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -380,18 +399,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float y0[32], y1[32];
               load_row32(ep.pool_vals, DT_BF16, rin * g.N + n, y0);
               if (has1) load_row32(ep.pool_vals, DT_BF16, (rin + 1) * g.N + n, y1);
+              if (has1) {
+                // softmax over the pair = sigmoid of the logit difference
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float a0 = __uint_as_float(raw[0][i]);
-                if (has1) {
-                  const float a1 = __uint_as_float(raw[1][i]);
-                  const float m = fmaxf(a0, a1);
-                  const float e0 = __expf(a0 - m), e1 = __expf(a1 - m);
-                  const float inv = fast_rcp(e0 + e1);
-                  v[i] = y0[i] * (e0 * inv) + y1[i] * (e1 * inv);
-                } else {
-                  v[i] = y0[i];
+                for (int i = 0; i < 32; ++i) {
+                  const float d = __uint_as_float(raw[1][i]) - __uint_as_float(raw[0][i]);
+                  const float w0 = fast_rcp(1.0f + fast_ex2(1.4426950408889634f * d));
+                  v[i] = y1[i] + w0 * (y0[i] - y1[i]);
                 }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = y0[i];
               }
             }
           } else {
@@ -415,19 +433,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += pv[i];
               }
-              if (ep.act != ACT_NONE && !ep.act_after_res) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
-              }
+              if (!ep.act_after_res) apply_act32(v, ep.act);
               if (ep.res != nullptr) {
                 load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, pv);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += pv[i];
               }
-              if (ep.act != ACT_NONE && ep.act_after_res) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
-              }
+              if (ep.act_after_res) apply_act32(v, ep.act);
             }
             if constexpr (MODE == EPI_HEADDOT) {
               load_param32(P + P_HEADW * BN + c0, pv);
@@ -443,8 +455,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
               }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act2);
+              apply_act32(v, ep.act2);
               store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n, v);
             }
           }

@@ -62,7 +62,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 26)) {
+    __nanosleep(16);   // do not steal issue slots from the epilogue warps while waiting
+    if (++spins == (1u << 24)) {
       printf("svdd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
              (int)threadIdx.x);
       __trap();

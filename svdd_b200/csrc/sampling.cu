@@ -338,8 +338,9 @@ extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x
                                 const uint64_t* seed_dev, int step, int64_t row_offset,
                                 float mc_t, float mc_s, void* cand,
                                 float* q_out, int B, int L, int M, void* stream) {
-  SVDD_CHECK_ARG(logits && x && cand, "svdd_subs_sample: null pointer");
   SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_subs_sample: bad shape B=%d L=%d M=%d", B, L, M);
+  if ((int64_t)B * L == 0) return SVDD_OK;   // empty batch: nothing to do (pointers may be null)
+  SVDD_CHECK_ARG(logits && x && cand, "svdd_subs_sample: null pointer");
   SVDD_CHECK_ARG(M < (1 << 16), "svdd_subs_sample: M must be < 65536");
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
   SVDD_TRY(check_device());
@@ -361,8 +362,9 @@ extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x
 
 extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype, void* out,
                               int64_t n_rows, int L, void* stream) {
-  SVDD_CHECK_ARG(logits && x && out, "svdd_x0_argmax: null pointer");
   SVDD_CHECK_ARG(n_rows >= 0 && L >= 0, "svdd_x0_argmax: bad shape");
+  if (n_rows * L == 0) return SVDD_OK;
+  SVDD_CHECK_ARG(logits && x && out, "svdd_x0_argmax: null pointer");
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
   SVDD_TRY(check_device());
   const int64_t NL = n_rows * L;
@@ -380,8 +382,9 @@ extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype,
 
 extern "C" int svdd_subs_log_p(const float* logits, const void* x, int tok_dtype, float* log_p,
                                int64_t n_rows, int L, void* stream) {
-  SVDD_CHECK_ARG(logits && x && log_p, "svdd_subs_log_p: null pointer");
   SVDD_CHECK_ARG(n_rows >= 0 && L >= 0, "svdd_subs_log_p: bad shape");
+  if (n_rows * L == 0) return SVDD_OK;
+  SVDD_CHECK_ARG(logits && x && log_p, "svdd_subs_log_p: null pointer");
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
   SVDD_TRY(check_device());
   const int64_t NL = n_rows * L;
@@ -402,8 +405,9 @@ extern "C" int svdd_select_gather(const float* scores, const void* cand, int tok
                                   const uint64_t* seed_dev, int step, int64_t row_offset,
                                   void* x_out, int32_t* idx_out, int B,
                                   int L, int M, void* stream) {
-  SVDD_CHECK_ARG(scores && cand && x_out, "svdd_select_gather: null pointer");
   SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_select_gather: bad shape");
+  if (B == 0) return SVDD_OK;
+  SVDD_CHECK_ARG(scores && cand && x_out, "svdd_select_gather: null pointer");
   SVDD_CHECK_ARG(M <= 32 * kMaxIterSel, "svdd_select_gather: M=%d exceeds %d", M, 32 * kMaxIterSel);
   SVDD_CHECK_ARG(alpha >= 0.0f, "svdd_select_gather: alpha must be >= 0");
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
