@@ -338,8 +338,11 @@ class _ScoreHandle(_Handle):
 
 
 def _named_with_head(sd_embedding, sd_head):
+  """Trunk tensors under their own names + the head's under 'head.'.  A multi-task head
+  (the DNA oracle has 3) contributes task 0 only: the path reads ``reward_model(x)[:, 0]``
+  (diffusion_gosai.py:1430, Enformer.py:447)."""
   named = [(k, v) for k, v in sd_embedding.items() if v.dtype.is_floating_point]
-  named += [('head.' + k, v) for k, v in sd_head.items() if v.dtype.is_floating_point]
+  named += [('head.' + k, v[:1]) for k, v in sd_head.items() if v.dtype.is_floating_point]
   if not named or named[0][1].device.type != 'cuda':
     raise SvddError('move the value network to a CUDA device before scoring')
   return named

@@ -105,8 +105,12 @@ int pick_bn(const GemmShape& g, int mode) {
   if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL) return 128;
   if (mode == EPI_POOL) return (g.N % 128 == 0) ? 128 : 64;
   if (forced > 0 && g.N % forced == 0) return forced;
-  if (g.N % 256 == 0 && m_tiles * (g.N / 256) >= 2 * (int64_t)num_sms()) return 256;
+  const int64_t two_waves = 2 * (int64_t)num_sms();
+  if (g.N % 256 == 0 && m_tiles * (g.N / 256) >= two_waves) return 256;
+  if (g.N % 224 == 0 && g.N % 256 != 0 && m_tiles * (g.N / 224) >= two_waves) return 224;
+  if (g.N % 192 == 0 && g.N % 256 != 0 && m_tiles * (g.N / 192) >= two_waves) return 192;
   if (g.N % 128 == 0) return 128;
+  if (g.N % 192 == 0) return 192;
   return 64;
 }
 
@@ -126,7 +130,7 @@ void choose_row_tiling(int L, int taps, GemmShape* g) {
 }
 
 int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
-                     const EpiParams& ep, cudaStream_t stream) {
+                     const EpiParams& ep_in, cudaStream_t stream) {
   SVDD_CHECK_ARG(g.K > 0 && g.K % 64 == 0, "conv_gemm: K=%d must be a positive multiple of 64", g.K);
   SVDD_CHECK_ARG(g.N > 0 && g.N % 64 == 0, "conv_gemm: N=%d must be a positive multiple of 64", g.N);
   SVDD_CHECK_ARG(g.BL >= 1 && g.BS >= 1 && g.BL * g.BS <= 128, "conv_gemm: bad tile %dx%d", g.BL, g.BS);
@@ -138,6 +142,14 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   SVDD_CHECK_ARG(g.N % bn == 0, "conv_gemm: N=%d not divisible by tile %d", g.N, bn);
   if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL)
     SVDD_CHECK_ARG(g.N == 128, "conv_gemm: denoiser epilogues need N == 128 (got %d)", g.N);
+
+  static int prefetch_flag = -1;
+  if (prefetch_flag < 0) {
+    const char* e = getenv("SVDD_EPI_PREFETCH");
+    prefetch_flag = e ? atoi(e) : 1;
+  }
+  EpiParams ep = ep_in;
+  ep.prefetch = prefetch_flag;
 
   CUtensorMap tmA, tmW;
   if (mode == EPI_POOL) {
@@ -163,6 +175,8 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   if (bn == BN_ && mode == MODE_) return launch_impl<BN_, MODE_>(tmA, tmW, g, ep, stream)
   CASE(64, EPI_GENERIC);
   CASE(128, EPI_GENERIC);
+  CASE(192, EPI_GENERIC);
+  CASE(224, EPI_GENERIC);
   CASE(256, EPI_GENERIC);
   CASE(128, EPI_DEN_LN);
   CASE(128, EPI_DEN_FINAL);

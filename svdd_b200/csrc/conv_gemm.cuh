@@ -67,6 +67,9 @@ struct EpiParams {
   // EPI_HEADDOT: partials[r, 2*n_tile + half] = sum_{n in that half tile} v[n] * head_w[n]
   const float* head_w = nullptr;
   float* partials = nullptr;
+  // tuning switch (set by the launcher from SVDD_EPI_PREFETCH, default on): fetch bf16
+  // residual / pooled rows ahead of the accumulator wait
+  int prefetch = 1;
 };
 
 struct GemmShape {
@@ -101,15 +104,20 @@ struct Cfg {
   static constexpr int kTmemColsRaw = 2 * kAcc * BN;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64
                                    : kTmemColsRaw <= 128 ? 128 : kTmemColsRaw <= 256 ? 256 : 512;
-  static constexpr int kHalf = BN / 2;             // columns per epilogue thread
-  static constexpr int kChunks = kHalf / 32;       // tcgen05.ld 32x32b.x32 per thread per accumulator
+  // columns per epilogue thread: half 0 takes ceil(BN/64)*32 columns, half 1 the rest, so that
+  // both are whole 32-column tcgen05.ld chunks for BN in {64,128,192,224,256}
+  static constexpr int kHalf = ((BN + 63) / 64) * 32;
+  static constexpr int kHalf1 = BN - kHalf;
+  static constexpr int kChunks = kHalf / 32;       // chunks of half 0 (>= chunks of half 1)
+  static constexpr int kChunks1 = kHalf1 / 32;
   static constexpr int kParamBytes = 2 * kParamVecs * BN * 4;          // double-buffered per tile
   static constexpr int kXchBytes = 2 * kBM * 8 * 4;                    // half <-> half exchange
   static constexpr int kW2Bytes = (MODE == EPI_DEN_FINAL) ? (kVocab * 128 + 8) * 4 : 0;
   static constexpr int kExtraBytes = kParamBytes + kXchBytes + kW2Bytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kTmemColsRaw <= 512, "accumulators exceed tensor memory");
-  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "N tile must be 64, 128 or 256");
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "N tile must be a multiple of 32 in [64,256]");
+  static_assert(MODE == EPI_GENERIC || MODE == EPI_HEADDOT || kHalf == kHalf1, "even halves required");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -374,18 +382,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       epi_bar_sync();
-
-      ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
-      ptx::tc_fence_after();
+      if constexpr (MODE == EPI_DEN_LN || MODE == EPI_DEN_FINAL) {
+        ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        ptx::tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * (kAcc * BN) + half * kHalf;
       const int cbase = half * kHalf;    // first column (within the tile) of this thread
+      const int my_chunks = half ? C::kChunks1 : kChunks;   // warp-uniform
 
       if constexpr (MODE == EPI_GENERIC || MODE == EPI_POOL || MODE == EPI_HEADDOT) {
         float head_acc = 0.0f;
         uint32_t raw[2][32];
+        // bf16 residual / pooled values do not depend on the accumulator: fetch them two chunks
+        // ahead so their latency hides behind the wait for the MMA and the previous chunk's math
+        uint4 pre[2][2][4];
+        const bool pre_res = (MODE == EPI_GENERIC || MODE == EPI_HEADDOT) && ep.res != nullptr &&
+                             ep.res_dtype == DT_BF16 && valid && ep.prefetch;
+        const bool has1 = (MODE == EPI_POOL) && (2 * l + 1) < g.L_in;
+        const __nv_bfloat16* pre_base = nullptr;
+        if (MODE == EPI_POOL) {
+          if (valid) pre_base = reinterpret_cast<const __nv_bfloat16*>(ep.pool_vals) +
+                                ((int64_t)s * g.L_in + 2 * l) * g.N + n0 + cbase;
+        } else if (pre_res) {
+          pre_base = reinterpret_cast<const __nv_bfloat16*>(ep.res) + row * ep.ld_res + n0 + cbase;
+        }
+        auto prefetch = [&](int c) {
+          if (pre_base == nullptr || c >= kChunks || (C::kChunks1 != kChunks && c >= my_chunks)) return;
+          const uint4* p = reinterpret_cast<const uint4*>(pre_base + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pre[c & 1][0][i] = p[i];
+          if (MODE == EPI_POOL && has1) {
+            const uint4* q = reinterpret_cast<const uint4*>(pre_base + g.N + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre[c & 1][1][i] = q[i];
+          }
+        };
+        auto unpack = [&](const uint4* u, float* o) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+              o[8 * i + 2 * j] = __low2float(hh);
+              o[8 * i + 2 * j + 1] = __high2float(hh);
+            }
+          }
+        };
+        if (ep.prefetch) {
+          prefetch(0);
+          prefetch(1);
+        }
+        ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        ptx::tc_fence_after();
         if constexpr (MODE != EPI_POOL) ptx::tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
+          if (C::kChunks1 != kChunks && c >= my_chunks) continue;   // uneven halves (BN 192/224)
           const int c0 = cbase + c * 32;   // column within the tile
           const int n = n0 + c0;           // global column
           float v[32];
@@ -394,11 +447,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tmem_ld_32x32(taddr + BN + c * 32, raw[1]);
             ptx::tmem_ld_wait();
             if (valid) {
-              const int64_t rin = (int64_t)s * g.L_in + 2 * l;
-              const bool has1 = (2 * l + 1) < g.L_in;
               float y0[32], y1[32];
-              load_row32(ep.pool_vals, DT_BF16, rin * g.N + n, y0);
-              if (has1) load_row32(ep.pool_vals, DT_BF16, (rin + 1) * g.N + n, y1);
+              if (ep.prefetch) {
+                unpack(pre[c & 1][0], y0);
+                if (has1) unpack(pre[c & 1][1], y1);
+                prefetch(c + 2);
+              } else {
+                load_row32(pre_base, DT_BF16, c * 32, y0);
+                if (has1) load_row32(pre_base, DT_BF16, g.N + c * 32, y1);
+              }
               if (has1) {
                 // softmax over the pair = sigmoid of the logit difference
 #pragma unroll
@@ -414,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else {
             ptx::tmem_ld_wait();
-            if (c + 1 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
+            if (c + 1 < my_chunks) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
           }
@@ -435,7 +492,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (!ep.act_after_res) apply_act32(v, ep.act);
               if (ep.res != nullptr) {
-                load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, pv);
+                if (pre_res) {
+                  unpack(pre[c & 1][0], pv);
+                  prefetch(c + 2);
+                } else {
+                  load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n, pv);
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += pv[i];
               }
