@@ -198,6 +198,20 @@ int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16,
                             int N, int taps, int dil, int use_tensor_cores,
                             void* stream);
 
+/* The fused epilogue chain of the GEMM in isolation (tests only):
+ *   v = acc*scale+shift ; v += bias ; [act] ; v += res ; [act]  -> out
+ *   out2 = act2(v*scale2 + shift2)
+ * act: 0 none, 1 ReLU, 2 Enformer GELU x*sigmoid(1.702x); dtypes: 1 bf16, 2 fp32;
+ * any of bias/scale/res/out/out2 may be NULL; res may alias out (in-place residual
+ * stream).  flat != 0 treats A as [S*L, K] rows of a plain GEMM. */
+int svdd_selftest_gemm_epilogue(const void* A_bf16, const void* W_bf16, const float* bias,
+                                const float* scale, const float* shift, int act,
+                                int act_after_res, const void* res, int res_dtype,
+                                void* out, int out_dtype, void* out2, int out2_dtype,
+                                const float* scale2, const float* shift2, int act2, int S,
+                                int L, int K, int N, int taps, int dil, int flat,
+                                void* stream);
+
 /* Unit-test hooks for the fused pieces of stage 3b (used by tests only):
  *  - attention pooling over position pairs (enformer_pytorch AttentionPool,
  *    Enformer.py:2447): y bf16 [S,L_in,C], Wp bf16 [C,C] -> fp32 [S*ceil(L_in/2),C];

@@ -45,6 +45,8 @@ def _declare(lib):
   lib.svdd_subs_log_p.argtypes = [vp, vp, i32, vp, i64, i32, vp]
   lib.svdd_selftest_conv_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                           i32, i32, vp]
+  lib.svdd_selftest_gemm_epilogue.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i32,
+                                              vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
   lib.svdd_selftest_pool.argtypes = [vp, vp, vp, i32, i32, i32, vp]
   lib.svdd_selftest_rel_positions.argtypes = [i32, i32, vp]
   lib.svdd_selftest_attention.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
@@ -202,6 +204,24 @@ def selftest_conv_gemm(A, W, bias, taps, dil, tensor_cores=True):
                                       _ptr(C), S, L, K, N, taps, dil, int(tensor_cores),
                                       _stream()))
   return C
+
+
+_DT = {torch.bfloat16: 1, torch.float32: 2}
+
+
+def selftest_gemm_epilogue(A, W, taps=1, dil=1, flat=False, bias=None, scale=None, shift=None, act=0,
+                           act_after_res=False, res=None, out=None, out2=None, scale2=None,
+                           shift2=None, act2=0):
+  """EPI_GENERIC chain on A bf16[S,L,K], W bf16[taps,N,K]; writes `out` / `out2` ([S*L,N]
+  bf16 or fp32 tensors supplied by the caller; `res` may alias `out`)."""
+  _require_cuda(A, W, bias, scale, shift, res, out, out2, scale2, shift2)
+  S, L, K = A.shape
+  N = W.shape[1]
+  dt = lambda t: 0 if t is None else _DT[t.dtype]
+  check(lib().svdd_selftest_gemm_epilogue(
+      _ptr(A.contiguous()), _ptr(W.contiguous()), _ptr(bias), _ptr(scale), _ptr(shift), int(act),
+      int(act_after_res), _ptr(res), dt(res), _ptr(out), dt(out), _ptr(out2), dt(out2), _ptr(scale2),
+      _ptr(shift2), int(act2), S, L, K, N, taps, dil, int(flat), _stream()))
 
 
 def selftest_pool(y, Wp):

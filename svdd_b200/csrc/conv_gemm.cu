@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "conv_gemm.cuh"
+#include "conv_gemm2.cuh"
 
 namespace svdd {
 namespace {
@@ -28,15 +29,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box);
 int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
     return SVDD_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base),
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -53,6 +60,8 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64
 struct ProfState {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // start/stop pairs
+  struct Rec { GemmShape g; int bn, mode; double flops; };
+  std::vector<Rec> recs;
   double flops = 0.0;
   std::mutex mu;
 };
@@ -90,7 +99,9 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape&
     P.ev.push_back(e0);
     P.ev.push_back(e1);
     // nominal dense count (padding taps included), the figure SURVEY.md section 8(d) uses
-    P.flops += 2.0 * (double)g.S * g.L * (C::kAcc) * (double)g.N * g.K * g.taps;
+    const double fl = 2.0 * (double)g.S * g.L * (C::kAcc) * (double)g.N * g.K * g.taps;
+    P.flops += fl;
+    P.recs.push_back({g, BN, MODE, fl});
   }
   return SVDD_OK;
 }
@@ -114,9 +125,104 @@ int pick_bn(const GemmShape& g, int mode) {
   return 64;
 }
 
+
+// ---- second-generation kernel (conv_gemm2.cuh) ----------------------------------------
+int gemm2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_GEMM2"); v = e ? atoi(e) : 1; }
+  return v;
+}
+int gemm2_cg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_GEMM_CG"); v = e ? atoi(e) : 2; if (v != 1) v = 2; }
+  return v;
+}
+
+template <int BN, int MODE, int CG>
+int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                 const CUtensorMap& tmR, const GemmShape& g, const EpiParams& ep, cudaStream_t stream) {
+  using C = gemm2::Cfg2<BN, CG>;
+  auto kern = gemm2::gemm2_kernel<BN, MODE, CG>;
+  static bool configured = false;
+  if (!configured) {
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const int64_t m_tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS);
+  const int64_t tiles = ceil_div<int64_t>(m_tiles, CG) * (g.N / BN);
+  if (tiles == 0) return SVDD_OK;
+  const int64_t max_clusters = num_sms() / CG;
+  const int grid = (int)(tiles < max_clusters ? tiles : max_clusters) * CG;
+  ProfState& P = prof();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (P.on) {
+    SVDD_CUDA(cudaEventCreate(&e0));
+    SVDD_CUDA(cudaEventCreate(&e1));
+    SVDD_CUDA(cudaEventRecord(e0, stream));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(gemm2::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SVDD_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmO, tmO2, tmR, g, ep));
+  count_launch();
+  if (P.on) {
+    SVDD_CUDA(cudaEventRecord(e1, stream));
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.ev.push_back(e0);
+    P.ev.push_back(e1);
+    const double fl = 2.0 * (double)g.S * g.L * (double)g.N * g.K * g.taps;
+    P.flops += fl;
+    P.recs.push_back({g, BN + 1000 * CG, MODE, fl});
+  }
+  return SVDD_OK;
+}
+
+bool gemm2_handles(const GemmShape& g, int mode, const EpiParams& ep) {
+  if (!gemm2_enabled()) return false;
+  if (mode != EPI_GENERIC && mode != EPI_HEADDOT) return false;
+  if (g.N % 128 != 0) return false;
+  auto ok_dt = [](int dt) { return dt == DT_BF16 || dt == DT_F32; };
+  auto es = [](int dt) { return dt == DT_F32 ? 4 : 2; };
+  auto aligned = [&](const void* p, int64_t ld, int dt) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * es(dt)) % 16 == 0;
+  };
+  if (mode == EPI_HEADDOT) return ep.res == nullptr && ep.out == nullptr && ep.out2 == nullptr;
+  if (ep.out == nullptr && ep.out2 == nullptr) return false;
+  if (ep.out != nullptr && !(ok_dt(ep.out_dtype) && aligned(ep.out, ep.ld_out, ep.out_dtype))) return false;
+  if (ep.res != nullptr) {
+    if (ep.out == nullptr || ep.res_dtype != ep.out_dtype || !aligned(ep.res, ep.ld_res, ep.res_dtype)) return false;
+  } else if (ep.out2 != nullptr) {
+    if (!ok_dt(ep.out2_dtype) || !aligned(ep.out2, ep.ld_out2, ep.out2_dtype)) return false;
+    if (ep.out != nullptr && ep.out2_dtype != ep.out_dtype) return false;
+  }
+  return true;
+}
+
+int pick_bn2(const GemmShape& g, int cg) {
+  const int64_t m_tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS);
+  const int64_t mp = ceil_div<int64_t>(m_tiles, cg);
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("SVDD_GEMM2_BN"); forced = e ? atoi(e) : 0; }
+  if (forced > 0 && g.N % forced == 0) return forced;
+  if (g.N % 256 == 0 && mp * (g.N / 256) >= (num_sms() / cg) / 2) return 256;
+  return 128;
+}
+
 }  // namespace
 
-int conv_gemm_n_tiles(const GemmShape& g, int mode) { return 2 * (g.N / pick_bn(g, mode)); }
+int conv_gemm_n_tiles(const GemmShape& g, int mode) {
+  if (mode == EPI_HEADDOT && gemm2_enabled() && g.N % 128 == 0) return 2 * (g.N / pick_bn2(g, gemm2_cg()));
+  return 2 * (g.N / pick_bn(g, mode));
+}
 
 void choose_row_tiling(int L, int taps, GemmShape* g) {
   (void)taps;
@@ -138,6 +244,43 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   SVDD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                  "conv_gemm: operands must be 16-byte aligned");
   if (g.S == 0 || g.L == 0) return SVDD_OK;
+
+  if (gemm2_handles(g, mode, ep_in)) {
+    const int cg = gemm2_cg();
+    const int bn2 = pick_bn2(g, cg);
+    EpiParams ep2 = ep_in;
+    if (ep2.out == nullptr && ep2.out2 != nullptr) ep2.out_dtype = ep2.out2_dtype;   // slab geometry follows the staged output
+    CUtensorMap tA, tW, tO, tO2, tR;
+    {
+      const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.L_in, (cuuint64_t)g.S};
+      const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.L_in * g.K * 2};
+      const cuuint32_t box[3] = {64, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+      SVDD_TRY(encode_bf16_map(&tA, A, 3, dims, str, box));
+      const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.N};
+      const cuuint64_t ws[1] = {(cuuint64_t)g.K * 2};
+      const cuuint32_t wb[2] = {64, (cuuint32_t)(bn2 / cg)};
+      SVDD_TRY(encode_bf16_map(&tW, W, 2, wd, ws, wb));
+    }
+    auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld) -> int {
+      if (p == nullptr) { *m = tA; return SVDD_OK; }
+      const cuuint64_t es = dt == DT_F32 ? 4 : 2;
+      const cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)g.L, (cuuint64_t)g.S};
+      const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)g.L * ld * es};
+      const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+      return encode_map(m, dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3,
+                        dims, str, box);
+    };
+    SVDD_TRY(io_map(&tO, ep2.out, ep2.out_dtype, ep2.ld_out));
+    SVDD_TRY(io_map(&tO2, ep2.res == nullptr ? ep2.out2 : nullptr, ep2.out2_dtype, ep2.ld_out2));
+    SVDD_TRY(io_map(&tR, ep2.res, ep2.res_dtype, ep2.ld_res));
+#define CASE2(BN_, MODE_, CG_) \
+    if (bn2 == BN_ && mode == MODE_ && cg == CG_) return launch2_impl<BN_, MODE_, CG_>(tA, tW, tO, tO2, tR, g, ep2, stream)
+    CASE2(128, EPI_GENERIC, 1); CASE2(256, EPI_GENERIC, 1);
+    CASE2(128, EPI_GENERIC, 2); CASE2(256, EPI_GENERIC, 2);
+    CASE2(128, EPI_HEADDOT, 1); CASE2(256, EPI_HEADDOT, 1);
+    CASE2(128, EPI_HEADDOT, 2); CASE2(256, EPI_HEADDOT, 2);
+#undef CASE2
+  }
   const int bn = pick_bn(g, mode);
   SVDD_CHECK_ARG(g.N % bn == 0, "conv_gemm: N=%d not divisible by tile %d", g.N, bn);
   if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL)
@@ -197,6 +340,7 @@ extern "C" int svdd_profile_begin(void) {
   std::lock_guard<std::mutex> lk(P.mu);
   for (cudaEvent_t e : P.ev) cudaEventDestroy(e);
   P.ev.clear();
+  P.recs.clear();
   P.flops = 0.0;
   P.on = true;
   return SVDD_OK;
@@ -211,6 +355,12 @@ extern "C" int svdd_profile_end(double* gemm_ms, int64_t* gemm_launches, double*
     if (cudaEventSynchronize(P.ev[i + 1]) != cudaSuccess) break;
     float t = 0.0f;
     if (cudaEventElapsedTime(&t, P.ev[i], P.ev[i + 1]) == cudaSuccess) ms += t;
+    if (getenv("SVDD_PROF_DUMP") && i / 2 < P.recs.size()) {   // per-launch table for tuning
+      const svdd::ProfState::Rec& r = P.recs[i / 2];
+      fprintf(stderr, "gemm %3zu mode %d BN %3d S %6d L %6d K %5d N %5d taps %d dil %2d  %8.1f us  %7.1f TFLOP/s\n",
+              i / 2, r.mode, r.bn, r.g.S, r.g.L, r.g.K, r.g.N, r.g.taps, r.g.dil, t * 1e3,
+              r.flops / (t * 1e-3) / 1e12);
+    }
   }
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_launches) *gemm_launches = (int64_t)(P.ev.size() / 2);
@@ -275,6 +425,37 @@ extern "C" int svdd_selftest_conv_gemm(const void* A_bf16, const void* W_bf16, c
   ep.bias = bias;
   ep.out = C; ep.out_dtype = DT_F32; ep.ld_out = N;
   return launch_conv_gemm(A_bf16, W_bf16, g, EPI_GENERIC, ep, st);
+}
+
+// Fused epilogue chain of EPI_GENERIC in isolation (tests only):
+//   v = acc*scale+shift ; v += bias ; [act] ; v += res ; [act] -> out ; out2 = act2(v*scale2+shift2)
+// dtypes: 1 = bf16, 2 = fp32 (svdd::DType).  `flat` treats A as [S*L, K] rows (plain GEMM).
+extern "C" int svdd_selftest_gemm_epilogue(const void* A_bf16, const void* W_bf16, const float* bias,
+                                           const float* scale, const float* shift, int act, int act_after_res,
+                                           const void* res, int res_dtype, void* out, int out_dtype,
+                                           void* out2, int out2_dtype, const float* scale2,
+                                           const float* shift2, int act2, int S, int L, int K, int N,
+                                           int taps, int dil, int flat, void* stream) {
+  SVDD_CHECK_ARG(A_bf16 && W_bf16, "selftest_gemm_epilogue: null pointer");
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  GemmShape g;
+  g.K = K; g.N = N; g.taps = taps; g.dil = dil;
+  if (flat) {
+    SVDD_CHECK_ARG(taps == 1, "selftest_gemm_epilogue: flat rows need taps == 1");
+    g.S = 1; g.L = S * L; g.L_in = S * L; g.BL = 128; g.BS = 1;
+  } else {
+    g.S = S; g.L = L; g.L_in = L;
+    choose_row_tiling(L, taps, &g);
+  }
+  EpiParams ep;
+  ep.bias = bias; ep.scale = scale; ep.shift = shift; ep.act = act; ep.act_after_res = act_after_res;
+  ep.res = res; ep.res_dtype = res_dtype; ep.ld_res = N;
+  ep.out = out; ep.out_dtype = out_dtype; ep.ld_out = N;
+  ep.out2 = out2; ep.out2_dtype = out2_dtype; ep.ld_out2 = N;
+  ep.scale2 = scale2; ep.shift2 = shift2; ep.act2 = act2;
+  return launch_conv_gemm(A_bf16, W_bf16, g, EPI_GENERIC, ep, (cudaStream_t)stream);
 }
 
 // Attention pooling (EPI_POOL) in isolation: y bf16 [S, L_in, C], Wp bf16 [C, C] ->

@@ -1,0 +1,559 @@
+// Second-generation tcgen05 implicit GEMM (same contraction as conv_gemm.cuh):
+//
+//   * cta_group::2: a CTA pair (two SMs of one TPC) computes a 256 x BN tile with one
+//     tcgen05.mma; each CTA stages its own 128 rows of A and HALF of the B tile, so the
+//     L2 -> SM operand traffic per FLOP drops by a third against the 128 x 256 single-CTA
+//     tile (the k5 convs were L2-feed bound);
+//   * the epilogue no longer touches global memory from the math threads: accumulators go
+//     TMEM -> registers -> 128B-swizzled shared-memory slabs (128 rows x 128 bytes) that two
+//     dedicated store warps push out with TMA (cp.async.bulk.tensor store), and the
+//     residual / pooled operand comes in the same way (TMA load into the slab, then read
+//     by the thread that owns the row).  Thread-per-row global accesses cost 32 L1
+//     wavefronts per instruction and made every K <= 1536 GEMM epilogue bound.
+//
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer (leader CTA only), 2-9 epilogue
+// math (thread = (row, column half)), 10-11 slab store / prefetch (one per column half).
+//
+// Slab protocol, per column half h, job j = 0,1,2,... in a fixed order (tile, slab, output):
+//   buffer b = j & 1;  rin[h][b]  : store warp -> math warps  "buffer free / residual landed"
+//                      rout[h][b] : math warps -> store warp  "slab written"
+// The store warp provisions job j+2 right after job j's TMA store has drained the buffer.
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace svdd {
+namespace gemm2 {
+
+using gemm_detail::kBK;
+using gemm_detail::kBM;
+using gemm_detail::kEpiWarps;
+using gemm_detail::kEpiThreads;
+using gemm_detail::kParamVecs;
+using gemm_detail::P_BIAS;
+using gemm_detail::P_SCALE;
+using gemm_detail::P_SHIFT;
+using gemm_detail::P_SCALE2;
+using gemm_detail::P_SHIFT2;
+using gemm_detail::P_HEADW;
+
+constexpr int kStoreWarps = 2;
+constexpr int kThreads = 64 + kEpiThreads + 32 * kStoreWarps;   // 384
+constexpr int kSlabBytes = kBM * 128;                            // 128 rows x 128 B
+constexpr int kStagingBytes = 2 * 2 * kSlabBytes;                // [half][buffer]
+constexpr int kBarBytes = 512;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // shared::cluster address of the pair's even CTA
+
+template <int BN, int CG>
+struct Cfg2 {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kParamBytes = 2 * kParamVecs * BN * 4;
+  static constexpr int kAvail = 227 * 1024 - 1024 - kStagingBytes - kParamBytes - kBarBytes;
+  static constexpr int kStagesRaw = kAvail / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                                   : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int kHalf = BN / 2;
+  static constexpr int kChunks = kHalf / 32;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kParamBytes + kBarBytes + 1024;
+  static_assert(BN == 128 || BN == 256, "gemm2 tiles are 128 or 256 columns wide");
+  static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
+  static_assert(kStages >= 2, "operand ring too shallow");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+};
+
+// ---- PTX helpers that only this kernel needs --------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// operand loads: with CG == 2 both CTAs signal the LEADER's barrier
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    ptx::tma_load_2d(dst, m, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar) & kPeerMask),
+        "r"(c0), "r"(c1) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               int c2) {
+  if constexpr (CG == 1) {
+    ptx::tma_load_3d(dst, m, bar, c0, c1, c2);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar) & kPeerMask),
+        "r"(c0), "r"(c1), "r"(c2) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    ptx::umma_bf16(tmem_d, da, db, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+// arrives (once all prior MMAs of this thread retire) on the barrier at this smem offset in
+// every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    ptx::umma_commit(bar);
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(ptx::smem_u32(bar)), "h"(mask) : "memory");
+  }
+}
+// arrive on the pair leader's copy of `bar` (own copy when CG == 1)
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    ptx::mbar_arrive(bar);
+  } else {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ptx::smem_u32(bar) & kPeerMask)
+                 : "memory");
+  }
+}
+// TMA store of a 3-D box from shared memory (bulk async group)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)): one MUFU op per element
+__device__ __forceinline__ float gelu_tanh(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
+  const float h = 0.5f * v;
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ void act32(float* v, int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+  }
+}
+
+// One row's 32-column chunk <-> its place in a 128B-swizzled slab.  `row_base` = slab + r*128,
+// x7 = r & 7.  bf16: the chunk is half a row (16B units 4*(c&1) .. +3); fp32: the whole row.
+__device__ __forceinline__ void slab_write(uint8_t* row_base, int x7, bool f32, int chunk_in_slab, const float* v) {
+  if (f32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      *reinterpret_cast<float4*>(row_base + ((u ^ x7) << 4)) =
+          make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = chunk_in_slab * 4 + u;
+      *reinterpret_cast<uint4*>(row_base + ((j ^ x7) << 4)) =
+          make_uint4(gemm_detail::pack_bf16x2(v[8 * u], v[8 * u + 1]), gemm_detail::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                     gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+    }
+  }
+}
+__device__ __forceinline__ void slab_read(const uint8_t* row_base, int x7, bool f32, int chunk_in_slab, float* v) {
+  if (f32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 f = *reinterpret_cast<const float4*>(row_base + ((u ^ x7) << 4));
+      v[4 * u] = f.x; v[4 * u + 1] = f.y; v[4 * u + 2] = f.z; v[4 * u + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = chunk_in_slab * 4 + u;
+      const uint4 q = *reinterpret_cast<const uint4*>(row_base + ((j ^ x7) << 4));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[8 * u + 2 * k] = __low2float(hh);
+        v[8 * u + 2 * k + 1] = __high2float(hh);
+      }
+    }
+  }
+}
+
+struct TileCoord { int n0, s0, l0; bool in_range; };
+
+template <int BN, int MODE, int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+             const __grid_constant__ CUtensorMap tmRes, const GemmShape g, const EpiParams ep) {
+  using C = Cfg2<BN, CG>;
+  constexpr int kStages = C::kStages;
+  constexpr int kHalf = C::kHalf;
+  constexpr int kChunks = C::kChunks;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + kStages * C::kStageBytes;                // [half][buf] slabs, 1024-aligned
+  float* s_param = reinterpret_cast<float*>(staging + kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes + C::kParamBytes);
+  uint64_t* full_bar = bars;                       // [kStages]   (leader's copy is the live one)
+  uint64_t* empty_bar = bars + kStages;            // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;        // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]         (leader's copy is the live one)
+  uint64_t* rin_bar = bars + 2 * kStages + 4;      // [half][buf]
+  uint64_t* rout_bar = bars + 2 * kStages + 8;     // [half][buf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+
+  const int tiles_l = ceil_div(g.L, g.BL);
+  const int tiles_s = ceil_div(g.S, g.BS);
+  const int64_t m_tiles = (int64_t)tiles_l * tiles_s;
+  const int64_t mp_tiles = (m_tiles + CG - 1) / CG;
+  const int n_tiles = g.N / BN;
+  const int64_t total_tiles = mp_tiles * n_tiles;
+  const int kblocks = g.K / kBK;
+  const int64_t first_tile = blockIdx.x / CG;
+  const int64_t tile_step = gridDim.x / CG;
+
+  const bool out_f32 = ep.out_dtype == DT_F32;
+  const bool has_out = (MODE == EPI_GENERIC) && ep.out != nullptr;
+  const bool has_res = (MODE != EPI_POOL) && ep.res != nullptr;
+  const bool out2_staged = (MODE == EPI_GENERIC) && ep.out2 != nullptr && !has_res;
+  const int n_out = (has_out ? 1 : 0) + (out2_staged ? 1 : 0);       // staged jobs per slab
+  const int slab_chunks = out_f32 ? 1 : 2;                            // 32-column chunks per slab
+  const int slab_cols = slab_chunks * 32;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    if (has_out) ptx::prefetch_tmap(&tmOut);
+    if (out2_staged) ptx::prefetch_tmap(&tmOut2);
+    if (has_res) ptx::prefetch_tmap(&tmRes);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        ptx::mbar_init(&full_bar[i], 1);
+        ptx::mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&tfull_bar[i], 1);
+        ptx::mbar_init(&tempty_bar[i], CG * kEpiWarps);
+      }
+      for (int i = 0; i < 4; ++i) {
+        ptx::mbar_init(&rin_bar[i], 1);
+        ptx::mbar_init(&rout_bar[i], kEpiWarps / 2);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_cg<CG>(tmem_slot, C::kTmemCols);
+  }
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // coordinates of this CTA's half of pair-tile `t` (rr = rank within the pair)
+  auto tile_coords = [&](int64_t t, int rr) {
+    TileCoord c;
+    const int nt = (int)(t % n_tiles);
+    const int64_t mt = (t / n_tiles) * CG + rr;
+    c.n0 = nt * BN;
+    c.in_range = mt < m_tiles;
+    c.s0 = (int)(mt / tiles_l) * g.BS;       // >= S when out of range: TMA zero-fills / clips
+    c.l0 = (int)(mt % tiles_l) * g.BL;
+    return c;
+  };
+  // a tap is issued when it touches real data for either CTA of the pair
+  auto tap_active = [&](int tap, int64_t t) {
+    bool any = false;
+#pragma unroll
+    for (int rr = 0; rr < CG; ++rr) {
+      const TileCoord c = tile_coords(t, rr);
+      const int l_start = c.l0 + (tap - g.taps / 2) * g.dil;
+      any = any || (c.in_range && (l_start + g.BL > 0) && (l_start < g.L_in));
+    }
+    return any;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs of a pair) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(CG * (g.BL * g.BS * kBK * 2 + C::kBBytes));
+      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord c = tile_coords(t, rank);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          if (!tap_active(tap, t)) continue;
+          const int l_start = c.l0 + (tap - g.taps / 2) * g.dil;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stage_base + stage * C::kStageBytes;
+            uint8_t* sb = sa + C::kABytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_3d_cg<CG>(sa, &tmA, &full_bar[stage], kb * kBK, l_start, c.s0);
+            tma_load_2d_cg<CG>(sb, &tmW, &full_bar[stage], kb * kBK, tap * g.N + c.n0 + rank * (BN / CG));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM * CG, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc_stage = 0, acc_phase = 0;
+      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+        ptx::mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc_stage * BN;
+        uint32_t first = 1;
+        for (int tap = 0; tap < g.taps; ++tap) {
+          if (!tap_active(tap, t)) continue;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+              const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+              const uint64_t db = ptx::make_kmajor_sw128_desc(sa + C::kABytes);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_cg<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
+              umma_commit_cg<CG>(&empty_bar[stage]);
+            }
+            __syncwarp();
+            first = 0;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (lane == 0) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
+        __syncwarp();
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue math: thread = (row, column half) =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;
+    const int etid = threadIdx.x - 64;
+    const int r = quad * 32 + lane;      // tile row owned by this thread
+    const int x7 = r & 7;
+    uint8_t* my_bufs = staging + half * 2 * kSlabBytes + r * 128;     // + (job & 1) * kSlabBytes
+    uint64_t* my_rin = rin_bar + half * 2;
+    uint64_t* my_rout = rout_bar + half * 2;
+    uint32_t acc_stage = 0, acc_phase = 0;
+    uint32_t job = 0;                    // staged-slab counter of this half
+    for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+      const TileCoord tc = tile_coords(t, rank);
+      const int n0 = tc.n0;
+      const int s = tc.s0 + r / g.BL, l = tc.l0 + r % g.BL;
+      const bool valid = (r < g.BL * g.BS) && (s < g.S) && (l < g.L);
+      const int64_t row = (int64_t)s * g.L + l;
+
+      float* P = s_param + acc_stage * (kParamVecs * BN);
+      for (int i = etid; i < BN; i += kEpiThreads) {
+        if (ep.bias) P[P_BIAS * BN + i] = ep.bias[n0 + i];
+        if (ep.scale) { P[P_SCALE * BN + i] = ep.scale[n0 + i]; P[P_SHIFT * BN + i] = ep.shift[n0 + i]; }
+        if (ep.scale2) { P[P_SCALE2 * BN + i] = ep.scale2[n0 + i]; P[P_SHIFT2 * BN + i] = ep.shift2[n0 + i]; }
+        if (MODE == EPI_HEADDOT) P[P_HEADW * BN + i] = ep.head_w[n0 + i];
+      }
+      gemm_detail::epi_bar_sync();
+
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + half * kHalf;
+      const int cbase = half * kHalf;
+      float head_acc = 0.0f;
+      uint32_t raw[2][32];
+      ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32(taddr, raw[0]);
+      uint8_t* buf0 = nullptr;           // slab of the `out` job (holds the residual on entry)
+      uint8_t* buf1 = nullptr;           // slab of the staged `out2` job
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int c0 = cbase + c * 32;   // column within the tile
+        const int cis = c % slab_chunks; // chunk within its slab
+        if (n_out > 0 && cis == 0) {
+          buf0 = my_bufs + (job & 1) * kSlabBytes;
+          ptx::mbar_wait(&my_rin[job & 1], (job >> 1) & 1);
+          if (n_out == 2) {
+            buf1 = my_bufs + ((job + 1) & 1) * kSlabBytes;
+            ptx::mbar_wait(&my_rin[(job + 1) & 1], ((job + 1) >> 1) & 1);
+          }
+        }
+        float v[32];
+        ptx::tmem_ld_wait();
+        if (c + 1 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
+        if (c + 1 == kChunks) {          // accumulator fully read: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
+        }
+        float pv[32];
+        if (ep.scale != nullptr) {
+          float ps[32];
+          gemm_detail::load_param32(P + P_SCALE * BN + c0, ps);
+          gemm_detail::load_param32(P + P_SHIFT * BN + c0, pv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
+        }
+        if (ep.bias != nullptr) {
+          gemm_detail::load_param32(P + P_BIAS * BN + c0, pv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += pv[i];
+        }
+        if (!ep.act_after_res) act32(v, ep.act);
+        if (has_res) {
+          if (has_out) {
+            slab_read(buf0, x7, out_f32, cis, pv);
+          } else if (valid) {            // HEADDOT with a residual: direct (unused by the nets)
+            gemm_detail::load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n0 + c0, pv);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += pv[i];
+        }
+        if (ep.act_after_res) act32(v, ep.act);
+        if constexpr (MODE == EPI_HEADDOT) {
+          gemm_detail::load_param32(P + P_HEADW * BN + c0, pv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) head_acc += v[i] * pv[i];
+        }
+        if (has_out) slab_write(buf0, x7, out_f32, cis, v);
+        if (MODE == EPI_GENERIC && ep.out2 != nullptr) {
+          if (ep.scale2 != nullptr) {
+            float ps[32];
+            gemm_detail::load_param32(P + P_SCALE2 * BN + c0, ps);
+            gemm_detail::load_param32(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
+          }
+          act32(v, ep.act2);
+          if (out2_staged) {
+            slab_write(has_out ? buf1 : buf0, x7, out_f32, cis, v);
+          } else if (valid) {            // residual + second output (one launch per pass): direct
+            gemm_detail::store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n0 + c0, v);
+          }
+        }
+        if (n_out > 0 && cis == slab_chunks - 1) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(&my_rout[job & 1]);
+            if (n_out == 2) ptx::mbar_arrive(&my_rout[(job + 1) & 1]);
+          }
+          job += n_out;
+        }
+      }
+      if (MODE == EPI_HEADDOT && valid)
+        ep.partials[row * (2 * n_tiles) + 2 * (n0 / BN) + half] = head_acc;
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== slab store / prefetch warp (one per column half) =====================
+    const int half = warp - (2 + kEpiWarps);
+    if (lane == 0 && n_out > 0) {
+      uint8_t* bufs = staging + half * 2 * kSlabBytes;
+      uint64_t* my_rin = rin_bar + half * 2;
+      uint64_t* my_rout = rout_bar + half * 2;
+      const int slabs = kHalf / slab_cols;
+      const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
+      // job iterator: (tile, slab, output)
+      struct It { int64_t t; int slab, o; };
+      auto advance = [&](It& it) {
+        if (++it.o == n_out) { it.o = 0; if (++it.slab == slabs) { it.slab = 0; it.t += tile_step; } }
+      };
+      auto provision = [&](const It& it, uint32_t j) {     // make buffer j&1 ready for job j
+        if (it.t >= total_tiles) return;
+        if (has_res) {
+          const TileCoord c = tile_coords(it.t, rank);
+          ptx::mbar_arrive_expect_tx(&my_rin[j & 1], res_bytes);
+          ptx::tma_load_3d(bufs + (j & 1) * kSlabBytes, &tmRes, &my_rin[j & 1],
+                           c.n0 + half * kHalf + it.slab * slab_cols, c.l0, c.s0);
+        } else {
+          ptx::mbar_arrive(&my_rin[j & 1]);
+        }
+      };
+      It cur{first_tile, 0, 0}, ahead{first_tile, 0, 0};
+      provision(ahead, 0);
+      advance(ahead);
+      provision(ahead, 1);
+      advance(ahead);
+      for (uint32_t j = 0; cur.t < total_tiles; ++j) {
+        const TileCoord c = tile_coords(cur.t, rank);
+        ptx::mbar_wait(&my_rout[j & 1], (j >> 1) & 1);
+        const bool second = (cur.o == 1) || !has_out;      // this job carries `out2`
+        tma_store_3d(second ? &tmOut2 : &tmOut, bufs + (j & 1) * kSlabBytes,
+                     c.n0 + half * kHalf + cur.slab * slab_cols, c.l0, c.s0);
+        bulk_commit();
+        bulk_wait_read0();
+        provision(ahead, j + 2);
+        advance(ahead);
+        advance(cur);
+      }
+      bulk_wait_all();
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace gemm2
+
+// The host launcher lives in conv_gemm.cu (launch_conv_gemm routes here when the shape and
+// epilogue are ones this kernel handles).
+}  // namespace svdd

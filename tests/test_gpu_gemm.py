@@ -90,3 +90,67 @@ def test_attention_kernel(cuda, n):
   out = torch.einsum('bhij,bhjd->bhid', (content + rel).softmax(-1), v)
   ref = out.permute(0, 2, 1, 3).reshape(rows * n, H * dv)
   assert float((got - ref).abs().max()) < 0.02 * float(ref.abs().max())
+
+
+def _act(v, kind):
+  if kind == 1:
+    return v.relu()
+  if kind == 2:
+    return v * torch.sigmoid(1.702 * v)
+  return v
+
+
+EPI_CASES = [
+    # S, L, K, N, taps, flat, out dtype, res?, dual?, act, act_after_res, scale?
+    (9, 200, 64, 768, 1, True, torch.bfloat16, False, True, 0, False, False),     # stem: x0 + GELU(BN(x0))
+    (5, 100, 256, 768, 5, False, torch.bfloat16, False, True, 0, False, False),   # k5 conv, two outputs
+    (7, 200, 768, 768, 1, True, torch.bfloat16, True, False, 0, False, False),    # 1x1 + bf16 residual
+    (11, 25, 384, 256, 5, False, torch.bfloat16, False, True, 0, False, True),    # ragged tiles (125 rows), odd pair count
+    (300, 2, 1536, 2560, 1, True, torch.float32, False, False, 0, False, False),  # QKV: fp32 out
+    (300, 2, 512, 1536, 1, True, torch.float32, True, False, 0, False, False),    # out-proj: in-place fp32 residual
+    (300, 2, 512, 1536, 1, True, torch.float32, True, True, 0, False, False),     # last FFN2: residual + second output
+    (300, 2, 256, 3072, 1, True, torch.bfloat16, False, False, 1, False, False),  # FFN1: ReLU, bf16
+    (3, 200, 128, 128, 9, False, torch.float32, True, False, 1, True, False),     # activation after the residual
+    (1, 130, 128, 384, 1, True, torch.bfloat16, True, False, 2, False, True),     # 2 row tiles, second nearly empty
+    (1, 1, 64, 128, 1, True, torch.float32, False, False, 0, False, False),
+]
+
+
+@pytest.mark.parametrize('S,L,K,N,taps,flat,odt,use_res,dual,act,aar,use_scale', EPI_CASES)
+def test_gemm_fused_epilogues(cuda, S, L, K, N, taps, flat, odt, use_res, dual, act, aar, use_scale):
+  """Every epilogue combination the networks use (bias / BN affine / activation / residual /
+  second output, bf16 and fp32, in place) against torch fp32 on the same bf16 operands."""
+  g = torch.Generator().manual_seed(S * 17 + L + K)
+  A = torch.randn(S, L, K, generator=g).to(cuda).bfloat16()
+  W = (torch.randn(taps, N, K, generator=g) * (K * taps) ** -0.5).to(cuda).bfloat16()
+  bias = torch.randn(N, generator=g).to(cuda)
+  scale = (1 + 0.2 * torch.randn(N, generator=g)).to(cuda) if use_scale else None
+  shift = (0.3 * torch.randn(N, generator=g)).to(cuda) if use_scale else None
+  scale2 = (1 + 0.2 * torch.randn(N, generator=g)).to(cuda)
+  shift2 = (0.3 * torch.randn(N, generator=g)).to(cuda)
+  res0 = torch.randn(S * L, N, generator=g).to(cuda).to(odt) if use_res else None
+  out = res0.clone() if use_res else torch.full((S * L, N), 7.0, device=cuda, dtype=odt)
+  out2 = torch.full((S * L, N), 7.0, device=cuda, dtype=torch.bfloat16 if use_res else odt) if dual else None
+  guard = out.clone()
+  _lib.selftest_gemm_epilogue(A, W, taps=taps, flat=flat, bias=bias, scale=scale, shift=shift, act=act,
+                              act_after_res=aar, res=out if use_res else None, out=out, out2=out2,
+                              scale2=scale2 if dual else None, shift2=shift2 if dual else None,
+                              act2=2 if dual else 0)
+  torch.cuda.synchronize()
+  y = F.conv1d(A.float().permute(0, 2, 1), W.float().permute(1, 2, 0), None, padding=taps // 2)
+  v = y.permute(0, 2, 1).reshape(S * L, N)
+  if use_scale:
+    v = v * scale + shift
+  v = v + bias
+  if not aar:
+    v = _act(v, act)
+  if use_res:
+    v = v + res0.float()
+  if aar:
+    v = _act(v, act)
+  tol = 3e-2 if odt == torch.bfloat16 else 3e-3
+  assert float((out.float() - v).abs().max()) < tol * max(1.0, float(v.abs().max()))
+  assert not torch.equal(out, guard)
+  if dual:
+    v2 = _act(v * scale2 + shift2, 2)
+    assert float((out2.float() - v2).abs().max()) < 3e-2 * max(1.0, float(v2.abs().max()))
