@@ -188,6 +188,17 @@ int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok_dtype,
                         float* scores, int64_t n_rows, int L, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* Test hook for stage 2: same contract as svdd_subs_sample, but every Gumbel-max draw is
+ * taken on the exact logf + IEEE-division path (the reference's arithmetic, operation for
+ * operation).  svdd_subs_sample decides a draw with one approximate log per element only
+ * when an error-bound test proves the exact argmax; tests assert both entry points agree
+ * bit for bit, including on adversarial near-ties. */
+int svdd_selftest_subs_sample_exact(const float* logits, int is_log_p, const void* x,
+                                    int tok_dtype, const float* U, uint64_t seed,
+                                    const uint64_t* seed_dev, int step, int64_t row_offset,
+                                    float mc_t, float mc_s, void* cand, float* q_out, int B,
+                                    int L, int M, void* stream);
+
 /* ---- self test of the tcgen05 implicit-GEMM building block ----------------
  * C[r,n] = sum_{tap,k} A[seq(r), l(r)+(tap-taps/2)*dil, k] * W[tap,n,k]
  * (zero outside [0,L)) + bias[n], bf16 operands, fp32 accumulate, fp32 out.
@@ -221,6 +232,17 @@ int svdd_selftest_gemm_epilogue(const void* A_bf16, const void* W_bf16, const fl
  *    [H,2n-1,dk] -> bf16 [rows*n, H*dv]. */
 int svdd_selftest_pool(const void* y_bf16, const void* Wp_bf16, float* out, int S,
                        int L_in, int C, void* stream);
+/* The pair-split 1x1 conv + difference pooling used by svdd_enformer_score (tests only):
+ * y = A.W1^T + bias + res is never materialised; y0 = y[2j], yd = y[2j+1] - y[2j] (0 for the
+ * unpaired tail of an odd L); pooled[j] = y0 + sigmoid(Wp.yd) * yd -- AttentionPool(2) of
+ * enformer_pytorch (Enformer.py:2447) since softmax over a pair is the sigmoid of the logit
+ * difference and Wp.y1 - Wp.y0 = Wp.(y1 - y0).  A, res bf16 [S,L,C]; W1, Wp bf16 [C,C];
+ * y0, yd bf16 [S,ceil(L/2),C]; pooled fp32 and/or pooled_act = GELU(pooled*scale2+shift2) bf16. */
+int svdd_selftest_pair_pool(const void* A_bf16, const void* W1_bf16, const float* bias,
+                            const void* res_bf16, const void* Wp_bf16, void* y0_bf16,
+                            void* yd_bf16, float* pooled_f32, void* pooled_act_bf16,
+                            const float* scale2, const float* shift2, int S, int L, int C,
+                            void* stream);
 int svdd_selftest_rel_positions(int n, int F, float* out_host);
 int svdd_selftest_attention(const float* qkv, const float* rcb, const float* rpb,
                             const float* relk, void* out_bf16, int64_t rows, int n,

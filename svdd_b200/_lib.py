@@ -39,6 +39,7 @@ def _declare(lib):
   lib.svdd_launch_count.restype = i64
   lib.svdd_subs_sample.argtypes = [vp, i32, vp, i32, vp, u64, vp, i32, i64, f32, f32,
                                    vp, vp, i32, i32, i32, vp]
+  lib.svdd_selftest_subs_sample_exact.argtypes = lib.svdd_subs_sample.argtypes
   lib.svdd_select_gather.argtypes = [vp, vp, i32, f32, vp, u64, vp, i32, i64, vp, vp,
                                      i32, i32, i32, vp]
   lib.svdd_x0_argmax.argtypes = [vp, vp, i32, vp, i64, i32, vp]
@@ -48,6 +49,7 @@ def _declare(lib):
   lib.svdd_selftest_gemm_epilogue.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i32,
                                               vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
   lib.svdd_selftest_pool.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+  lib.svdd_selftest_pair_pool.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
   lib.svdd_selftest_rel_positions.argtypes = [i32, i32, vp]
   lib.svdd_selftest_attention.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
   tp = c.POINTER(_Tensor)
@@ -132,9 +134,10 @@ def tok_dtype(t):
 
 # -- stage 2 ---------------------------------------------------------------------
 def subs_sample(logits, x, M, mc_t, mc_s, U=None, seed=0, step=0, row_offset=0,
-                is_log_p=False, want_q=False, out=None, seed_dev=None):
+                is_log_p=False, want_q=False, out=None, seed_dev=None, exact=False):
   """svdd_subs_sample: logits fp32[B,L,5], x [B,L] -> candidates [M,B,L]
-  (+ q_xs fp32[B,L,5] when want_q)."""
+  (+ q_xs fp32[B,L,5] when want_q).  exact=True is the test hook that forces every draw
+  onto the exact-arithmetic path (svdd_selftest_subs_sample_exact)."""
   _require_cuda(logits, x, U)
   B, L = x.shape
   assert logits.shape == (B, L, 5) and logits.dtype == torch.float32
@@ -144,11 +147,10 @@ def subs_sample(logits, x, M, mc_t, mc_s, U=None, seed=0, step=0, row_offset=0,
     U = U.contiguous()
   cand = out if out is not None else torch.empty((M, B, L), dtype=x.dtype, device=x.device)
   q = torch.empty((B, L, 5), dtype=torch.float32, device=x.device) if want_q else None
-  check(lib().svdd_subs_sample(_ptr(logits), int(is_log_p), _ptr(x), tok_dtype(x),
-                               _ptr(U), int(seed), _ptr(seed_dev), int(step),
-                               int(row_offset), float(mc_t), float(mc_s), _ptr(cand),
-                               _ptr(q), B, L, M,
-                               _stream()))
+  fn = lib().svdd_selftest_subs_sample_exact if exact else lib().svdd_subs_sample
+  check(fn(_ptr(logits), int(is_log_p), _ptr(x), tok_dtype(x), _ptr(U), int(seed),
+           _ptr(seed_dev), int(step), int(row_offset), float(mc_t), float(mc_s), _ptr(cand),
+           _ptr(q), B, L, M, _stream()))
   return (cand, q) if want_q else cand
 
 
@@ -233,6 +235,24 @@ def selftest_pool(y, Wp):
   pad[:S * L] = y.reshape(S * L, C)
   check(lib().svdd_selftest_pool(_ptr(pad), _ptr(Wp.contiguous()), _ptr(out), S, L, C, _stream()))
   return out
+
+
+def selftest_pair_pool(A, W1, bias, res, Wp, scale2=None, shift2=None, want_act=False):
+  """Pair-split 1x1 conv + difference pooling (EPI_PAIR -> EPI_POOL2).  A, res bf16 [S,L,C];
+  W1, Wp bf16 [C,C] -> (y0, yd bf16 [S,Lo,C], pooled fp32 [S*Lo,C], pooled_act bf16 or None)."""
+  _require_cuda(A, W1, res, Wp)
+  S, L, C = A.shape
+  Lo = (L + 1) // 2
+  dev = A.device
+  y0 = torch.empty((S, Lo, C), dtype=torch.bfloat16, device=dev)
+  yd = torch.empty((S, Lo, C), dtype=torch.bfloat16, device=dev)
+  pooled = torch.empty((S * Lo, C), dtype=torch.float32, device=dev)
+  pact = torch.empty((S * Lo, C), dtype=torch.bfloat16, device=dev) if want_act else None
+  check(lib().svdd_selftest_pair_pool(_ptr(A.contiguous()), _ptr(W1.contiguous()), _ptr(bias),
+                                      _ptr(res.contiguous()), _ptr(Wp.contiguous()), _ptr(y0), _ptr(yd),
+                                      _ptr(pooled), _ptr(pact), _ptr(scale2), _ptr(shift2), S, L, C,
+                                      _stream()))
+  return y0, yd, pooled, pact
 
 
 def selftest_rel_positions(n, F):

@@ -140,7 +140,8 @@ int gemm2_cg() {
 
 template <int BN, int MODE, int CG>
 int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmO2,
-                 const CUtensorMap& tmR, const GemmShape& g, const EpiParams& ep, cudaStream_t stream) {
+                 const CUtensorMap& tmR, const CUtensorMap& tmR2, const GemmShape& g, const EpiParams& ep,
+                 cudaStream_t stream) {
   using C = gemm2::Cfg2<BN, CG>;
   auto kern = gemm2::gemm2_kernel<BN, MODE, CG>;
   static bool configured = false;
@@ -172,7 +173,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SVDD_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmO, tmO2, tmR, g, ep));
+  SVDD_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmO, tmO2, tmR, tmR2, g, ep));
   count_launch();
   if (P.on) {
     SVDD_CUDA(cudaEventRecord(e1, stream));
@@ -187,6 +188,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
 }
 
 bool gemm2_handles(const GemmShape& g, int mode, const EpiParams& ep) {
+  if (mode == EPI_PAIR || mode == EPI_POOL2) return true;     // validated by the launcher
   if (!gemm2_enabled()) return false;
   if (mode != EPI_GENERIC && mode != EPI_HEADDOT) return false;
   if (g.N % 128 != 0) return false;
@@ -226,13 +228,22 @@ int conv_gemm_n_tiles(const GemmShape& g, int mode) {
 
 void choose_row_tiling(int L, int taps, GemmShape* g) {
   (void)taps;
-  if (L <= 128) {
-    g->BL = L;
-    g->BS = 128 / L;
-  } else {
-    g->BL = 128;
-    g->BS = 1;
+  // A tile is BL positions x BS sequences (BL*BS <= 128 MMA rows).  Pick the pair that leaves
+  // the fewest of the 128 rows empty: L = 200/100/50/25 -> 25 x 5 (125 rows, 97.7 %) where
+  // whole-sequence or 128-position tiles only fill 78 %.  Smaller BL is taken only for a
+  // gain above 3 % (fewer, longer TMA box rows otherwise).
+  static int legacy = -1;
+  if (legacy < 0) { const char* e = getenv("SVDD_TILING_LEGACY"); legacy = e ? atoi(e) : 0; }
+  int best_bl = L <= 128 ? L : 128;
+  double best_eff = 0.0;
+  for (int bl = best_bl; bl >= (L >= 2 ? 2 : 1) && !legacy; --bl) {
+    const int bs = 128 / bl;
+    if (bs > 256) continue;
+    const double eff = (double)L * bs / ((double)ceil_div(L, bl) * 128.0);
+    if (eff > best_eff * 1.03) { best_eff = eff; best_bl = bl; }
   }
+  g->BL = best_bl;
+  g->BS = 128 / best_bl;
 }
 
 int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
@@ -250,7 +261,7 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
     const int bn2 = pick_bn2(g, cg);
     EpiParams ep2 = ep_in;
     if (ep2.out == nullptr && ep2.out2 != nullptr) ep2.out_dtype = ep2.out2_dtype;   // slab geometry follows the staged output
-    CUtensorMap tA, tW, tO, tO2, tR;
+    CUtensorMap tA, tW, tO, tO2, tR, tR2;
     {
       const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.L_in, (cuuint64_t)g.S};
       const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.L_in * g.K * 2};
@@ -261,25 +272,61 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
       const cuuint32_t wb[2] = {64, (cuuint32_t)(bn2 / cg)};
       SVDD_TRY(encode_bf16_map(&tW, W, 2, wd, ws, wb));
     }
-    auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld) -> int {
+    // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes x box_l x BS
+    auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l) -> int {
       if (p == nullptr) { *m = tA; return SVDD_OK; }
       const cuuint64_t es = dt == DT_F32 ? 4 : 2;
-      const cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)g.L, (cuuint64_t)g.S};
-      const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)g.L * ld * es};
-      const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+      const cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)Lr, (cuuint64_t)g.S};
+      const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)Lr * ld * es};
+      const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_l, (cuuint32_t)g.BS};
       return encode_map(m, dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3,
                         dims, str, box);
     };
-    SVDD_TRY(io_map(&tO, ep2.out, ep2.out_dtype, ep2.ld_out));
-    SVDD_TRY(io_map(&tO2, ep2.res == nullptr ? ep2.out2 : nullptr, ep2.out2_dtype, ep2.ld_out2));
-    SVDD_TRY(io_map(&tR, ep2.res, ep2.res_dtype, ep2.ld_res));
+    auto aligned16 = [](const void* p, int64_t ld_elems, int es) {
+      return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_elems * es) % 16 == 0;
+    };
+    if (mode == EPI_PAIR) {
+      SVDD_CHECK_ARG(g.N % 128 == 0 && g.BL % 2 == 0 && g.taps == 1, "conv_gemm: EPI_PAIR needs N %% 128 == 0, an even BL, 1x1");
+      SVDD_CHECK_ARG(ep2.res && ep2.out && ep2.out2 && ep2.res_dtype == DT_BF16 && ep2.out_dtype == DT_BF16 &&
+                     ep2.out2_dtype == DT_BF16, "conv_gemm: EPI_PAIR needs bf16 res / out / out2");
+      SVDD_CHECK_ARG(aligned16(ep2.res, ep2.ld_res, 2) && aligned16(ep2.out, ep2.ld_out, 2) &&
+                     aligned16(ep2.out2, ep2.ld_out2, 2), "conv_gemm: EPI_PAIR operands must be 16-byte aligned");
+      const int Lo = (g.L + 1) / 2;
+      SVDD_TRY(io_map(&tO, ep2.out, DT_BF16, ep2.ld_out, Lo, g.BL / 2));
+      SVDD_TRY(io_map(&tO2, ep2.out2, DT_BF16, ep2.ld_out2, Lo, g.BL / 2));
+      SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL));
+      tR2 = tA;
+    } else if (mode == EPI_POOL2) {
+      SVDD_CHECK_ARG(g.N % 128 == 0 && g.taps == 1, "conv_gemm: EPI_POOL2 needs N %% 128 == 0, 1x1");
+      SVDD_CHECK_ARG(ep2.res && ep2.res2 && (ep2.out || ep2.out2), "conv_gemm: EPI_POOL2 needs res, res2 and an output");
+      SVDD_CHECK_ARG(ep2.out == nullptr || ep2.out_dtype == DT_F32, "conv_gemm: EPI_POOL2 `out` is fp32");
+      SVDD_CHECK_ARG(ep2.out2 == nullptr || ep2.out2_dtype == DT_BF16, "conv_gemm: EPI_POOL2 `out2` is bf16");
+      SVDD_CHECK_ARG(aligned16(ep2.res, ep2.ld_res, 2) && aligned16(ep2.res2, ep2.ld_res2, 2) &&
+                     (ep2.out2 == nullptr || aligned16(ep2.out2, ep2.ld_out2, 2)),
+                     "conv_gemm: EPI_POOL2 operands must be 16-byte aligned");
+      tO = tA;
+      SVDD_TRY(io_map(&tO2, ep2.out2, DT_BF16, ep2.ld_out2, g.L, g.BL));
+      SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL));
+      SVDD_TRY(io_map(&tR2, ep2.res2, DT_BF16, ep2.ld_res2, g.L, g.BL));
+    } else {
+      SVDD_TRY(io_map(&tO, ep2.out, ep2.out_dtype, ep2.ld_out, g.L, g.BL));
+      SVDD_TRY(io_map(&tO2, ep2.res == nullptr ? ep2.out2 : nullptr, ep2.out2_dtype, ep2.ld_out2, g.L, g.BL));
+      SVDD_TRY(io_map(&tR, ep2.res, ep2.res_dtype, ep2.ld_res, g.L, g.BL));
+      tR2 = tA;
+    }
 #define CASE2(BN_, MODE_, CG_) \
-    if (bn2 == BN_ && mode == MODE_ && cg == CG_) return launch2_impl<BN_, MODE_, CG_>(tA, tW, tO, tO2, tR, g, ep2, stream)
+    if (bn2 == BN_ && mode == MODE_ && cg == CG_) return launch2_impl<BN_, MODE_, CG_>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream)
     CASE2(128, EPI_GENERIC, 1); CASE2(256, EPI_GENERIC, 1);
     CASE2(128, EPI_GENERIC, 2); CASE2(256, EPI_GENERIC, 2);
     CASE2(128, EPI_HEADDOT, 1); CASE2(256, EPI_HEADDOT, 1);
     CASE2(128, EPI_HEADDOT, 2); CASE2(256, EPI_HEADDOT, 2);
+    CASE2(128, EPI_PAIR, 1); CASE2(256, EPI_PAIR, 1);
+    CASE2(128, EPI_PAIR, 2); CASE2(256, EPI_PAIR, 2);
+    CASE2(128, EPI_POOL2, 1); CASE2(256, EPI_POOL2, 1);
+    CASE2(128, EPI_POOL2, 2); CASE2(256, EPI_POOL2, 2);
 #undef CASE2
+    set_last_error("conv_gemm: no gemm2 kernel for BN=%d mode=%d", bn2, mode);
+    return SVDD_ERR_INTERNAL;
   }
   const int bn = pick_bn(g, mode);
   SVDD_CHECK_ARG(g.N % bn == 0, "conv_gemm: N=%d not divisible by tile %d", g.N, bn);
@@ -473,4 +520,46 @@ extern "C" int svdd_selftest_pool(const void* y_bf16, const void* Wp_bf16, float
   ep.pool_vals = y_bf16;
   ep.out = out; ep.out_dtype = DT_F32; ep.ld_out = C;
   return launch_conv_gemm(y_bf16, Wp_bf16, g, EPI_POOL, ep, (cudaStream_t)stream);
+}
+
+// The pair-split 1x1 conv + difference pooling (EPI_PAIR -> EPI_POOL2) in isolation:
+//   y = A.W1^T + bias + res  (never materialised);  y0 = y[2j], yd = y[2j+1] - y[2j];
+//   pooled[j] = y0 + sigmoid(Wp.yd) * yd  = softmax-weighted sum over the pair.
+// A, res bf16 [S, L, C]; W1, Wp bf16 [C, C]; y0, yd bf16 [S, ceil(L/2), C]; pooled fp32 (optional)
+// and/or pooled_act bf16 = GELU(pooled * scale2 + shift2) (optional), both [S*ceil(L/2), C].
+extern "C" int svdd_selftest_pair_pool(const void* A_bf16, const void* W1_bf16, const float* bias,
+                                       const void* res_bf16, const void* Wp_bf16, void* y0_bf16,
+                                       void* yd_bf16, float* pooled_f32, void* pooled_act_bf16,
+                                       const float* scale2, const float* shift2, int S, int L, int C,
+                                       void* stream) {
+  SVDD_CHECK_ARG(A_bf16 && W1_bf16 && res_bf16 && Wp_bf16 && y0_bf16 && yd_bf16, "selftest_pair_pool: null pointer");
+  SVDD_CHECK_ARG(pooled_f32 || pooled_act_bf16, "selftest_pair_pool: no output requested");
+  SVDD_CHECK_ARG(L % 2 == 0 || L + 1 <= 128, "selftest_pair_pool: odd lengths above 127 are not supported");
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  const int Lo = (L + 1) / 2;
+  {
+    GemmShape g;
+    g.K = C; g.N = C; g.taps = 1; g.dil = 1;
+    if (L % 2 == 0) { g.S = 1; g.L = S * L; g.L_in = g.L; g.BL = 128; g.BS = 1; }
+    else { g.S = S; g.L = L; g.L_in = L; g.BL = L + 1; g.BS = 128 / (L + 1); }
+    EpiParams ep;
+    ep.bias = bias;
+    ep.res = res_bf16; ep.res_dtype = DT_BF16; ep.ld_res = C;
+    ep.out = y0_bf16; ep.out_dtype = DT_BF16; ep.ld_out = C;
+    ep.out2 = yd_bf16; ep.out2_dtype = DT_BF16; ep.ld_out2 = C;
+    SVDD_TRY(launch_conv_gemm(A_bf16, W1_bf16, g, EPI_PAIR, ep, (cudaStream_t)stream));
+  }
+  GemmShape g;
+  g.S = 1; g.L = S * Lo; g.L_in = g.L; g.K = C; g.N = C; g.taps = 1; g.dil = 1; g.BL = 128; g.BS = 1;
+  EpiParams ep;
+  ep.res = y0_bf16; ep.res_dtype = DT_BF16; ep.ld_res = C;
+  ep.res2 = yd_bf16; ep.ld_res2 = C;
+  if (pooled_f32) { ep.out = pooled_f32; ep.out_dtype = DT_F32; ep.ld_out = C; }
+  if (pooled_act_bf16) {
+    ep.out2 = pooled_act_bf16; ep.out2_dtype = DT_BF16; ep.ld_out2 = C;
+    ep.scale2 = scale2; ep.shift2 = shift2; ep.act2 = ACT_GELU;
+  }
+  return launch_conv_gemm(yd_bf16, Wp_bf16, g, EPI_POOL2, ep, (cudaStream_t)stream);
 }

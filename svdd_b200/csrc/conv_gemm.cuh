@@ -32,7 +32,8 @@ namespace svdd {
 
 enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 enum DType { DT_NONE = 0, DT_BF16 = 1, DT_F32 = 2 };
-enum EpiMode { EPI_GENERIC = 0, EPI_DEN_LN = 1, EPI_DEN_FINAL = 2, EPI_POOL = 3, EPI_HEADDOT = 4 };
+enum EpiMode { EPI_GENERIC = 0, EPI_DEN_LN = 1, EPI_DEN_FINAL = 2, EPI_POOL = 3, EPI_HEADDOT = 4,
+               EPI_PAIR = 5, EPI_POOL2 = 6 };   // 5, 6: conv_gemm2.cuh only
 
 struct EpiParams {
   // generic chain on v = acc:  v = v*scale + shift ; v += bias ; [act] ; v += res ; [act]
@@ -64,6 +65,11 @@ struct EpiParams {
   const float* b2 = nullptr;
   // EPI_POOL: values being pooled (bf16 [S*L_in, N])
   const void* pool_vals = nullptr;
+  // EPI_PAIR : out = y[2j] and out2 = y[2j+1] - y[2j], both bf16 [S, ceil(L/2), N] (res = block input)
+  // EPI_POOL2: A = yd; res = y0, res2 = yd (bf16 [rows, N]); pooled = y0 + sigmoid(acc) * yd ->
+  //            out (fp32, optional) and out2 = act2(pooled * scale2 + shift2) (bf16, optional)
+  const void* res2 = nullptr;
+  int64_t ld_res2 = 0;
   // EPI_HEADDOT: partials[r, 2*n_tile + half] = sum_{n in that half tile} v[n] * head_w[n]
   const float* head_w = nullptr;
   float* partials = nullptr;

@@ -11,6 +11,15 @@
 //     by the thread that owns the row).  Thread-per-row global accesses cost 32 L1
 //     wavefronts per instruction and made every K <= 1536 GEMM epilogue bound.
 //
+// Attention pooling over position pairs (enformer_pytorch AttentionPool, softmax over a pair)
+// only needs the DIFFERENCE of the two logits, and Wp.y1 - Wp.y0 = Wp.(y1 - y0).  So:
+//   EPI_PAIR   (the residual 1x1 conv feeding a pool): the epilogue exchanges each row with
+//              its pair partner (adjacent lane) and stores y0 = y[2j] and yd = y[2j+1] - y[2j]
+//              at half length instead of y (yd = 0 for the unpaired tail of an odd length);
+//   EPI_POOL2  one GEMM over yd (half the rows, one accumulator) instead of two over y:
+//              pooled = y0 + sigmoid(Wp.yd) * yd, then the next layer's BN+GELU.
+// Half the pooling FLOPs of the two-accumulator EPI_POOL kernel, on the cta_group::2 path.
+//
 // Warp roles (384 threads): 0 TMA producer, 1 MMA issuer (leader CTA only), 2-9 epilogue
 // math (thread = (row, column half)), 10-11 slab store / prefetch (one per column half).
 //
@@ -227,7 +236,8 @@ template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-             const __grid_constant__ CUtensorMap tmRes, const GemmShape g, const EpiParams ep) {
+             const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes2,
+             const GemmShape g, const EpiParams ep) {
   using C = Cfg2<BN, CG>;
   constexpr int kStages = C::kStages;
   constexpr int kHalf = C::kHalf;
@@ -259,20 +269,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int64_t first_tile = blockIdx.x / CG;
   const int64_t tile_step = gridDim.x / CG;
 
-  const bool out_f32 = ep.out_dtype == DT_F32;
+  constexpr bool kPair = (MODE == EPI_PAIR), kPool2 = (MODE == EPI_POOL2);
+  const bool out_f32 = !(kPair || kPool2) && ep.out_dtype == DT_F32;  // dtype of the staged slabs
   const bool has_out = (MODE == EPI_GENERIC) && ep.out != nullptr;
-  const bool has_res = (MODE != EPI_POOL) && ep.res != nullptr;
+  const bool has_res = (MODE == EPI_GENERIC || MODE == EPI_HEADDOT) && ep.res != nullptr;
   const bool out2_staged = (MODE == EPI_GENERIC) && ep.out2 != nullptr && !has_res;
-  const int n_out = (has_out ? 1 : 0) + (out2_staged ? 1 : 0);       // staged jobs per slab
+  // slab buffers used per 64/32-column step: EPI_PAIR = {residual in, (yd | y0) out},
+  // EPI_POOL2 = {y0 in / next operand out, yd in}
+  const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
   const int slab_chunks = out_f32 ? 1 : 2;                            // 32-column chunks per slab
   const int slab_cols = slab_chunks * 32;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
-    if (has_out) ptx::prefetch_tmap(&tmOut);
-    if (out2_staged) ptx::prefetch_tmap(&tmOut2);
-    if (has_res) ptx::prefetch_tmap(&tmRes);
+    if (has_out || kPair) ptx::prefetch_tmap(&tmOut);
+    if (out2_staged || kPair || (kPool2 && ep.out2 != nullptr)) ptx::prefetch_tmap(&tmOut2);
+    if (has_res || kPair || kPool2) ptx::prefetch_tmap(&tmRes);
+    if (kPool2) ptx::prefetch_tmap(&tmRes2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -439,6 +453,31 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
         }
         float pv[32];
+        if constexpr (kPool2) {
+          // v = Wp.(y1 - y0): pooled = y0 + sigmoid(v) * (y1 - y0)
+          float yd[32];
+          slab_read(buf0, x7, false, cis, pv);
+          slab_read(buf1, x7, false, cis, yd);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float w1 = gemm_detail::fast_rcp(1.0f + gemm_detail::fast_ex2(-1.4426950408889634f * v[i]));
+            v[i] = fmaf(w1, yd[i], pv[i]);
+          }
+          if (ep.out != nullptr) {         // last stage: fp32 transformer stream, direct
+            if (valid) gemm_detail::store_row32(ep.out, DT_F32, row * ep.ld_out + n0 + c0, v);
+          }
+          if (ep.out2 != nullptr) {
+            if (ep.scale2 != nullptr) {
+              float ps[32];
+              gemm_detail::load_param32(P + P_SCALE2 * BN + c0, ps);
+              gemm_detail::load_param32(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
+            }
+            act32(v, ep.act2);
+            slab_write(buf0, x7, false, cis, v);     // in place: this thread owns the row
+          }
+        } else {
         if (ep.scale != nullptr) {
           float ps[32];
           gemm_detail::load_param32(P + P_SCALE * BN + c0, ps);
@@ -452,8 +491,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 32; ++i) v[i] += pv[i];
         }
         if (!ep.act_after_res) act32(v, ep.act);
-        if (has_res) {
-          if (has_out) {
+        if (has_res || kPair) {
+          if (has_out || kPair) {
             slab_read(buf0, x7, out_f32, cis, pv);
           } else if (valid) {            // HEADDOT with a residual: direct (unused by the nets)
             gemm_detail::load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n0 + c0, pv);
@@ -467,6 +506,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 32; ++i) head_acc += v[i] * pv[i];
         }
+        if constexpr (kPair) {
+          // rows (2j, 2j+1) sit on adjacent lanes: even lane keeps y0 = y[2j], odd lane forms
+          // yd = y[2j+1] - y[2j] (0 when 2j+1 is past the sequence end); slab row j of the
+          // lower half (yd) / upper half (y0) of buf1
+          const bool odd = (r & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float other = __shfl_xor_sync(0xffffffffu, v[i], 1);
+            v[i] = odd ? (valid ? v[i] - other : 0.0f) : v[i];
+          }
+          const int pr = r >> 1;
+          slab_write(buf1 + (odd ? 0 : (kBM / 2) * 128) + pr * 128 - r * 128, pr & 7, false, cis, v);
+        } else {
         if (has_out) slab_write(buf0, x7, out_f32, cis, v);
         if (MODE == EPI_GENERIC && ep.out2 != nullptr) {
           if (ep.scale2 != nullptr) {
@@ -482,6 +534,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else if (valid) {            // residual + second output (one launch per pass): direct
             gemm_detail::store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n0 + c0, v);
           }
+        }
+        }
         }
         if (n_out > 0 && cis == slab_chunks - 1) {
           ptx::fence_proxy_async_smem();
@@ -506,17 +560,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint64_t* my_rout = rout_bar + half * 2;
       const int slabs = kHalf / slab_cols;
       const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
-      // job iterator: (tile, slab, output)
+      // job iterator: (tile, slab, buffer-of-the-step)
       struct It { int64_t t; int slab, o; };
       auto advance = [&](It& it) {
         if (++it.o == n_out) { it.o = 0; if (++it.slab == slabs) { it.slab = 0; it.t += tile_step; } }
       };
+      // what is loaded into the buffer before the math warps may touch it
+      auto load_map = [&](int o) -> const CUtensorMap* {
+        if (kPair) return o == 0 ? &tmRes : nullptr;
+        if (kPool2) return o == 0 ? &tmRes : &tmRes2;
+        return (has_res && o == 0) ? &tmRes : nullptr;
+      };
       auto provision = [&](const It& it, uint32_t j) {     // make buffer j&1 ready for job j
         if (it.t >= total_tiles) return;
-        if (has_res) {
+        const CUtensorMap* m = load_map(it.o);
+        if (m != nullptr) {
           const TileCoord c = tile_coords(it.t, rank);
           ptx::mbar_arrive_expect_tx(&my_rin[j & 1], res_bytes);
-          ptx::tma_load_3d(bufs + (j & 1) * kSlabBytes, &tmRes, &my_rin[j & 1],
+          ptx::tma_load_3d(bufs + (j & 1) * kSlabBytes, m, &my_rin[j & 1],
                            c.n0 + half * kHalf + it.slab * slab_cols, c.l0, c.s0);
         } else {
           ptx::mbar_arrive(&my_rin[j & 1]);
@@ -530,11 +591,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (uint32_t j = 0; cur.t < total_tiles; ++j) {
         const TileCoord c = tile_coords(cur.t, rank);
         ptx::mbar_wait(&my_rout[j & 1], (j >> 1) & 1);
-        const bool second = (cur.o == 1) || !has_out;      // this job carries `out2`
-        tma_store_3d(second ? &tmOut2 : &tmOut, bufs + (j & 1) * kSlabBytes,
-                     c.n0 + half * kHalf + cur.slab * slab_cols, c.l0, c.s0);
-        bulk_commit();
-        bulk_wait_read0();
+        const uint8_t* buf = bufs + (j & 1) * kSlabBytes;
+        const int col = c.n0 + half * kHalf + cur.slab * slab_cols;
+        bool stored = false;
+        if (kPair) {
+          if (cur.o == 1) {               // rows 0..63: yd, rows 64..127: y0, both at half length
+            tma_store_3d(&tmOut2, buf, col, c.l0 >> 1, c.s0);
+            tma_store_3d(&tmOut, buf + (kBM / 2) * 128, col, c.l0 >> 1, c.s0);
+            stored = true;
+          }
+        } else if (kPool2) {
+          if (cur.o == 0 && ep.out2 != nullptr) { tma_store_3d(&tmOut2, buf, col, c.l0, c.s0); stored = true; }
+        } else {
+          const bool second = (cur.o == 1) || !has_out;      // this job carries `out2`
+          tma_store_3d(second ? &tmOut2 : &tmOut, buf, col, c.l0, c.s0);
+          stored = true;
+        }
+        if (stored) {
+          bulk_commit();
+          bulk_wait_read0();
+        }
         provision(ahead, j + 2);
         advance(ahead);
         advance(cur);

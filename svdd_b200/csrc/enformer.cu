@@ -18,6 +18,7 @@
 //
 // Activations are bf16 channels-last [rows, L_i, f_i]; the transformer residual stream is fp32.
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
@@ -106,6 +107,68 @@ ef_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const flo
   }
 }
 
+// Warp-per-row variant for C % 128 == 0, C <= 128 * kLnWarpVecs: the row lives in registers as
+// float4s (coalesced 512 B per warp per load), both statistics are warp shuffles, the bf16
+// result goes out as 8-byte stores.  Same arithmetic as ef_ln_kernel (two-pass variance).
+constexpr int kLnWarpVecs = 16;    // C <= 2048
+constexpr int kLnWarpsPerBlock = 8;
+__global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
+ef_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                  __nv_bfloat16* __restrict__ out, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 7;                       // float4s per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[kLnWarpVecs];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnWarpVecs; ++i) {
+    if (i < nvec) {
+      v[i] = xr[i * 32 + lane];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnWarpVecs; ++i) {
+    if (i < nvec) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  uint2* o2 = reinterpret_cast<uint2*>(out + row * C);
+#pragma unroll
+  for (int i = 0; i < kLnWarpVecs; ++i) {
+    if (i < nvec) {
+      const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+      const float y0 = (v[i].x - mean) * rstd * gg.x + bb.x, y1 = (v[i].y - mean) * rstd * gg.y + bb.y;
+      const float y2 = (v[i].z - mean) * rstd * gg.z + bb.z, y3 = (v[i].w - mean) * rstd * gg.w + bb.w;
+      o2[i * 32 + lane] = make_uint2(gemm_detail::pack_bf16x2(y0, y1), gemm_detail::pack_bf16x2(y2, y3));
+    }
+  }
+}
+
+int launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* out, int64_t rows, int C,
+              cudaStream_t st) {
+  if (C % 128 == 0 && C <= 128 * kLnWarpVecs)
+    ef_ln_warp_kernel<<<(unsigned)ceil_div<int64_t>(rows, kLnWarpsPerBlock), kLnWarpsPerBlock * 32, 0, st>>>(
+        x, g, b, out, rows, C);
+  else
+    ef_ln_kernel<<<(unsigned)rows, kLnThreads, 0, st>>>(x, g, b, out, C);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
 // ---- attention over n <= 8 positions (enformer_pytorch Attention.forward) ----------------
 // qkv fp32 [rows*n, 2*H*dk + H*dv]; relk fp32 [H][2n-1][dk]; out bf16 [rows*n, H*dv].
 //   logits[i,j] = (q_i*scale + rcb).k_j + (q_i*scale + rpb).relk[(j-i)+(n-1)]   (relative_shift)
@@ -155,6 +218,100 @@ ef_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb
     }
     __syncthreads();
   }
+}
+
+// Warp-per-(sequence, head) variant for small n (the transformer sees n = 2 positions at
+// L = 200): q/k/rel_k slices stay in registers, the n*n logits are warp-reduced, every lane
+// holds the softmax and produces dv/32 output channels per position.  One pass over qkv
+// (coalesced 128 B segments) instead of a block per sequence looping over heads.
+constexpr int kAttnSmallN = 4;     // n <= 4
+constexpr int kAttnDkPer = 4;      // dk <= 128
+constexpr int kAttnWarps = 8;
+template <int N>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+ef_attention_warp_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb,
+                         const float* __restrict__ rpb, const float* __restrict__ relk,
+                         __nv_bfloat16* __restrict__ out, int64_t rows, int H, int dk, int dv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
+  if (w >= rows * H) return;
+  const int64_t seq = w / H;
+  const int h = (int)(w % H);
+  const int ld = 2 * H * dk + H * dv;
+  const float* base = qkv + seq * N * ld;
+  const float scale = rsqrtf((float)dk);
+  float lg[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) lg[i][j] = 0.0f;
+#pragma unroll
+  for (int t = 0; t < kAttnDkPer; ++t) {
+    const int d = lane + 32 * t;
+    if (d < dk) {
+      const float cb = rcb[h * dk + d], pb = rpb[h * dk + d];
+      float q[N], k[N], rk[2 * N - 1];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        q[i] = base[i * ld + h * dk + d] * scale;
+        k[i] = base[i * ld + H * dk + h * dk + d];
+      }
+#pragma unroll
+      for (int p = 0; p < 2 * N - 1; ++p) rk[p] = relk[((size_t)h * (2 * N - 1) + p) * dk + d];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) lg[i][j] += (q[i] + cb) * k[j] + (q[i] + pb) * rk[j - i + N - 1];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lg[i][j] += __shfl_xor_sync(0xffffffffu, lg[i][j], o);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float mx = lg[i][0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) mx = fmaxf(mx, lg[i][j]);
+    float den = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { lg[i][j] = __expf(lg[i][j] - mx); den += lg[i][j]; }
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int j = 0; j < N; ++j) lg[i][j] *= inv;
+  }
+  for (int d = lane; d < dv; d += 32) {
+    float vv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) vv[j] = base[j * ld + 2 * H * dk + h * dv + d];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc += lg[i][j] * vv[j];
+      out[(seq * N + i) * (size_t)(H * dv) + h * dv + d] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
+int launch_attention(const float* qkv, const float* rcb, const float* rpb, const float* relk,
+                     __nv_bfloat16* out, int64_t rows, int n, int H, int dk, int dv, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div<int64_t>(rows * H, kAttnWarps);
+  if (dk <= 32 * kAttnDkPer && n == 1)
+    ef_attention_warp_kernel<1><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+  else if (dk <= 32 * kAttnDkPer && n == 2)
+    ef_attention_warp_kernel<2><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+  else if (dk <= 32 * kAttnDkPer && n == 3)
+    ef_attention_warp_kernel<3><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+  else if (dk <= 32 * kAttnDkPer && n == 4)
+    ef_attention_warp_kernel<4><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+  else
+    ef_attention_kernel<<<(unsigned)rows, 256, 0, st>>>(qkv, rcb, rpb, relk, out, n, H, dk, dv);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
 }
 
 // relk[blk][h][p][d] = sum_f W[blk][(h*dk+d)][f] * pos[p][f]
@@ -428,10 +585,8 @@ extern "C" int svdd_selftest_attention(const float* qkv, const float* rcb, const
                                        int H, int dk, int dv, void* stream) {
   SVDD_CHECK_ARG(qkv && rcb && rpb && relk && out_bf16, "selftest_attention: null pointer");
   SVDD_CHECK_ARG(n >= 1 && n <= kMaxPos, "selftest_attention: n out of range");
-  ef_attention_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
-      qkv, rcb, rpb, relk, (__nv_bfloat16*)out_bf16, n, H, dk, dv);
-  SVDD_LAUNCH_CHECK();
-  return SVDD_OK;
+  return launch_attention(qkv, rcb, rpb, relk, (__nv_bfloat16*)out_bf16, rows, n, H, dk, dv,
+                          (cudaStream_t)stream);
 }
 
 namespace {
@@ -445,6 +600,11 @@ struct EfWs {
   __nv_bfloat16* u;
   float* partials;
 };
+bool pool2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_POOL2"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 int ef_final_len(const svdd_enformer* h, int L) {
   int n = L;
   for (int i = 0; i < h->n_stage; ++i) n = (n + 1) / 2;
@@ -571,54 +731,95 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         }
         __nv_bfloat16* t = a; a = y; y = t;          // a <- a' ; old a is free (now y)
       }
-      {  // y = Conv_1x1(a) + b + x     (residual ConvBlock, Enformer.py:1836-1838 / 1866-1868)
-        EpiParams ep;
-        ep.bias = h->b1[i];
-        ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
-        ep.out = y; ep.out_dtype = DT_BF16; ep.ld_out = fi;
-        SVDD_TRY(gemm_flat(a, h->w1[i], rows * len, fi, fi, ep, EPI_GENERIC));
-        if (debug_dump_enabled())
-          debug_dump(("ef_y" + std::to_string(i)).c_str(), y, (size_t)rows * len * fi * 2, st);
-      }
-      {  // attention pool over position pairs; epilogue also prepares the next conv's operand
-        const int lo = (len + 1) / 2;
-        GemmShape g;
-        g.S = (int)rows; g.L = lo; g.L_in = len; g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
-        choose_row_tiling(lo, 1, &g);
-        EpiParams ep;
-        ep.pool_vals = y;
-        if (i + 1 < h->n_stage) {
-          ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
-          ep.scale2 = h->bn5_s[i + 1]; ep.shift2 = h->bn5_t[i + 1]; ep.act2 = ACT_GELU;
-        } else {
-          ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
+      // Attention pooling needs only the difference of the two logits of a pair, and
+      // Wp.y[2j+1] - Wp.y[2j] = Wp.(y[2j+1] - y[2j]): the 1x1 conv's epilogue emits y0 = y[2j] and
+      // yd = y[2j+1] - y[2j] at half length (EPI_PAIR) and the pool is ONE GEMM over yd (EPI_POOL2)
+      // instead of two over y.  Odd lengths: whole-sequence tiles padded to an even BL, yd = 0 for
+      // the unpaired tail (= the reference's -inf logit on the padded slot).
+      const int lo = (len + 1) / 2;
+      const bool pair_path = pool2_enabled() && fi % 128 == 0 && (len % 2 == 0 || len + 1 <= 128);
+      if (pair_path) {
+        __nv_bfloat16* y0 = y;
+        __nv_bfloat16* yd = y + (size_t)rows * lo * fi;
+        {
+          GemmShape g;
+          g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
+          if (len % 2 == 0) {
+            g.S = 1; g.L = (int)(rows * len); g.L_in = g.L; g.BL = 128; g.BS = 1;
+          } else {
+            g.S = (int)rows; g.L = len; g.L_in = len; g.BL = len + 1; g.BS = 128 / (len + 1);
+          }
+          EpiParams ep;
+          ep.bias = h->b1[i];
+          ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          ep.out = y0; ep.out_dtype = DT_BF16; ep.ld_out = fi;
+          ep.out2 = yd; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+          SVDD_TRY(launch_conv_gemm(a, h->w1[i], g, EPI_PAIR, ep, st));
+          if (debug_dump_enabled()) {
+            debug_dump(("ef_y0_" + std::to_string(i)).c_str(), y0, (size_t)rows * lo * fi * 2, st);
+            debug_dump(("ef_yd_" + std::to_string(i)).c_str(), yd, (size_t)rows * lo * fi * 2, st);
+          }
         }
-        SVDD_TRY(launch_conv_gemm(y, h->wp[i], g, EPI_POOL, ep, st));
-        if (debug_dump_enabled()) {
-          if (i + 1 < h->n_stage)
-            debug_dump(("ef_a" + std::to_string(i + 1)).c_str(), a, (size_t)rows * lo * fi * 2, st);
-          else
-            debug_dump("ef_xt_in", b.xt, (size_t)rows * lo * fi * 4, st);
+        {
+          GemmShape g;
+          g.S = 1; g.L = (int)(rows * lo); g.L_in = g.L; g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
+          g.BL = 128; g.BS = 1;
+          EpiParams ep;
+          ep.res = y0; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          ep.res2 = yd; ep.ld_res2 = fi;
+          if (i + 1 < h->n_stage) {
+            ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+            ep.scale2 = h->bn5_s[i + 1]; ep.shift2 = h->bn5_t[i + 1]; ep.act2 = ACT_GELU;
+          } else {
+            ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
+          }
+          SVDD_TRY(launch_conv_gemm(yd, h->wp[i], g, EPI_POOL2, ep, st));
         }
-        len = lo;
+      } else {
+        {  // y = Conv_1x1(a) + b + x     (residual ConvBlock, Enformer.py:1836-1838 / 1866-1868)
+          EpiParams ep;
+          ep.bias = h->b1[i];
+          ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          ep.out = y; ep.out_dtype = DT_BF16; ep.ld_out = fi;
+          SVDD_TRY(gemm_flat(a, h->w1[i], rows * len, fi, fi, ep, EPI_GENERIC));
+          if (debug_dump_enabled())
+            debug_dump(("ef_y" + std::to_string(i)).c_str(), y, (size_t)rows * len * fi * 2, st);
+        }
+        {  // attention pool over position pairs; epilogue also prepares the next conv's operand
+          GemmShape g;
+          g.S = (int)rows; g.L = lo; g.L_in = len; g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
+          choose_row_tiling(lo, 1, &g);
+          EpiParams ep;
+          ep.pool_vals = y;
+          if (i + 1 < h->n_stage) {
+            ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+            ep.scale2 = h->bn5_s[i + 1]; ep.shift2 = h->bn5_t[i + 1]; ep.act2 = ACT_GELU;
+          } else {
+            ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
+          }
+          SVDD_TRY(launch_conv_gemm(y, h->wp[i], g, EPI_POOL, ep, st));
+        }
       }
+      if (debug_dump_enabled()) {
+        if (i + 1 < h->n_stage)
+          debug_dump(("ef_a" + std::to_string(i + 1)).c_str(), a, (size_t)rows * lo * fi * 2, st);
+        else
+          debug_dump("ef_xt_in", b.xt, (size_t)rows * lo * fi * 4, st);
+      }
+      len = lo;
     }
     // ---- transformer tower ------------------------------------------------------------------
     const int64_t R = rows * n;
     for (int j = 0; j < h->n_blocks; ++j) {
       auto& blk = h->blk[j];
-      ef_ln_kernel<<<(unsigned)R, kLnThreads, 0, st>>>(b.xt, blk.ln1_g, blk.ln1_b, b.hn, C);
-      count_launch();
-      SVDD_LAUNCH_CHECK();
+      SVDD_TRY(launch_ln(b.xt, blk.ln1_g, blk.ln1_b, b.hn, R, C, st));
       {
         EpiParams ep;
         ep.out = b.qkv; ep.out_dtype = DT_F32; ep.ld_out = nqkv;
         SVDD_TRY(gemm_flat(b.hn, blk.wqkv, R, C, nqkv, ep, EPI_GENERIC));
       }
-      ef_attention_kernel<<<(unsigned)rows, 256, 0, st>>>(b.qkv, blk.rcb, blk.rpb,
-                                                          h->relk + (size_t)j * H * P * dk, b.ao, n, H, dk, dv);
-      count_launch();
-      SVDD_LAUNCH_CHECK();
+      SVDD_TRY(launch_attention(b.qkv, blk.rcb, blk.rpb, h->relk + (size_t)j * H * P * dk, b.ao, rows, n, H,
+                                dk, dv, st));
       {
         EpiParams ep;                                // x += to_out(attn)   (:1941-1945)
         ep.bias = blk.bo;
@@ -631,9 +832,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         debug_dump(("ef_ao" + std::to_string(j)).c_str(), b.ao, (size_t)R * H * dv * 2, st);
         debug_dump(("ef_xattn" + std::to_string(j)).c_str(), b.xt, (size_t)R * C * 4, st);
       }
-      ef_ln_kernel<<<(unsigned)R, kLnThreads, 0, st>>>(b.xt, blk.ln2_g, blk.ln2_b, b.hn, C);
-      count_launch();
-      SVDD_LAUNCH_CHECK();
+      SVDD_TRY(launch_ln(b.xt, blk.ln2_g, blk.ln2_b, b.hn, R, C, st));
       {
         EpiParams ep;                                // ReLU(Linear(C, 2C))
         ep.bias = blk.bf1; ep.act = ACT_RELU;

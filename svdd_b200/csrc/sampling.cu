@@ -61,7 +61,43 @@ __device__ __forceinline__ int gumbel_argmax5(const float* q, const float* u) {
   return best;
 }
 
-template <typename Tok, bool kInjected>
+// The same argmax decided with one MUFU log per element and no division, when that is
+// PROVABLY the exact answer; otherwise falls back to gumbel_argmax5.
+//   g~ = 1e-10 - __logf(u + 1e-10) differs from the exact-path g by at most
+//   e = 8e-7 * max(1, g~): __logf is within 2^-21.41 absolute on [0.5, 2] and 3 ulp
+//   elsewhere (CUDA C Programming Guide, intrinsic error table), the exact path's logf and
+//   subtraction within 1.5 ulp.  Candidate w is certainly the exact argmax when, for every
+//   v != w,  q[w] * (g~[v] - e[v]) > q[v] * (g~[w] + e[w]) * (1 + 2^-19)
+//   (cross-multiplied form of key[w] > key[v]; the last factor covers the roundings of the
+//   two products and of the exact path's division).  Exact ties and near-ties fail the test
+//   and take the exact path, so first-index tie-breaking is the reference's.
+__device__ __forceinline__ int gumbel_argmax5_checked(const float* q, const float* u) {
+  float lo[kVocab], hi[kVocab], g[kVocab];
+  bool ok = true;
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) {
+    g[v] = 1e-10f - __logf(__fadd_rn(u[v], 1e-10f));
+    const float e = 8e-7f * fmaxf(g[v], 1.0f);
+    lo[v] = g[v] - e;
+    hi[v] = g[v] + e;
+    ok = ok && (lo[v] > 0.0f);
+  }
+  int best = 0;
+  float bq = q[0], bg = g[0], bhi = hi[0];
+#pragma unroll
+  for (int v = 1; v < kVocab; ++v) {
+    if (q[v] * bg > bq * g[v]) { best = v; bq = q[v]; bg = g[v]; bhi = hi[v]; }
+  }
+  const float rhs_scale = bhi * 1.0000020f;
+  ok = ok && (bq > 1e-20f);        // keeps both products far from the subnormal range
+#pragma unroll
+  for (int v = 0; v < kVocab; ++v) ok = ok && (v == best || bq * lo[v] > q[v] * rhs_scale);
+  return ok ? best : gumbel_argmax5(q, u);
+}
+
+constexpr int kNoiseGroup = 2;   // candidates whose noise is in flight per warp (x2: one being consumed)
+
+template <typename Tok, bool kInjected, bool kFast>
 __global__ void __launch_bounds__(kThreads)
 subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                    const Tok* __restrict__ x, const float* __restrict__ U,
@@ -69,14 +105,14 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                    int64_t row_offset,
                    float mc_t, float mc_s, Tok* __restrict__ cand,
                    float* __restrict__ q_out, int64_t BL, int L, int M) {
-  __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
+  __shared__ float s_stage[kWarpsPerBlock][kNoiseGroup][32 * kVocab];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
   if (pos0 >= BL) return;
   const int64_t pos = pos0 + lane;
   const bool valid = pos < BL;
   const int64_t n_el = BL * kVocab;
-  float* stage = s_stage[warp];
+  float* stage = s_stage[warp][0];
 
   // coalesced load of this warp's 32x5 logits, transposed through smem
   const int64_t e0 = pos0 * kVocab;
@@ -123,30 +159,46 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
   }
 
   if (kInjected) {
-    float pre[kVocab];
-    auto prefetch = [&](int m) {
-      const int64_t b0 = ((int64_t)m * BL + pos0) * kVocab;
-      const int64_t lim = ((int64_t)m + 1) * n_el;
+    // noise of kNoiseGroup candidates is consumed while the next group's loads are in flight
+    float pre[kNoiseGroup][kVocab];
+    auto prefetch = [&](int m0) {
 #pragma unroll
-      for (int k = 0; k < kVocab; ++k) {
-        const int64_t e = b0 + k * 32 + lane;
-        pre[k] = (e < lim) ? __ldg(U + e) : 0.5f;
+      for (int gi = 0; gi < kNoiseGroup; ++gi) {
+        const int m = m0 + gi;
+        if (m < M) {
+          const int64_t b0 = ((int64_t)m * BL + pos0) * kVocab;
+          const int64_t lim = ((int64_t)m + 1) * n_el;
+#pragma unroll
+          for (int k = 0; k < kVocab; ++k) {
+            const int64_t e = b0 + k * 32 + lane;
+            pre[gi][k] = (e < lim) ? __ldg(U + e) : 0.5f;
+          }
+        }
       }
     };
     prefetch(0);
-    for (int m = 0; m < M; ++m) {
+    for (int m0 = 0; m0 < M; m0 += kNoiseGroup) {
 #pragma unroll
-      for (int k = 0; k < kVocab; ++k) stage[k * 32 + lane] = pre[k];
-      __syncwarp();
-      if (m + 1 < M) prefetch(m + 1);
-      float u[kVocab];
+      for (int gi = 0; gi < kNoiseGroup; ++gi)
 #pragma unroll
-      for (int v = 0; v < kVocab; ++v) u[v] = stage[lane * kVocab + v];
+        for (int k = 0; k < kVocab; ++k) s_stage[warp][gi][k * 32 + lane] = pre[gi][k];
       __syncwarp();
-      if (valid) {
-        const int draw = masked ? gumbel_argmax5(q, u) : tok;
-        store_tok(cand, (size_t)m * BL + pos, draw);
+      prefetch(m0 + kNoiseGroup);
+#pragma unroll
+      for (int gi = 0; gi < kNoiseGroup; ++gi) {
+        const int m = m0 + gi;
+        if (m < M && valid) {
+          int draw = tok;
+          if (masked) {
+            float u[kVocab];
+#pragma unroll
+            for (int v = 0; v < kVocab; ++v) u[v] = s_stage[warp][gi][lane * kVocab + v];
+            draw = kFast ? gumbel_argmax5_checked(q, u) : gumbel_argmax5(q, u);
+          }
+          store_tok(cand, (size_t)m * BL + pos, draw);
+        }
       }
+      __syncwarp();
     }
   } else {
     const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
@@ -162,7 +214,7 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
         const float u[kVocab] = {philox_uniform(a.x), philox_uniform(a.y),
                                  philox_uniform(a.z), philox_uniform(a.w),
                                  philox_uniform(e.x)};
-        draw = gumbel_argmax5(q, u);
+        draw = kFast ? gumbel_argmax5_checked(q, u) : gumbel_argmax5(q, u);
       }
       store_tok(cand, (size_t)m * BL + pos, draw);
     }
@@ -333,11 +385,10 @@ int check_device() {
 
 using namespace svdd;
 
-extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
-                                int tok_dtype, const float* U, uint64_t seed,
-                                const uint64_t* seed_dev, int step, int64_t row_offset,
-                                float mc_t, float mc_s, void* cand,
-                                float* q_out, int B, int L, int M, void* stream) {
+namespace {
+int subs_sample_impl(const float* logits, int is_log_p, const void* x, int tok_dtype, const float* U,
+                     uint64_t seed, const uint64_t* seed_dev, int step, int64_t row_offset, float mc_t,
+                     float mc_s, void* cand, float* q_out, int B, int L, int M, bool fast, void* stream) {
   SVDD_CHECK_ARG(B >= 0 && L >= 0 && M >= 1, "svdd_subs_sample: bad shape B=%d L=%d M=%d", B, L, M);
   if ((int64_t)B * L == 0) return SVDD_OK;   // empty batch: nothing to do (pointers may be null)
   SVDD_CHECK_ARG(logits && x && cand, "svdd_subs_sample: null pointer");
@@ -345,19 +396,41 @@ extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
   SVDD_TRY(check_device());
   const int64_t BL = (int64_t)B * L;
-  if (BL == 0) return SVDD_OK;
   const unsigned grid = (unsigned)ceil_div<int64_t>(BL, kThreads);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(Tok, INJ)                                                              \
-  subs_sample_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                            \
+#define LAUNCH(Tok, INJ, FAST)                                                        \
+  subs_sample_kernel<Tok, INJ, FAST><<<grid, kThreads, 0, st>>>(                      \
       logits, is_log_p, (const Tok*)x, U, seed, seed_dev, (uint32_t)step, row_offset, \
       mc_t, mc_s, (Tok*)cand, q_out, BL, L, M)
-  if (tok_dtype == SVDD_TOK_I64) { if (U) LAUNCH(int64_t, true); else LAUNCH(int64_t, false); }
-  else                           { if (U) LAUNCH(uint8_t, true); else LAUNCH(uint8_t, false); }
+#define LAUNCH2(Tok, INJ) do { if (fast) LAUNCH(Tok, INJ, true); else LAUNCH(Tok, INJ, false); } while (0)
+  if (tok_dtype == SVDD_TOK_I64) { if (U) LAUNCH2(int64_t, true); else LAUNCH2(int64_t, false); }
+  else                           { if (U) LAUNCH2(uint8_t, true); else LAUNCH2(uint8_t, false); }
+#undef LAUNCH2
 #undef LAUNCH
   count_launch();
   SVDD_LAUNCH_CHECK();
   return SVDD_OK;
+}
+}  // namespace
+
+extern "C" int svdd_subs_sample(const float* logits, int is_log_p, const void* x,
+                                int tok_dtype, const float* U, uint64_t seed,
+                                const uint64_t* seed_dev, int step, int64_t row_offset,
+                                float mc_t, float mc_s, void* cand,
+                                float* q_out, int B, int L, int M, void* stream) {
+  return subs_sample_impl(logits, is_log_p, x, tok_dtype, U, seed, seed_dev, step, row_offset, mc_t, mc_s,
+                          cand, q_out, B, L, M, /*fast=*/true, stream);
+}
+
+// Test hook: the same stage with every draw taken on the exact (logf + division) path, to
+// check that the verified fast path of svdd_subs_sample never changes a draw.
+extern "C" int svdd_selftest_subs_sample_exact(const float* logits, int is_log_p, const void* x,
+                                               int tok_dtype, const float* U, uint64_t seed,
+                                               const uint64_t* seed_dev, int step, int64_t row_offset,
+                                               float mc_t, float mc_s, void* cand, float* q_out, int B,
+                                               int L, int M, void* stream) {
+  return subs_sample_impl(logits, is_log_p, x, tok_dtype, U, seed, seed_dev, step, row_offset, mc_t, mc_s,
+                          cand, q_out, B, L, M, /*fast=*/false, stream);
 }
 
 extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype, void* out,

@@ -64,6 +64,47 @@ def test_attention_pool_epilogue(cuda, S, L, C):
   assert float((out - ref).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize('S,L,C', [(3, 200, 128), (5, 100, 768), (7, 50, 256), (40, 25, 256), (9, 13, 128),
+                                   (20, 7, 384), (33, 4, 128), (70, 1, 128), (2, 3, 256), (1300, 2, 128)])
+def test_pair_split_difference_pooling(cuda, S, L, C):
+  """EPI_PAIR + EPI_POOL2 (the path svdd_enformer_score takes): the residual 1x1 conv emits
+  y0 = y[2j] and yd = y[2j+1] - y[2j]; ONE GEMM over yd gives the pair softmax.  Checked
+  against the reference formulation (two logits per pair, softmax, weighted sum; the padded
+  slot of an odd length gets -max), incl. ragged tiles and odd lengths."""
+  g = torch.Generator().manual_seed(S * 7 + L)
+  A = torch.randn(S, L, C, generator=g).to(cuda).bfloat16()
+  res = torch.randn(S, L, C, generator=g).to(cuda).bfloat16()
+  W1 = (torch.randn(C, C, generator=g) * C ** -0.5).to(cuda).bfloat16()
+  bias = torch.randn(C, generator=g).to(cuda)
+  Wp = (2 * torch.eye(C) + torch.randn(C, C, generator=g) * C ** -0.5).to(cuda).bfloat16()
+  scale2 = (1 + 0.2 * torch.randn(C, generator=g)).to(cuda)
+  shift2 = (0.3 * torch.randn(C, generator=g)).to(cuda)
+  y0, yd, pooled, pact = _lib.selftest_pair_pool(A, W1, bias, res, Wp, scale2, shift2, want_act=True)
+  torch.cuda.synchronize()
+  y = A.float() @ W1.float().t() + bias + res.float()                     # [S, L, C] fp32
+  Lo = (L + 1) // 2
+  yp = F.pad(y, (0, 0, 0, 2 * Lo - L))
+  ref_y0, ref_y1 = yp[:, 0::2], yp[:, 1::2]
+  ref_yd = ref_y1 - ref_y0
+  if L % 2:
+    ref_yd[:, -1] = 0.0
+  scale = max(1.0, float(y.abs().max()))
+  assert float((y0.float() - ref_y0).abs().max()) < 2e-2 * scale
+  assert float((yd.float() - ref_yd).abs().max()) < 2e-2 * scale
+  # pooling semantics on the kernel's own (bf16) y0 / yd, as the reference formulates them
+  y0f, y1f = y0.float(), y0.float() + yd.float()
+  l0, l1 = y0f @ Wp.float().t(), y1f @ Wp.float().t()
+  if L % 2:
+    l1[:, -1] = -torch.finfo(torch.float32).max
+  w = torch.stack([l0, l1], 2).softmax(dim=2)
+  ref = (torch.stack([y0f, y1f], 2) * w).sum(2).reshape(-1, C)
+  # the logit difference is formed from bf16(yd): |d err| <= 2^-9 |Wp.yd|, sigmoid slope <= 1/4
+  assert float((pooled - ref).abs().max()) < 3e-2 * scale
+  assert float((pooled - ref).abs().mean()) < 2e-3 * scale
+  ref_act = _act(ref * scale2 + shift2, 2)
+  assert float((pact.float() - ref_act).abs().max()) < 4e-2 * max(1.0, float(ref_act.abs().max()))
+
+
 def test_relative_position_basis_matches_oracle():
   from oracle import enformer_shim
   for n, Fdim in [(2, 192), (2, 48), (4, 96), (7, 192)]:

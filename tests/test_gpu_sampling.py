@@ -105,6 +105,44 @@ def test_stage2_large_property(cuda):
   assert int(bad.sum()) <= 4, int(bad.sum())
 
 
+@pytest.mark.parametrize('tok_dtype', [torch.int64, torch.uint8])
+def test_stage2_fast_path_equals_exact_path(cuda, tok_dtype):
+  """svdd_subs_sample decides a draw with approximate logs only when an error-bound test
+  proves the exact argmax; it must therefore agree bit for bit with the all-exact kernel --
+  on random inputs at BASELINE config-4 per-GPU size and on adversarial inputs built to sit
+  on ties and near-ties (equal keys, keys 1 ulp apart, u next to 0 and to 1)."""
+  sched, _ = svdd.move_chances(128, 1e-5)
+  g = torch.Generator().manual_seed(123)
+  B, L, M = 512, 200, 20
+  logits = (torch.randn(B, L, 5, generator=g) * 3).to(cuda)
+  x = helpers.random_tokens(B, L, 10, 0.7).to(cuda).to(tok_dtype)
+  U = torch.rand(M, B, L, 5, generator=g).to(cuda)
+  for step in (0, 64, 127):
+    a = _lib.subs_sample(logits, x, M, sched[step, 0], sched[step, 1], U=U)
+    b = _lib.subs_sample(logits, x, M, sched[step, 0], sched[step, 1], U=U, exact=True)
+    assert torch.equal(a, b), step
+  # adversarial: flat logits (equal q over the 4 bases) and noise with repeated / adjacent values
+  B, L, M = 64, 200, 16
+  x = torch.full((B, L), 4, dtype=tok_dtype, device=cuda)
+  logits = torch.zeros(B, L, 5, device=cuda)
+  base = torch.rand(M, B, L, 1, generator=g).expand(M, B, L, 5).clone()
+  ulp = torch.tensor(2.0 ** -24)
+  U = base.clone()
+  U[..., 1] = torch.nextafter(base[..., 1], torch.tensor(1.0))        # 1 ulp above
+  U[..., 2] = torch.nextafter(base[..., 2], torch.tensor(0.0))        # 1 ulp below
+  U[0::4, ..., :] = base[0::4]                                        # exact ties -> first index
+  U[1::4, ..., 3] = 1.0 - ulp                                         # g ~ 6e-8: tiny denominators
+  U[2::4, ..., 0] = 0.0                                               # g = 23.03: largest denominator
+  U[3::4, ..., 4] = torch.rand(M // 4, B, L, generator=g) * 1e-6 + (1.0 - 1e-6 - ulp)
+  U = U.clamp_(0.0, float(1.0 - ulp)).to(cuda)
+  for step in (0, 100, 127):
+    a = _lib.subs_sample(logits, x, M, sched[step, 0], sched[step, 1], U=U)
+    b = _lib.subs_sample(logits, x, M, sched[step, 0], sched[step, 1], U=U, exact=True)
+    assert torch.equal(a, b), step
+  # exact ties resolve to the first index, as torch.argmax does
+  assert int(a[0].max()) == 0
+
+
 def test_stage2_philox_stream(cuda):
   """U == NULL: the in-kernel Philox stream equals oracle/philox.py, is
   independent of how rows are sharded, and differs per step / seed."""

@@ -52,7 +52,13 @@ for i in range(7):
   C = filters[i]
   if i > 0:
     cmp(f'z{i}', load(f'ef_z{i}', (N, L, C), 'bf16'), rec[f'z{i}'].permute(0, 2, 1), f'z{i}')
-  cmp(f'y{i}', load(f'ef_y{i}', (N, L, C), 'bf16'), rec[f'y{i}'].permute(0, 2, 1), f'y{i}')
+  if os.path.exists(os.path.join(d, f'ef_y{i}.bin')):
+    cmp(f'y{i}', load(f'ef_y{i}', (N, L, C), 'bf16'), rec[f'y{i}'].permute(0, 2, 1), f'y{i}')
+  else:    # pair path: y0 = y[2j], yd = y[2j+1] - y[2j] at half length
+    Lo = (L + 1) // 2
+    y0, yd = load(f'ef_y0_{i}', (N, Lo, C), 'bf16'), load(f'ef_yd_{i}', (N, Lo, C), 'bf16')
+    y = torch.stack([y0, y0 + yd], 2).reshape(N, 2 * Lo, C)[:, :L]
+    cmp(f'y{i}', y, rec[f'y{i}'].permute(0, 2, 1), f'y{i}')
   L = (L + 1) // 2
   if i == 6:
     cmp('xt_in', load('ef_xt_in', (N, L, C), 'f32'), rec['y6_pooled'].permute(0, 2, 1), 'y6_pooled')
