@@ -20,6 +20,12 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SVDD_PDL"); on = e ? (atoi(e) != 0) : 1; }
+  return on == 1;
+}
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool debug_dump_enabled() {

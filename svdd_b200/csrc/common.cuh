@@ -66,6 +66,44 @@ inline int num_sms() {
   return n;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// Every kernel of a reverse step is launched with programmatic stream serialisation: its
+// CTAs may become resident (barrier init, TMEM allocation, tensor-map prefetch) while the
+// previous kernel drains, and block in pdl_wait() until that kernel's memory is visible.
+// Rule: a kernel launched through launch_k() calls pdl_wait() before its first access to
+// global memory another kernel may have written (or may still be reading).
+// SVDD_PDL=0 turns the launch attribute off (pdl_wait() is then a no-op).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            int cluster_x, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 constexpr int kMaskIndex = 4;            // diffusion_gosai.py:85,94-95
 constexpr int kVocab = 5;                // A,C,G,T,MASK
 constexpr float kNegInfinity = -1000000.0f;  // diffusion_gosai.py:156

@@ -90,9 +90,9 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape&
     SVDD_CUDA(cudaEventCreate(&e1));
     SVDD_CUDA(cudaEventRecord(e0, stream));
   }
-  kern<<<grid, gemm_detail::kThreads, C::kSmemBytes, stream>>>(tmA, tmW, g, ep);
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm_detail::kThreads), C::kSmemBytes, stream, 1,
+                     tmA, tmW, g, ep));
   count_launch();
-  SVDD_LAUNCH_CHECK();
   if (P.on) {
     SVDD_CUDA(cudaEventRecord(e1, stream));
     std::lock_guard<std::mutex> lk(P.mu);
@@ -161,19 +161,8 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     SVDD_CUDA(cudaEventCreate(&e1));
     SVDD_CUDA(cudaEventRecord(e0, stream));
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(gemm2::kThreads, 1, 1);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CG;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  SVDD_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmO, tmO2, tmR, tmR2, g, ep));
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm2::kThreads), C::kSmemBytes, stream, CG,
+                     tmA, tmW, tmO, tmO2, tmR, tmR2, g, ep));
   count_launch();
   if (P.on) {
     SVDD_CUDA(cudaEventRecord(e1, stream));
@@ -246,6 +235,11 @@ void choose_row_tiling(int L, int taps, GemmShape* g) {
   g->BS = 128 / best_bl;
 }
 
+static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g, int mode, const EpiParams& ep_in,
+                               cudaStream_t stream);
+static int launch_gemm1(const void* A, const void* W, const GemmShape& g, int mode, const EpiParams& ep_in,
+                        cudaStream_t stream);
+
 int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
                      const EpiParams& ep_in, cudaStream_t stream) {
   SVDD_CHECK_ARG(g.K > 0 && g.K % 64 == 0, "conv_gemm: K=%d must be a positive multiple of 64", g.K);
@@ -257,6 +251,31 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   if (g.S == 0 || g.L == 0) return SVDD_OK;
 
   if (gemm2_handles(g, mode, ep_in)) {
+    // N = 896 / 1152 (not a multiple of 256): two launches over column windows, 256-wide tiles
+    // for the first floor(N/256)*256 columns and 128-wide tiles for the rest, instead of
+    // 128-wide tiles everywhere (the k5 convs run at 0.85 vs 1.45 PFLOP/s on the two widths).
+    static int nsplit = -1;
+    if (nsplit < 0) { const char* e = getenv("SVDD_NSPLIT"); nsplit = e ? atoi(e) : 1; }
+    GemmShape gw = g;
+    gw.N_w = g.N;
+    gw.n_off = 0;
+    if (nsplit && mode != EPI_HEADDOT && g.N > 256 && g.N % 256 == 128) {
+      GemmShape ga = gw;
+      ga.N = (g.N / 256) * 256;
+      if (pick_bn2(ga, gemm2_cg()) == 256) {
+        SVDD_TRY(launch_gemm2_window(A, W, ga, mode, ep_in, stream));
+        gw.n_off = ga.N;
+        gw.N = g.N - ga.N;
+      }
+    }
+    return launch_gemm2_window(A, W, gw, mode, ep_in, stream);
+  }
+  return launch_gemm1(A, W, g, mode, ep_in, stream);
+}
+
+static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g, int mode, const EpiParams& ep_in,
+                               cudaStream_t stream) {
+  {
     const int cg = gemm2_cg();
     const int bn2 = pick_bn2(g, cg);
     EpiParams ep2 = ep_in;
@@ -267,7 +286,7 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
       const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.L_in * g.K * 2};
       const cuuint32_t box[3] = {64, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
       SVDD_TRY(encode_bf16_map(&tA, A, 3, dims, str, box));
-      const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.N};
+      const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.N_w};
       const cuuint64_t ws[1] = {(cuuint64_t)g.K * 2};
       const cuuint32_t wb[2] = {64, (cuuint32_t)(bn2 / cg)};
       SVDD_TRY(encode_bf16_map(&tW, W, 2, wd, ws, wb));
@@ -276,7 +295,7 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
     auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l) -> int {
       if (p == nullptr) { *m = tA; return SVDD_OK; }
       const cuuint64_t es = dt == DT_F32 ? 4 : 2;
-      const cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)Lr, (cuuint64_t)g.S};
+      const cuuint64_t dims[3] = {(cuuint64_t)g.N_w, (cuuint64_t)Lr, (cuuint64_t)g.S};
       const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)Lr * ld * es};
       const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_l, (cuuint32_t)g.BS};
       return encode_map(m, dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3,
@@ -328,6 +347,10 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
     set_last_error("conv_gemm: no gemm2 kernel for BN=%d mode=%d", bn2, mode);
     return SVDD_ERR_INTERNAL;
   }
+}
+
+static int launch_gemm1(const void* A, const void* W, const GemmShape& g, int mode, const EpiParams& ep_in,
+                        cudaStream_t stream) {
   const int bn = pick_bn(g, mode);
   SVDD_CHECK_ARG(g.N % bn == 0, "conv_gemm: N=%d not divisible by tile %d", g.N, bn);
   if (mode == EPI_DEN_LN || mode == EPI_DEN_FINAL)

@@ -85,6 +85,9 @@ struct GemmShape {
   int K = 0, N = 0;
   int taps = 1, dil = 1;
   int BL = 128, BS = 1;  // tile = BL positions x BS sequences (BL*BS <= 128)
+  // column window of one launch (conv_gemm2 only): this launch computes columns
+  // [n_off, n_off + N) of a weight / output that is N_w columns wide (0 = N)
+  int n_off = 0, N_w = 0;
 };
 
 namespace gemm_detail {
@@ -269,6 +272,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // everything above overlapped the previous kernel's tail
+  pdl_trigger();
 
   auto tile_coords = [&](int64_t t, int& n0, int& s0, int& l0) {
     const int nt = (int)(t % n_tiles);

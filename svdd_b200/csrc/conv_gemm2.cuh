@@ -311,13 +311,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // everything above overlapped the previous kernel's tail
+  pdl_trigger();
 
   // coordinates of this CTA's half of pair-tile `t` (rr = rank within the pair)
   auto tile_coords = [&](int64_t t, int rr) {
     TileCoord c;
     const int nt = (int)(t % n_tiles);
     const int64_t mt = (t / n_tiles) * CG + rr;
-    c.n0 = nt * BN;
+    c.n0 = g.n_off + nt * BN;    // global column
     c.in_range = mt < m_tiles;
     c.s0 = (int)(mt / tiles_l) * g.BS;       // >= S when out of range: TMA zero-fills / clips
     c.l0 = (int)(mt % tiles_l) * g.BL;
@@ -351,7 +353,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint8_t* sb = sa + C::kABytes;
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_3d_cg<CG>(sa, &tmA, &full_bar[stage], kb * kBK, l_start, c.s0);
-            tma_load_2d_cg<CG>(sb, &tmW, &full_bar[stage], kb * kBK, tap * g.N + c.n0 + rank * (BN / CG));
+            tma_load_2d_cg<CG>(sb, &tmW, &full_bar[stage], kb * kBK, tap * g.N_w + c.n0 + rank * (BN / CG));
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -548,7 +550,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       if (MODE == EPI_HEADDOT && valid)
-        ep.partials[row * (2 * n_tiles) + 2 * (n0 / BN) + half] = head_acc;
+        ep.partials[row * (2 * n_tiles) + 2 * ((n0 - g.n_off) / BN) + half] = head_acc;
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else {

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256)
 cg_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[taps][4][64]*/,
                 const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t NL, int L,
                 int taps) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(8) float s_w[kStemTapsMax * 4 * kC];
   for (int i = threadIdx.x; i < taps * 4 * kC; i += blockDim.x) s_w[i] = w[i];
   __syncthreads();
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(kG3)
 cg_gru_kernel(const float* __restrict__ gi, const float* __restrict__ whh /*[2][192][64]*/,
               const float* __restrict__ bhn /*[2][64]*/, float* __restrict__ y /*[2][rows*L][64]*/,
               int64_t rows, int L) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float s_h[kSeq][kC];
   __shared__ float s_g[kSeq][kG3];
   const int dir = blockIdx.y;
@@ -146,6 +150,8 @@ cg_gru_kernel(const float* __restrict__ gi, const float* __restrict__ whh /*[2][
 __global__ void __launch_bounds__(256)
 cg_ln_kernel(const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ b,
              __nv_bfloat16* __restrict__ out, int64_t NL) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos = (int64_t)blockIdx.x * 8 + warp;
   if (pos >= NL) return;
@@ -169,6 +175,8 @@ cg_ln_kernel(const float* __restrict__ y, const float* __restrict__ g, const flo
 // score[n] = const + mean_l sum_tiles partials[(n*L+l), tile]
 __global__ void cg_mean_kernel(const float* __restrict__ partials, int n_tiles, float bias_const,
                                float* __restrict__ scores, int64_t rows, int L) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= rows) return;
   float s = 0.0f;
@@ -413,9 +421,9 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
     const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)r0 * L * tok_bytes;
     const unsigned eg = (unsigned)ceil_div<int64_t>(NL, 64);
     if (tok_dtype == SVDD_TOK_I64)
-      cg_embed_kernel<int64_t><<<eg, 256, 0, st>>>((const int64_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
+      launch_k(cg_embed_kernel<int64_t>, dim3(eg), dim3(256), 0, st, 1, (const int64_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
     else
-      cg_embed_kernel<uint8_t><<<eg, 256, 0, st>>>((const uint8_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
+      launch_k(cg_embed_kernel<uint8_t>, dim3(eg), dim3(256), 0, st, 1, (const uint8_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
     count_launch();
     SVDD_LAUNCH_CHECK();
     int cur = 0;
@@ -440,10 +448,10 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
       ep.out = b.gi; ep.out_dtype = DT_F32; ep.ld_out = 2 * kG3;
       SVDD_TRY(launch_conv_gemm(b.x[cur], h->wih, g, EPI_GENERIC, ep, st));
     }
-    cg_gru_kernel<<<dim3((unsigned)ceil_div<int64_t>(rows, kSeq), 2), kG3, 0, st>>>(b.gi, h->whh, h->bhn, b.y, rows, L);
+    launch_k(cg_gru_kernel, dim3(dim3((unsigned)ceil_div<int64_t>(rows, kSeq), 2)), dim3(kG3), 0, st, 1, b.gi, h->whh, h->bhn, b.y, rows, L);
     count_launch();
     SVDD_LAUNCH_CHECK();
-    cg_ln_kernel<<<(unsigned)ceil_div<int64_t>(NL, 8), 256, 0, st>>>(b.y, h->ln_g, h->ln_b, b.z, NL);
+    launch_k(cg_ln_kernel, dim3((unsigned)ceil_div<int64_t>(NL, 8)), dim3(256), 0, st, 1, b.y, h->ln_g, h->ln_b, b.z, NL);
     count_launch();
     SVDD_LAUNCH_CHECK();
     int n_tiles = 1;
@@ -458,7 +466,7 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
       n_tiles = conv_gemm_n_tiles(g, EPI_HEADDOT);
       SVDD_TRY(launch_conv_gemm(b.z, h->w1, g, EPI_HEADDOT, ep, st));
     }
-    cg_mean_kernel<<<(unsigned)ceil_div<int64_t>(rows, 128), 128, 0, st>>>(b.partials, n_tiles, h->head_const,
+    launch_k(cg_mean_kernel, dim3((unsigned)ceil_div<int64_t>(rows, 128)), dim3(128), 0, st, 1, b.partials, n_tiles, h->head_const,
                                                                            scores + r0, rows, L);
     count_launch();
     SVDD_LAUNCH_CHECK();

@@ -29,6 +29,8 @@ den_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[
                  const float* __restrict__ b, const float* __restrict__ tbias0,
                  const float* __restrict__ g0, const float* __restrict__ be0,
                  float* __restrict__ feat, __nv_bfloat16* __restrict__ h, int64_t NL, int L) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float s_w[kTaps * kVocab * kH];
   for (int i = threadIdx.x; i < kTaps * kVocab * kH; i += blockDim.x) s_w[i] = w[i];
   __syncthreads();
@@ -225,10 +227,10 @@ extern "C" int svdd_denoiser_forward(svdd_denoiser* h, const void* tokens, int t
 
   const unsigned grid = (unsigned)ceil_div<int64_t>(NL, kEmbedWarps * kEmbedPosPerWarp);
   if (tok_dtype == SVDD_TOK_I64)
-    den_embed_kernel<int64_t><<<grid, kEmbedWarps * 32, 0, st>>>(
+    launch_k(den_embed_kernel<int64_t>, dim3(grid), dim3(kEmbedWarps * 32), 0, st, 1, 
         (const int64_t*)tokens, h->embed_w, h->embed_b, time_bias, h->ln_g, h->ln_b, feat, hbuf[0], NL, L);
   else
-    den_embed_kernel<uint8_t><<<grid, kEmbedWarps * 32, 0, st>>>(
+    launch_k(den_embed_kernel<uint8_t>, dim3(grid), dim3(kEmbedWarps * 32), 0, st, 1, 
         (const uint8_t*)tokens, h->embed_w, h->embed_b, time_bias, h->ln_g, h->ln_b, feat, hbuf[0], NL, L);
   count_launch();
   SVDD_LAUNCH_CHECK();

@@ -39,6 +39,8 @@ constexpr int kMaxPos = 8;       // positions entering the transformer (2 for L=
 template <typename Tok>
 __global__ void ef_im2col_kernel(const Tok* __restrict__ tokens, __nv_bfloat16* __restrict__ col,
                                  int64_t NL, int L, int taps) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NL * 8) return;
   const int64_t pos = i >> 3;
@@ -73,6 +75,8 @@ constexpr int kLnMaxPer = 16;   // C <= 4096
 __global__ void __launch_bounds__(kLnThreads)
 ef_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
              __nv_bfloat16* __restrict__ out, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_red[kLnThreads / 32];
   __shared__ float s_stat;
   const int64_t row = blockIdx.x;
@@ -115,6 +119,8 @@ constexpr int kLnWarpsPerBlock = 8;
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 ef_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                   __nv_bfloat16* __restrict__ out, int64_t rows, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -160,10 +166,10 @@ ef_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g, cons
 int launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* out, int64_t rows, int C,
               cudaStream_t st) {
   if (C % 128 == 0 && C <= 128 * kLnWarpVecs)
-    ef_ln_warp_kernel<<<(unsigned)ceil_div<int64_t>(rows, kLnWarpsPerBlock), kLnWarpsPerBlock * 32, 0, st>>>(
+    launch_k(ef_ln_warp_kernel, dim3((unsigned)ceil_div<int64_t>(rows, kLnWarpsPerBlock)), dim3(kLnWarpsPerBlock * 32), 0, st, 1, 
         x, g, b, out, rows, C);
   else
-    ef_ln_kernel<<<(unsigned)rows, kLnThreads, 0, st>>>(x, g, b, out, C);
+    launch_k(ef_ln_kernel, dim3((unsigned)rows), dim3(kLnThreads), 0, st, 1, x, g, b, out, C);
   count_launch();
   SVDD_LAUNCH_CHECK();
   return SVDD_OK;
@@ -176,6 +182,8 @@ __global__ void __launch_bounds__(256)
 ef_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb,
                     const float* __restrict__ rpb, const float* __restrict__ relk,
                     __nv_bfloat16* __restrict__ out, int n, int H, int dk, int dv) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_attn[8][kMaxPos][kMaxPos];   // H <= 8 per pass
   const int64_t seq = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,6 +240,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 ef_attention_warp_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb,
                          const float* __restrict__ rpb, const float* __restrict__ relk,
                          __nv_bfloat16* __restrict__ out, int64_t rows, int H, int dk, int dv) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (w >= rows * H) return;
@@ -300,15 +310,15 @@ int launch_attention(const float* qkv, const float* rcb, const float* rpb, const
                      __nv_bfloat16* out, int64_t rows, int n, int H, int dk, int dv, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div<int64_t>(rows * H, kAttnWarps);
   if (dk <= 32 * kAttnDkPer && n == 1)
-    ef_attention_warp_kernel<1><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+    launch_k(ef_attention_warp_kernel<1>, dim3(grid), dim3(kAttnWarps * 32), 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
   else if (dk <= 32 * kAttnDkPer && n == 2)
-    ef_attention_warp_kernel<2><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+    launch_k(ef_attention_warp_kernel<2>, dim3(grid), dim3(kAttnWarps * 32), 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
   else if (dk <= 32 * kAttnDkPer && n == 3)
-    ef_attention_warp_kernel<3><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+    launch_k(ef_attention_warp_kernel<3>, dim3(grid), dim3(kAttnWarps * 32), 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
   else if (dk <= 32 * kAttnDkPer && n == 4)
-    ef_attention_warp_kernel<4><<<grid, kAttnWarps * 32, 0, st>>>(qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+    launch_k(ef_attention_warp_kernel<4>, dim3(grid), dim3(kAttnWarps * 32), 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
   else
-    ef_attention_kernel<<<(unsigned)rows, 256, 0, st>>>(qkv, rcb, rpb, relk, out, n, H, dk, dv);
+    launch_k(ef_attention_kernel, dim3((unsigned)rows), dim3(256), 0, st, 1, qkv, rcb, rpb, relk, out, n, H, dk, dv);
   count_launch();
   SVDD_LAUNCH_CHECK();
   return SVDD_OK;
@@ -330,6 +340,8 @@ __global__ void ef_relk_kernel(const float* __restrict__ w, const float* __restr
 // score[s] = head_b + mean_p sum_tiles partials[(s*n+p), tile]
 __global__ void ef_mean_kernel(const float* __restrict__ partials, int n_tiles, const float* __restrict__ hb,
                                float* __restrict__ scores, int64_t rows, int n) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= rows) return;
   float acc = 0.0f;
@@ -691,9 +703,9 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
     {
       const unsigned grid = (unsigned)ceil_div<int64_t>(NL * 8, 256);
       if (tok_dtype == SVDD_TOK_I64)
-        ef_im2col_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)tok, b.col, NL, L, h->stem_taps);
+        launch_k(ef_im2col_kernel<int64_t>, dim3(grid), dim3(256), 0, st, 1, (const int64_t*)tok, b.col, NL, L, h->stem_taps);
       else
-        ef_im2col_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)tok, b.col, NL, L, h->stem_taps);
+        launch_k(ef_im2col_kernel<uint8_t>, dim3(grid), dim3(256), 0, st, 1, (const uint8_t*)tok, b.col, NL, L, h->stem_taps);
       count_launch();
       SVDD_LAUNCH_CHECK();
     }
@@ -868,7 +880,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
       n_tiles = conv_gemm_n_tiles(g, EPI_HEADDOT);
       SVDD_TRY(launch_conv_gemm(b.hn, h->wpw, g, EPI_HEADDOT, ep, st));
     }
-    ef_mean_kernel<<<(unsigned)ceil_div<int64_t>(rows, 128), 128, 0, st>>>(b.partials, n_tiles, h->hb,
+    launch_k(ef_mean_kernel, dim3((unsigned)ceil_div<int64_t>(rows, 128)), dim3(128), 0, st, 1, b.partials, n_tiles, h->hb,
                                                                            scores + r0, rows, n);
     count_launch();
     SVDD_LAUNCH_CHECK();

@@ -105,6 +105,8 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                    int64_t row_offset,
                    float mc_t, float mc_s, Tok* __restrict__ cand,
                    float* __restrict__ q_out, int64_t BL, int L, int M) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_stage[kWarpsPerBlock][kNoiseGroup][32 * kVocab];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
@@ -226,6 +228,8 @@ template <typename Tok>
 __global__ void __launch_bounds__(kThreads)
 x0_argmax_kernel(const float* __restrict__ logits, const Tok* __restrict__ x,
                  Tok* __restrict__ out, int64_t NL) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
@@ -257,6 +261,8 @@ template <typename Tok>
 __global__ void __launch_bounds__(kThreads)
 subs_log_p_kernel(const float* __restrict__ logits, const Tok* __restrict__ x,
                   float* __restrict__ out, int64_t NL) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
@@ -301,6 +307,8 @@ select_gather_kernel(const float* __restrict__ scores, const Tok* __restrict__ c
                      const uint64_t* __restrict__ seed_dev, uint32_t step, int64_t row_offset,
                      Tok* __restrict__ x_out, int32_t* __restrict__ idx_out, int B,
                      int L, int M, int lanes, int iters) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerBlock + warp;
   if (b >= B) return;
@@ -399,7 +407,7 @@ int subs_sample_impl(const float* logits, int is_log_p, const void* x, int tok_d
   const unsigned grid = (unsigned)ceil_div<int64_t>(BL, kThreads);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(Tok, INJ, FAST)                                                        \
-  subs_sample_kernel<Tok, INJ, FAST><<<grid, kThreads, 0, st>>>(                      \
+  launch_k((subs_sample_kernel<Tok, INJ, FAST>), dim3(grid), dim3(kThreads), 0, st, 1,                       \
       logits, is_log_p, (const Tok*)x, U, seed, seed_dev, (uint32_t)step, row_offset, \
       mc_t, mc_s, (Tok*)cand, q_out, BL, L, M)
 #define LAUNCH2(Tok, INJ) do { if (fast) LAUNCH(Tok, INJ, true); else LAUNCH(Tok, INJ, false); } while (0)
@@ -445,9 +453,9 @@ extern "C" int svdd_x0_argmax(const float* logits, const void* x, int tok_dtype,
   const unsigned grid = (unsigned)ceil_div<int64_t>(NL, kThreads);
   cudaStream_t st = (cudaStream_t)stream;
   if (tok_dtype == SVDD_TOK_I64)
-    x0_argmax_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)x, (int64_t*)out, NL);
+    launch_k(x0_argmax_kernel<int64_t>, dim3(grid), dim3(kThreads), 0, st, 1, logits, (const int64_t*)x, (int64_t*)out, NL);
   else
-    x0_argmax_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)x, (uint8_t*)out, NL);
+    launch_k(x0_argmax_kernel<uint8_t>, dim3(grid), dim3(kThreads), 0, st, 1, logits, (const uint8_t*)x, (uint8_t*)out, NL);
   count_launch();
   SVDD_LAUNCH_CHECK();
   return SVDD_OK;
@@ -465,9 +473,9 @@ extern "C" int svdd_subs_log_p(const float* logits, const void* x, int tok_dtype
   const unsigned grid = (unsigned)ceil_div<int64_t>(NL, kThreads);
   cudaStream_t st = (cudaStream_t)stream;
   if (tok_dtype == SVDD_TOK_I64)
-    subs_log_p_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)x, log_p, NL);
+    launch_k(subs_log_p_kernel<int64_t>, dim3(grid), dim3(kThreads), 0, st, 1, logits, (const int64_t*)x, log_p, NL);
   else
-    subs_log_p_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)x, log_p, NL);
+    launch_k(subs_log_p_kernel<uint8_t>, dim3(grid), dim3(kThreads), 0, st, 1, logits, (const uint8_t*)x, log_p, NL);
   count_launch();
   SVDD_LAUNCH_CHECK();
   return SVDD_OK;
@@ -493,7 +501,7 @@ extern "C" int svdd_select_gather(const float* scores, const void* cand, int tok
   const unsigned grid = (unsigned)ceil_div(B, kWarpsPerBlock);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(Tok, INJ)                                                               \
-  select_gather_kernel<Tok, INJ><<<grid, kThreads, 0, st>>>(                           \
+  launch_k((select_gather_kernel<Tok, INJ>), dim3(grid), dim3(kThreads), 0, st, 1,                            \
       scores, (const Tok*)cand, alpha, U_sel, seed, seed_dev, (uint32_t)step,         \
       row_offset, (Tok*)x_out, idx_out, B, L, M, lanes, iters)
   const bool inj = U_sel != nullptr;

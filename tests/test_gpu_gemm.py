@@ -24,6 +24,8 @@ CASES = [
     (300, 2, 1536, 2560, 1, 1),    # fused QKV projection
     (300, 2, 3072, 1536, 1, 1),
     (1, 1, 64, 64, 1, 1),
+    (80, 50, 256, 896, 5, 1),      # N = 3*256 + 128: two column windows (256- and 128-wide tiles)
+    (60, 100, 128, 1152, 1, 1),
 ]
 
 
@@ -65,7 +67,8 @@ def test_attention_pool_epilogue(cuda, S, L, C):
 
 
 @pytest.mark.parametrize('S,L,C', [(3, 200, 128), (5, 100, 768), (7, 50, 256), (40, 25, 256), (9, 13, 128),
-                                   (20, 7, 384), (33, 4, 128), (70, 1, 128), (2, 3, 256), (1300, 2, 128)])
+                                   (20, 7, 384), (33, 4, 128), (70, 1, 128), (2, 3, 256), (1300, 2, 128),
+                                   (64, 50, 896), (200, 13, 1152)])
 def test_pair_split_difference_pooling(cuda, S, L, C):
   """EPI_PAIR + EPI_POOL2 (the path svdd_enformer_score takes): the residual 1x1 conv emits
   y0 = y[2j] and yd = y[2j+1] - y[2j]; ONE GEMM over yd gives the pair softmax.  Checked
@@ -154,6 +157,8 @@ EPI_CASES = [
     (3, 200, 128, 128, 9, False, torch.float32, True, False, 1, True, False),     # activation after the residual
     (1, 130, 128, 384, 1, True, torch.bfloat16, True, False, 2, False, True),     # 2 row tiles, second nearly empty
     (1, 1, 64, 128, 1, True, torch.float32, False, False, 0, False, False),
+    (80, 50, 256, 896, 5, False, torch.bfloat16, False, True, 0, False, True),    # column windows, two outputs
+    (60, 100, 128, 1152, 1, True, torch.bfloat16, True, False, 2, False, False),  # column windows, residual
 ]
 
 
