@@ -289,13 +289,9 @@ def main():
                 'frac': achieved / pk['tf_sust'], 'traffic': None, 'peak_source': pk['src'] + ', sustained',
                 'launches': gemm_n, 'flops_per_step': gemm_flops, 'gemm_ms_per_step': gemm_ms,
                 'share_of_step': gemm_ms / step_ms if step_ms > 0 else None}
-    # HBM-bound stages at the per-GPU size of BASELINE config 4 (B=4096/8, M=20): algorithmic bytes
+    # HBM-bound stages at BASELINE config 4 (B=4096, M=20): the whole batch on one GPU and the
+    # per-GPU shard at N=8; algorithmic bytes in the reference's dtypes
     sched_mc = (0.5, 0.49)
-    Bc, Mc = 512, 20
-    lg = torch.randn(Bc, L, 5, device=device)
-    xs = torch.full((Bc, L), 4, dtype=torch.int64, device=device)
-    U = torch.rand(Mc, Bc, L, 5, device=device)
-    sc = torch.randn(Mc, Bc, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def timed(fn, reps=10):
@@ -307,17 +303,24 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
       return statistics.median(ts)
-    cand64 = _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U)
-    t2 = timed(lambda: _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U, out=cand64))
-    bytes2 = Bc * L * (28 + 28 * Mc)
-    t4 = timed(lambda: _lib.select_gather(sc, cand64))
-    bytes4 = Bc * (4 * Mc + 16 * L)
-    for name, t, nb in (('stage2_subs_sample', t2, bytes2), ('stage4_select_gather', t4, bytes4)):
-      ach = nb / (t * 1e-3) / 1e9
-      stage_rooflines[name] = {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
-                               'frac': ach / pk['hbm'], 'algorithmic_bytes': nb, 'ms': t,
-                               'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 flushed'}
-    del flush, U, lg
+    for tag, Bc, Mc in (('c4_1gpu', 4096, 20), ('c4_shard_of_8', 512, 20)):
+      lg = torch.randn(Bc, L, 5, device=device)
+      xs = torch.full((Bc, L), 4, dtype=torch.int64, device=device)
+      U = torch.rand(Mc, Bc, L, 5, device=device)
+      sc = torch.randn(Mc, Bc, device=device)
+      cand64 = _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U)
+      t2 = timed(lambda: _lib.subs_sample(lg, xs, Mc, *sched_mc, U=U, out=cand64))
+      bytes2 = Bc * L * (28 + 28 * Mc)
+      t4 = timed(lambda: _lib.select_gather(sc, cand64))
+      bytes4 = Bc * (4 * Mc + 16 * L)
+      for name, t, nb in (('stage2_subs_sample', t2, bytes2), ('stage4_select_gather', t4, bytes4)):
+        ach = nb / (t * 1e-3) / 1e9
+        stage_rooflines[f'{name}@{tag}'] = {
+            'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+            'algorithmic_bytes': nb, 'ms': t,
+            'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 flushed, one launch'}
+      del U, lg, xs, sc, cand64
+    del flush
 
   # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
   cpu = None

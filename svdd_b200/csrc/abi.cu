@@ -22,7 +22,7 @@ void set_last_error(const char* fmt, ...) {
 
 bool pdl_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("SVDD_PDL"); on = e ? (atoi(e) != 0) : 1; }
+  if (on < 0) { const char* e = getenv("SVDD_PDL"); on = e ? (atoi(e) != 0) : 0; }
   return on == 1;
 }
 

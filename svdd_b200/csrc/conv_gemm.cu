@@ -169,7 +169,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     std::lock_guard<std::mutex> lk(P.mu);
     P.ev.push_back(e0);
     P.ev.push_back(e1);
-    const double fl = 2.0 * (double)g.S * g.L * (double)g.N * g.K * g.taps;
+    const double fl = 2.0 * (double)g.S * g.L * (double)g.N * ((double)g.K * g.taps + g.K2);
     P.flops += fl;
     P.recs.push_back({g, BN + 1000 * CG, MODE, fl});
   }
@@ -209,6 +209,14 @@ int pick_bn2(const GemmShape& g, int cg) {
 }
 
 }  // namespace
+
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                        uint32_t box_inner, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t str[1] = {(cuuint64_t)inner * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  return encode_bf16_map(map, base, 2, dims, str, box);
+}
 
 int conv_gemm_n_tiles(const GemmShape& g, int mode) {
   if (mode == EPI_HEADDOT && gemm2_enabled() && g.N % 128 == 0) return 2 * (g.N / pick_bn2(g, gemm2_cg()));
@@ -251,15 +259,17 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
   if (g.S == 0 || g.L == 0) return SVDD_OK;
 
   if (gemm2_handles(g, mode, ep_in)) {
-    // N = 896 / 1152 (not a multiple of 256): two launches over column windows, 256-wide tiles
-    // for the first floor(N/256)*256 columns and 128-wide tiles for the rest, instead of
-    // 128-wide tiles everywhere (the k5 convs run at 0.85 vs 1.45 PFLOP/s on the two widths).
+    // k5 convs with N = 896 / 1152 (not a multiple of 256): two launches over column windows,
+    // 256-wide tiles for the first floor(N/256)*256 columns and 128-wide tiles for the rest,
+    // instead of 128-wide tiles everywhere (0.85 vs 1.45 PFLOP/s on the two widths; measured
+    // 516 -> 369 us and 244 -> 175 us on the c2 step).  The short-K 1x1 GEMMs lose on the extra
+    // launch and stay on one width.
     static int nsplit = -1;
     if (nsplit < 0) { const char* e = getenv("SVDD_NSPLIT"); nsplit = e ? atoi(e) : 1; }
     GemmShape gw = g;
     gw.N_w = g.N;
     gw.n_off = 0;
-    if (nsplit && mode != EPI_HEADDOT && g.N > 256 && g.N % 256 == 128) {
+    if (nsplit && mode == EPI_GENERIC && g.taps > 1 && g.N > 256 && g.N % 256 == 128) {
       GemmShape ga = gw;
       ga.N = (g.N / 256) * 256;
       if (pick_bn2(ga, gemm2_cg()) == 256) {
@@ -275,6 +285,7 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& g, int mode,
 
 static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g, int mode, const EpiParams& ep_in,
                                cudaStream_t stream) {
+  SVDD_CHECK_ARG(g.K2 == 0 || (mode == EPI_PAIR && g.taps == 1), "conv_gemm: K2 is an EPI_PAIR (1x1) feature");
   {
     const int cg = gemm2_cg();
     const int bn2 = pick_bn2(g, cg);
@@ -306,15 +317,33 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     };
     if (mode == EPI_PAIR) {
       SVDD_CHECK_ARG(g.N % 128 == 0 && g.BL % 2 == 0 && g.taps == 1, "conv_gemm: EPI_PAIR needs N %% 128 == 0, an even BL, 1x1");
-      SVDD_CHECK_ARG(ep2.res && ep2.out && ep2.out2 && ep2.res_dtype == DT_BF16 && ep2.out_dtype == DT_BF16 &&
-                     ep2.out2_dtype == DT_BF16, "conv_gemm: EPI_PAIR needs bf16 res / out / out2");
-      SVDD_CHECK_ARG(aligned16(ep2.res, ep2.ld_res, 2) && aligned16(ep2.out, ep2.ld_out, 2) &&
-                     aligned16(ep2.out2, ep2.ld_out2, 2), "conv_gemm: EPI_PAIR operands must be 16-byte aligned");
+      SVDD_CHECK_ARG(ep2.out && ep2.out2 && ep2.out_dtype == DT_BF16 && ep2.out2_dtype == DT_BF16,
+                     "conv_gemm: EPI_PAIR needs bf16 out / out2");
+      SVDD_CHECK_ARG(aligned16(ep2.out, ep2.ld_out, 2) && aligned16(ep2.out2, ep2.ld_out2, 2),
+                     "conv_gemm: EPI_PAIR operands must be 16-byte aligned");
       const int Lo = (g.L + 1) / 2;
       SVDD_TRY(io_map(&tO, ep2.out, DT_BF16, ep2.ld_out, Lo, g.BL / 2));
       SVDD_TRY(io_map(&tO2, ep2.out2, DT_BF16, ep2.ld_out2, Lo, g.BL / 2));
-      SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL));
-      tR2 = tA;
+      if (g.K2 > 0) {
+        // the residual is recomputed from a second K-concatenated operand pair instead of read
+        SVDD_CHECK_ARG(g.K2 % 64 == 0 && ep2.a2 && ep2.w2k && ep2.res == nullptr,
+                       "conv_gemm: K2 needs a2 / w2k, a multiple of 64 and no residual");
+        SVDD_CHECK_ARG((reinterpret_cast<uintptr_t>(ep2.a2) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep2.w2k) & 15) == 0,
+                       "conv_gemm: a2 / w2k must be 16-byte aligned");
+        const cuuint64_t dims[3] = {(cuuint64_t)g.K2, (cuuint64_t)g.L_in, (cuuint64_t)g.S};
+        const cuuint64_t str[2] = {(cuuint64_t)g.K2 * 2, (cuuint64_t)g.L_in * g.K2 * 2};
+        const cuuint32_t box[3] = {64, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+        SVDD_TRY(encode_bf16_map(&tR, ep2.a2, 3, dims, str, box));
+        const cuuint64_t wd[2] = {(cuuint64_t)g.K2, (cuuint64_t)g.N_w};
+        const cuuint64_t ws[1] = {(cuuint64_t)g.K2 * 2};
+        const cuuint32_t wb[2] = {64, (cuuint32_t)(bn2 / cg)};
+        SVDD_TRY(encode_bf16_map(&tR2, ep2.w2k, 2, wd, ws, wb));
+      } else {
+        SVDD_CHECK_ARG(ep2.res && ep2.res_dtype == DT_BF16 && aligned16(ep2.res, ep2.ld_res, 2),
+                       "conv_gemm: EPI_PAIR needs a 16-byte aligned bf16 residual");
+        SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL));
+        tR2 = tA;
+      }
     } else if (mode == EPI_POOL2) {
       SVDD_CHECK_ARG(g.N % 128 == 0 && g.taps == 1, "conv_gemm: EPI_POOL2 needs N %% 128 == 0, 1x1");
       SVDD_CHECK_ARG(ep2.res && ep2.res2 && (ep2.out || ep2.out2), "conv_gemm: EPI_POOL2 needs res, res2 and an output");

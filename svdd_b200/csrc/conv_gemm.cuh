@@ -70,6 +70,9 @@ struct EpiParams {
   //            out (fp32, optional) and out2 = act2(pooled * scale2 + shift2) (bf16, optional)
   const void* res2 = nullptr;
   int64_t ld_res2 = 0;
+  // GemmShape::K2 > 0: second operand pair (bf16 [rows, K2] and bf16 [N, K2]); replaces `res`
+  const void* a2 = nullptr;
+  const void* w2k = nullptr;
   // EPI_HEADDOT: partials[r, 2*n_tile + half] = sum_{n in that half tile} v[n] * head_w[n]
   const float* head_w = nullptr;
   float* partials = nullptr;
@@ -88,6 +91,9 @@ struct GemmShape {
   // column window of one launch (conv_gemm2 only): this launch computes columns
   // [n_off, n_off + N) of a weight / output that is N_w columns wide (0 = N)
   int n_off = 0, N_w = 0;
+  // K-concatenated second operand (conv_gemm2, EPI_PAIR, 1x1): C += A2[rows, K2] * W2[N, K2]^T;
+  // A2 has A's row structure, pointers in EpiParams::a2 / w2k
+  int K2 = 0;
 };
 
 namespace gemm_detail {
@@ -644,6 +650,10 @@ int launch_conv_gemm(const void* A, const void* W, const GemmShape& shape, int m
 // Number of partials per row that EPI_HEADDOT writes for this shape (2 per N tile: one per
 // column half).
 int conv_gemm_n_tiles(const GemmShape& shape, int mode);
+
+// 128B-swizzled 2-D tensor map over a row-major bf16 matrix [rows, inner] (inner contiguous).
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                        uint32_t box_inner, uint32_t box_rows);
 
 // Picks (BL, BS) for a conv over sequences of length L: whole-sequence tiles when
 // L <= 128 (several sequences per tile), else 128-position tiles.

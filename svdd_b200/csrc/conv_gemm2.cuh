@@ -266,6 +266,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int n_tiles = g.N / BN;
   const int64_t total_tiles = mp_tiles * n_tiles;
   const int kblocks = g.K / kBK;
+  const int kblocks2 = g.K2 / kBK;         // K-concatenated second operand (0 = none)
   const int64_t first_tile = blockIdx.x / CG;
   const int64_t tile_step = gridDim.x / CG;
 
@@ -357,6 +358,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        // K-concatenated second operand (EPI_PAIR stage 0: the stem conv is recomputed inside the
+        // residual 1x1 GEMM instead of being read back as a residual): A2 through tmRes, W2 [N, K2]
+        // through tmRes2
+        for (int kb = 0; kb < kblocks2; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_3d_cg<CG>(sa, &tmRes, &full_bar[stage], kb * kBK, c.l0, c.s0);
+          tma_load_2d_cg<CG>(sb, &tmRes2, &full_bar[stage], kb * kBK, c.n0 + rank * (BN / CG));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -370,25 +383,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc_stage * BN;
         uint32_t first = 1;
+        auto consume_stage = [&]() {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+            const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+            const uint64_t db = ptx::make_kmajor_sw128_desc(sa + C::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_cg<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
+            umma_commit_cg<CG>(&empty_bar[stage]);
+          }
+          __syncwarp();
+          first = 0;
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        };
         for (int tap = 0; tap < g.taps; ++tap) {
           if (!tap_active(tap, t)) continue;
-          for (int kb = 0; kb < kblocks; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
-              const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
-              const uint64_t db = ptx::make_kmajor_sw128_desc(sa + C::kABytes);
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k)
-                umma_bf16_cg<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
-              umma_commit_cg<CG>(&empty_bar[stage]);
-            }
-            __syncwarp();
-            first = 0;
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
+          for (int kb = 0; kb < kblocks; ++kb) consume_stage();
         }
+        for (int kb = 0; kb < kblocks2; ++kb) consume_stage();
         if (lane == 0) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
         __syncwarp();
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
@@ -493,7 +508,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 32; ++i) v[i] += pv[i];
         }
         if (!ep.act_after_res) act32(v, ep.act);
-        if (has_res || kPair) {
+        if (has_res || (kPair && ep.res != nullptr)) {
           if (has_out || kPair) {
             slab_read(buf0, x7, out_f32, cis, pv);
           } else if (valid) {            // HEADDOT with a residual: direct (unused by the nets)
@@ -569,7 +584,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
       // what is loaded into the buffer before the math warps may touch it
       auto load_map = [&](int o) -> const CUtensorMap* {
-        if (kPair) return o == 0 ? &tmRes : nullptr;
+        if (kPair) return (o == 0 && ep.res != nullptr) ? &tmRes : nullptr;
         if (kPool2) return o == 0 ? &tmRes : &tmRes2;
         return (has_res && o == 0) ? &tmRes : nullptr;
       };

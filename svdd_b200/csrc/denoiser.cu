@@ -11,7 +11,10 @@
 // [N*L,128] (ping-pong: layer i reads one through TMA while its epilogue writes the other).
 #include <new>
 
+#include <stdlib.h>
+
 #include "conv_gemm.cuh"
+#include "den_fused.cuh"
 #include "weights.cuh"
 
 namespace svdd {
@@ -198,6 +201,56 @@ extern "C" int svdd_denoiser_create(const svdd_tensor* tensors, int n_tensors, i
 
 extern "C" void svdd_denoiser_destroy(svdd_denoiser* h) { delete h; }
 
+// The whole network in one persistent kernel (den_fused.cuh) when the sequence fits two row
+// tiles and the padded operand fits shared memory; SVDD_ERR_INTERNAL = not handled here.
+// SVDD_DEN_FUSED=0 forces the layer-by-layer path (kept as the cross-check in the tests).
+static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype, const float* time_bias,
+                             float* logits, int64_t n_rows, int L, cudaStream_t st) {
+  const char* env = getenv("SVDD_DEN_FUSED");      // read per call: the tests flip it
+  const int enabled = env ? atoi(env) : 1;
+  if (!enabled || L > 256 || h->n_layers > denf::kMaxLayers) return SVDD_ERR_INTERNAL;
+  denf::Args a = {};
+  a.two_seq = (2 * L <= 128) ? 1 : 0;
+  int pad_before = 0, max_end = 256;
+  for (int i = 0; i < h->n_layers; ++i)
+    for (int t = 0; t < kTaps; ++t)
+      for (int m = 0; m < 2; ++m) {
+        const int o = (t - kTaps / 2) * h->dil[i];
+        if (!denf::tap_hits(m, o, L, a.two_seq)) continue;
+        const int start = 128 * m + o;
+        if (-start > pad_before) pad_before = -start;
+        if (start + 128 > max_end) max_end = start + 128;
+      }
+  a.pad_before = pad_before;
+  a.a_rows = (pad_before + max_end + 7) & ~7;
+  const int smem = denf::smem_bytes(a.a_rows);
+  if (smem > 227 * 1024) return SVDD_ERR_INTERNAL;
+  a.tokens = tokens;
+  a.embed_w = h->embed_w; a.embed_b = h->embed_b;
+  a.conv_b = h->conv_b; a.ln_g = h->ln_g; a.ln_b = h->ln_b;
+  a.time_bias = time_bias;
+  a.fc0_b = h->fc0_b; a.fc2_w = h->fc2_w; a.fc2_b = h->fc2_b;
+  a.logits = logits;
+  a.n_rows = n_rows; a.L = L; a.n_layers = h->n_layers;
+  for (int i = 0; i < h->n_layers; ++i) a.dil[i] = h->dil[i];
+  CUtensorMap tmW, tmW0;
+  SVDD_TRY(encode_tmap_2d_bf16(&tmW, h->conv_w, kH, (uint64_t)h->n_layers * kTaps * kH, 64, kH));
+  SVDD_TRY(encode_tmap_2d_bf16(&tmW0, h->fc0_w, kH, kH, 64, kH));
+  const int64_t items = a.two_seq ? (n_rows + 1) / 2 : n_rows;
+  const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+  if (tok_dtype == SVDD_TOK_I64) {
+    auto kern = denf::den_fused_kernel<int64_t>;
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SVDD_CUDA(launch_k(kern, dim3(grid), dim3(denf::kThreads), (size_t)smem, st, 1, tmW, tmW0, a));
+  } else {
+    auto kern = denf::den_fused_kernel<uint8_t>;
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SVDD_CUDA(launch_k(kern, dim3(grid), dim3(denf::kThreads), (size_t)smem, st, 1, tmW, tmW0, a));
+  }
+  count_launch();
+  return SVDD_OK;
+}
+
 extern "C" size_t svdd_denoiser_workspace_bytes(const svdd_denoiser* h, int64_t n_rows, int L) {
   (void)h;
   const size_t nl = (size_t)n_rows * L + 1;
@@ -219,6 +272,10 @@ extern "C" int svdd_denoiser_forward(svdd_denoiser* h, const void* tokens, int t
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t NL = n_rows * L;
+  {
+    int rc = den_fused_forward(h, tokens, tok_dtype, time_bias, logits, n_rows, L, st);
+    if (rc != SVDD_ERR_INTERNAL) return rc;     // SVDD_ERR_INTERNAL = shape not handled: layer-by-layer path
+  }
   Workspace W(ws, ws_bytes);
   float* feat = W.take<float>((size_t)(NL + 1) * kH);
   __nv_bfloat16* hbuf[2];

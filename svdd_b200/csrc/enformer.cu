@@ -324,6 +324,12 @@ int launch_attention(const float* qkv, const float* rcb, const float* rpb, const
   return SVDD_OK;
 }
 
+__global__ void ef_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                              int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 // relk[blk][h][p][d] = sum_f W[blk][(h*dk+d)][f] * pos[p][f]
 __global__ void ef_relk_kernel(const float* __restrict__ w, const float* __restrict__ pos,
                                float* __restrict__ relk, int H, int dk, int F, int P) {
@@ -396,6 +402,7 @@ struct svdd_enformer {
   __nv_bfloat16* w5[kMaxStages] = {}; float* b5[kMaxStages] = {};
   float* bn5_s[kMaxStages] = {}; float* bn5_t[kMaxStages] = {};   // BN feeding the k5 conv of stage i
   __nv_bfloat16* w1[kMaxStages] = {}; float* b1[kMaxStages] = {};
+  float* b1s = nullptr;                                           // b1[0] + stem bias (K-concatenated stage 0)
   float* bn1_s[kMaxStages] = {}; float* bn1_t[kMaxStages] = {};   // BN feeding the 1x1 conv of stage i
   __nv_bfloat16* wp[kMaxStages] = {};
   struct Block {
@@ -469,7 +476,7 @@ extern "C" int svdd_enformer_create(const svdd_tensor* tensors, int n_tensors, i
   auto plan = [&](bool take) {
 #define F32(ptr, n) do { if (take) ptr = A.take<float>(n); else A.reserve(sizeof(float) * (size_t)(n)); } while (0)
 #define B16(ptr, n) do { if (take) ptr = A.take<__nv_bfloat16>(n); else A.reserve(sizeof(__nv_bfloat16) * (size_t)(n)); } while (0)
-    B16(h->stem_w, (size_t)h->C0 * kStemK); F32(h->stem_b, h->C0);
+    B16(h->stem_w, (size_t)h->C0 * kStemK); F32(h->stem_b, h->C0); F32(h->b1s, h->C0);
     for (int i = 0; i < ns; ++i) {
       const size_t fi = h->f[i], fp = i > 0 ? h->f[i - 1] : 0;
       if (i > 0) { B16(h->w5[i], 5 * fi * fp); F32(h->b5[i], fi); F32(h->bn5_s[i], fp); F32(h->bn5_t[i], fp); }
@@ -525,6 +532,9 @@ extern "C" int svdd_enformer_create(const svdd_tensor* tensors, int n_tensors, i
     GET_OR_FAIL(wp, p1 + "pool.layer.to_attn_logits.weight", (int64_t)fi * fi);
     TRY_OR_FAIL(pack_conv_weight(w, h->w1[i], fi, fi, 1, st));
     TRY_OR_FAIL(copy_f32(b, h->b1[i], fi, st));
+    if (i == 0) {
+      ef_add_kernel<<<ceil_div(fi, 256), 256, 0, st>>>(h->b1[0], h->stem_b, h->b1s, fi);
+    }
     TRY_OR_FAIL(pack_conv_weight(wp, h->wp[i], fi, fi, 1, st));
     TRY_OR_FAIL(bn_fold(p1 + "norm.layer.", fi, h->bn1_s[i], h->bn1_t[i]));
   }
@@ -615,6 +625,11 @@ struct EfWs {
 bool pool2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SVDD_POOL2"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+bool stem_concat_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_STEM_CONCAT"); v = e ? atoi(e) : 1; }
   return v != 0;
 }
 int ef_final_len(const svdd_enformer* h, int L) {
@@ -710,15 +725,20 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
       SVDD_LAUNCH_CHECK();
     }
     __nv_bfloat16 *x = b.big[0], *a = b.big[1], *y = b.big[2];   // roles rotate below
+    // Stage 0's residual 1x1 conv needs x0 = stem(col) only as an addend: y = W1.a0 + b1 + x0 with
+    // x0 = Ws.col + bs is ONE contraction over the concatenated K = [a0 | col] (768 + 64), so x0
+    // is never written (393 MB at c2) nor read back; the stem GEMM only emits a0.
+    const bool stem_concat = stem_concat_enabled() && pool2_enabled() && h->C0 % 128 == 0 &&
+                             (L % 2 == 0 || L + 1 <= 128);
     {
       EpiParams ep;                                  // x0 = conv + b ; a0 = GELU(BN_{0.1}(x0))
       ep.bias = h->stem_b;
-      ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = h->C0;
+      if (!stem_concat) { ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = h->C0; }
       ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = h->C0;
       ep.scale2 = h->bn1_s[0]; ep.shift2 = h->bn1_t[0]; ep.act2 = ACT_GELU;
       SVDD_TRY(gemm_flat(b.col, h->stem_w, NL, kStemK, h->C0, ep, EPI_GENERIC));
       if (debug_dump_enabled()) {
-        debug_dump("ef_x0", x, (size_t)NL * h->C0 * 2, st);
+        if (!stem_concat) debug_dump("ef_x0", x, (size_t)NL * h->C0 * 2, st);
         debug_dump("ef_a0", a, (size_t)NL * h->C0 * 2, st);
       }
     }
@@ -762,8 +782,14 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
             g.S = (int)rows; g.L = len; g.L_in = len; g.BL = len + 1; g.BS = 128 / (len + 1);
           }
           EpiParams ep;
-          ep.bias = h->b1[i];
-          ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          if (i == 0 && stem_concat) {
+            g.K2 = kStemK;
+            ep.a2 = b.col; ep.w2k = h->stem_w;
+            ep.bias = h->b1s;
+          } else {
+            ep.bias = h->b1[i];
+            ep.res = x; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          }
           ep.out = y0; ep.out_dtype = DT_BF16; ep.ld_out = fi;
           ep.out2 = yd; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
           SVDD_TRY(launch_conv_gemm(a, h->w1[i], g, EPI_PAIR, ep, st));

@@ -74,6 +74,29 @@ def test_denoiser_batch_shapes(cuda):
       assert torch.equal(part, full[:n]), (L, n)
 
 
+@pytest.mark.parametrize('L,n', [(200, 150), (200, 3), (50, 301), (50, 1), (64, 5), (100, 9), (130, 4), (256, 2)])
+def test_denoiser_fused_kernel_matches_layer_by_layer(cuda, L, n, monkeypatch):
+  """The persistent whole-network kernel (activations in smem / TMEM, taps as descriptor row
+  offsets) against the layer-by-layer conv_gemm path: same bf16 rounding points, so the two
+  agree to fp32-accumulation-order noise.  Covers two row tiles (L > 128), one tile
+  (64 < L <= 128), two sequences per CTA (L <= 64, odd count) and several items per CTA."""
+  m = helpers.build_denoiser(44, L).to(cuda)
+  x = helpers.random_tokens(n, L, 5, 0.6).to(cuda)
+  den = m.packed()
+  monkeypatch.setenv('SVDD_DEN_FUSED', '0')
+  layered = den.forward(x, 0.3)
+  monkeypatch.setenv('SVDD_DEN_FUSED', '1')
+  before = _lib.launch_count()
+  fused = den.forward(x, 0.3)
+  torch.cuda.synchronize()
+  assert _lib.launch_count() - before == 1, 'the fused path is one launch'
+  torch.cuda.synchronize()
+  scale = float(layered.abs().max())
+  err = float((fused - layered).abs().max()) / scale
+  print(f'\n[denoiser fused vs layered L={L} n={n}] rel.err {err:.3e}')
+  assert err < 6e-3
+
+
 def test_convgru_value(cuda):
   g = helpers.load_golden('value_nets.npz')
   tok = T(g['convgru_tokens'])
