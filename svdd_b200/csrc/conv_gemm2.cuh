@@ -158,7 +158,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   if constexpr (CG == 1) {
     ptx::mbar_arrive(bar);
   } else {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ptx::smem_u32(bar) & kPeerMask)
+    // relaxed: the accumulator reads it publishes are complete (tcgen05.wait::ld) and fenced
+    // (tcgen05.fence::before_thread_sync) by the caller; a release at cluster scope lowers to
+    // MEMBAR.ALL.GPU, 6.6 % of the EPI_PAIR kernel's stall samples
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ptx::smem_u32(bar) & kPeerMask)
                  : "memory");
   }
 }
