@@ -198,6 +198,7 @@ def main():
   if args.impl == 'reference':
     run_reference(args, rank, world)
     return
+  os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line
   if not torch.cuda.is_available():
     raise SystemExit('bench.py needs a CUDA device: svdd_b200 has no CPU path '
                      '(use --impl reference for the CPU port)')
@@ -292,12 +293,12 @@ def main():
     # HBM-bound stages at BASELINE config 4 (B=4096, M=20): the whole batch on one GPU and the
     # per-GPU shard at N=8; algorithmic bytes in the reference's dtypes
     sched_mc = (0.5, 0.49)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
 
     def timed(fn, reps=10):
       ts = []
       for _ in range(reps):
-        flush.zero_()
+        flush.sum()          # evict L2 with CLEAN lines (a write-flush leaves 126 MB of write-backs)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
@@ -318,7 +319,7 @@ def main():
         stage_rooflines[f'{name}@{tag}'] = {
             'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
             'algorithmic_bytes': nb, 'ms': t,
-            'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 flushed, one launch'}
+            'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 evicted by a 256 MB read, one launch'}
       del U, lg, xs, sc, cand64
     del flush
 

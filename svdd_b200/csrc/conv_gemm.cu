@@ -138,15 +138,16 @@ int gemm2_cg() {
   return v;
 }
 
-template <int BN, int MODE, int CG>
+template <int BN, int MODE, int CG, bool HALO = false>
 int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                  const CUtensorMap& tmR, const CUtensorMap& tmR2, const GemmShape& g, const EpiParams& ep,
                  cudaStream_t stream) {
   using C = gemm2::Cfg2<BN, CG>;
-  auto kern = gemm2::gemm2_kernel<BN, MODE, CG>;
+  auto kern = gemm2::gemm2_kernel<BN, MODE, CG, HALO>;
+  constexpr int kSmem = HALO ? C::kSmemBytesH : C::kSmemBytes;
   static bool configured = false;
   if (!configured) {
-    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int64_t m_tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS);
@@ -161,7 +162,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     SVDD_CUDA(cudaEventCreate(&e1));
     SVDD_CUDA(cudaEventRecord(e0, stream));
   }
-  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm2::kThreads), C::kSmemBytes, stream, CG,
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm2::kThreads), kSmem, stream, CG,
                      tmA, tmW, tmO, tmO2, tmR, tmR2, g, ep));
   count_launch();
   if (P.on) {
@@ -169,7 +170,8 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     std::lock_guard<std::mutex> lk(P.mu);
     P.ev.push_back(e0);
     P.ev.push_back(e1);
-    const double fl = 2.0 * (double)g.S * g.L * (double)g.N * ((double)g.K * g.taps + g.K2);
+    const double rows_fl = g.useful_rows > 0 ? (double)g.useful_rows : (double)g.S * g.L;
+    const double fl = 2.0 * rows_fl * (double)g.N * ((double)g.K * g.taps + g.K2);
     P.flops += fl;
     P.recs.push_back({g, BN + 1000 * CG, MODE, fl});
   }
@@ -292,10 +294,16 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     EpiParams ep2 = ep_in;
     if (ep2.out == nullptr && ep2.out2 != nullptr) ep2.out_dtype = ep2.out2_dtype;   // slab geometry follows the staged output
     CUtensorMap tA, tW, tO, tO2, tR, tR2;
+    if (g.halo) {
+      SVDD_CHECK_ARG(mode == EPI_GENERIC && cg == 2 && g.S == 1 && g.BS == 1 && g.BL == 128 && g.taps % 2 == 1 &&
+                     g.taps - 1 <= 8 && g.dil == 1 && g.K2 == 0,
+                     "conv_gemm: halo mode needs flat rows (S = 1, 128-row tiles), odd taps <= 9, cta_group 2");
+    }
     {
+      const int64_t a_pitch = g.a_pitch > 0 ? g.a_pitch : g.L_in;
       const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.L_in, (cuuint64_t)g.S};
-      const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.L_in * g.K * 2};
-      const cuuint32_t box[3] = {64, (cuuint32_t)g.BL, (cuuint32_t)g.BS};
+      const cuuint64_t str[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)a_pitch * g.K * 2};
+      const cuuint32_t box[3] = {64, (cuuint32_t)(g.halo ? g.BL + g.taps - 1 : g.BL), (cuuint32_t)g.BS};
       SVDD_TRY(encode_bf16_map(&tA, A, 3, dims, str, box));
       const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.N_w};
       const cuuint64_t ws[1] = {(cuuint64_t)g.K * 2};
@@ -303,11 +311,11 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       SVDD_TRY(encode_bf16_map(&tW, W, 2, wd, ws, wb));
     }
     // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes x box_l x BS
-    auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l) -> int {
+    auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l, int pitch = 0) -> int {
       if (p == nullptr) { *m = tA; return SVDD_OK; }
       const cuuint64_t es = dt == DT_F32 ? 4 : 2;
       const cuuint64_t dims[3] = {(cuuint64_t)g.N_w, (cuuint64_t)Lr, (cuuint64_t)g.S};
-      const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)Lr * ld * es};
+      const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)(pitch > 0 ? pitch : Lr) * ld * es};
       const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_l, (cuuint32_t)g.BS};
       return encode_map(m, dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3,
                         dims, str, box);
@@ -352,15 +360,20 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       SVDD_CHECK_ARG(aligned16(ep2.res, ep2.ld_res, 2) && aligned16(ep2.res2, ep2.ld_res2, 2) &&
                      (ep2.out2 == nullptr || aligned16(ep2.out2, ep2.ld_out2, 2)),
                      "conv_gemm: EPI_POOL2 operands must be 16-byte aligned");
+      SVDD_CHECK_ARG(ep2.out == nullptr || ep2.out_pitch == 0, "conv_gemm: EPI_POOL2 `out` is densely packed");
       tO = tA;
-      SVDD_TRY(io_map(&tO2, ep2.out2, DT_BF16, ep2.ld_out2, g.L, g.BL));
-      SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL));
-      SVDD_TRY(io_map(&tR2, ep2.res2, DT_BF16, ep2.ld_res2, g.L, g.BL));
+      SVDD_TRY(io_map(&tO2, ep2.out2, DT_BF16, ep2.ld_out2, g.L, g.BL, ep2.out2_pitch));
+      SVDD_TRY(io_map(&tR, ep2.res, DT_BF16, ep2.ld_res, g.L, g.BL, ep2.res_pitch));
+      SVDD_TRY(io_map(&tR2, ep2.res2, DT_BF16, ep2.ld_res2, g.L, g.BL, ep2.res2_pitch));
     } else {
       SVDD_TRY(io_map(&tO, ep2.out, ep2.out_dtype, ep2.ld_out, g.L, g.BL));
       SVDD_TRY(io_map(&tO2, ep2.res == nullptr ? ep2.out2 : nullptr, ep2.out2_dtype, ep2.ld_out2, g.L, g.BL));
       SVDD_TRY(io_map(&tR, ep2.res, ep2.res_dtype, ep2.ld_res, g.L, g.BL));
       tR2 = tA;
+    }
+    if (g.halo) {
+      if (bn2 == 256) return launch2_impl<256, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      if (bn2 == 128) return launch2_impl<128, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }
 #define CASE2(BN_, MODE_, CG_) \
     if (bn2 == BN_ && mode == MODE_ && cg == CG_) return launch2_impl<BN_, MODE_, CG_>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream)
@@ -541,7 +554,10 @@ extern "C" int svdd_selftest_gemm_epilogue(const void* A_bf16, const void* W_bf1
   SVDD_TRY(svdd_device_check(dev));
   GemmShape g;
   g.K = K; g.N = N; g.taps = taps; g.dil = dil;
-  if (flat) {
+  if (flat == 2) {
+    // halo mode: A is [S*L, K] flat rows that already carry taps/2 zero rows between sequences
+    g.S = 1; g.L = S * L; g.L_in = S * L; g.BL = 128; g.BS = 1; g.halo = 1;
+  } else if (flat) {
     SVDD_CHECK_ARG(taps == 1, "selftest_gemm_epilogue: flat rows need taps == 1");
     g.S = 1; g.L = S * L; g.L_in = S * L; g.BL = 128; g.BS = 1;
   } else {

@@ -73,6 +73,8 @@ struct EpiParams {
   // GemmShape::K2 > 0: second operand pair (bf16 [rows, K2] and bf16 [N, K2]); replaces `res`
   const void* a2 = nullptr;
   const void* w2k = nullptr;
+  // rows between consecutive sequences of res / res2 / out / out2 (conv_gemm2; 0 = densely packed)
+  int res_pitch = 0, res2_pitch = 0, out_pitch = 0, out2_pitch = 0;
   // EPI_HEADDOT: partials[r, 2*n_tile + half] = sum_{n in that half tile} v[n] * head_w[n]
   const float* head_w = nullptr;
   float* partials = nullptr;
@@ -94,6 +96,14 @@ struct GemmShape {
   // K-concatenated second operand (conv_gemm2, EPI_PAIR, 1x1): C += A2[rows, K2] * W2[N, K2]^T;
   // A2 has A's row structure, pointers in EpiParams::a2 / w2k
   int K2 = 0;
+  // conv_gemm2 HALO mode (flat rows, S == 1, BL == 128, taps odd): the A tile is fetched once per
+  // K block with taps-1 extra rows and each tap is a row offset of the smem descriptor.  The
+  // caller guarantees `taps/2` zero rows between consecutive sequences of the flat row space.
+  int halo = 0;
+  // rows between consecutive sequences of A when they are not densely packed (0 = L_in)
+  int a_pitch = 0;
+  // rows that carry real data, for the FLOP accounting of padded layouts (0 = S * L)
+  int64_t useful_rows = 0;
 };
 
 namespace gemm_detail {

@@ -66,6 +66,18 @@ struct Cfg2 {
   static constexpr int kHalf = BN / 2;
   static constexpr int kChunks = kHalf / 32;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kParamBytes + kBarBytes + 1024;
+  // HALO variant (flat-row conv, the A tile is loaded ONCE per K block with taps-1 extra rows and
+  // every tap is a row offset of the UMMA descriptor): separate A and B rings
+  static constexpr int kHaloRowsMax = 8;                              // taps - 1 <= 8
+  static constexpr int kAHBytes = (kBM + kHaloRowsMax) * kBK * 2;     // 136 rows x 128 B = 17 x 1024
+  static constexpr int kStagesAH = 3;
+  static constexpr int kStagesBHRaw = (kAvail - kStagesAH * kAHBytes) / kBBytes;
+  static constexpr int kStagesBH = kStagesBHRaw > 8 ? 8 : kStagesBHRaw;
+  static constexpr int kRingBytesH = kStagesAH * kAHBytes + kStagesBH * kBBytes;
+  static constexpr int kSmemBytesH = kRingBytesH + kStagingBytes + kParamBytes + kBarBytes + 1024;
+  static_assert(kAHBytes % 1024 == 0 && kBBytes % 1024 == 0, "ring stages must stay 1024-byte aligned");
+  static_assert(CG == 1 || kStagesBH >= 4, "halo weight ring too shallow");
+  static_assert(kSmemBytesH <= 227 * 1024, "shared memory budget exceeded (halo)");
   static_assert(BN == 128 || BN == 256, "gemm2 tiles are 128 or 256 columns wide");
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
   static_assert(kStages >= 2, "operand ring too shallow");
@@ -235,20 +247,21 @@ __device__ __forceinline__ void slab_read(const uint8_t* row_base, int x7, bool 
 
 struct TileCoord { int n0, s0, l0; bool in_range; };
 
-template <int BN, int MODE, int CG>
+template <int BN, int MODE, int CG, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes2,
              const GemmShape g, const EpiParams ep) {
   using C = Cfg2<BN, CG>;
-  constexpr int kStages = C::kStages;
+  constexpr int kStages = HALO ? C::kStagesBH : C::kStages;          // (HALO: the weight ring)
   constexpr int kHalf = C::kHalf;
   constexpr int kChunks = C::kChunks;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + kStages * C::kStageBytes;                // [half][buf] slabs, 1024-aligned
+  uint8_t* stage_base = smem;                                        // HALO: [kStagesAH] A tiles, then the B ring
+  uint8_t* ringb_base = smem + C::kStagesAH * C::kAHBytes;           // HALO only
+  uint8_t* staging = smem + (HALO ? C::kRingBytesH : kStages * C::kStageBytes);   // [half][buf] slabs, 1024-aligned
   float* s_param = reinterpret_cast<float*>(staging + kStagingBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes + C::kParamBytes);
   uint64_t* full_bar = bars;                       // [kStages]   (leader's copy is the live one)
@@ -258,6 +271,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* rin_bar = bars + 2 * kStages + 4;      // [half][buf]
   uint64_t* rout_bar = bars + 2 * kStages + 8;     // [half][buf]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
+  uint64_t* fulla_bar = bars + 2 * kStages + 14;   // [kStagesAH]  HALO only
+  uint64_t* emptya_bar = fulla_bar + C::kStagesAH; // [kStagesAH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
@@ -306,6 +321,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_init(&rin_bar[i], 1);
         ptx::mbar_init(&rout_bar[i], kEpiWarps / 2);
       }
+      if (HALO) {
+        for (int i = 0; i < C::kStagesAH; ++i) {
+          ptx::mbar_init(&fulla_bar[i], 1);
+          ptx::mbar_init(&emptya_bar[i], 1);
+        }
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -343,7 +364,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
-    if (lane == 0) {
+    if (lane == 0 && HALO) {
+      // flat rows: one A box of BL + taps - 1 rows per K block (rows l0 - taps/2 ..; out-of-range
+      // rows are zero-filled by TMA, pad rows between sequences are zero in memory), then the
+      // weight tile of every tap
+      uint32_t sa_i = 0, pa = 0, stage = 0, phase = 0;
+      const uint32_t txa = (uint32_t)(CG * (g.BL + g.taps - 1) * kBK * 2);
+      const uint32_t txb = (uint32_t)(CG * C::kBBytes);
+      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord c = tile_coords(t, rank);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&emptya_bar[sa_i], pa ^ 1);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&fulla_bar[sa_i], txa);
+          tma_load_3d_cg<CG>(stage_base + sa_i * C::kAHBytes, &tmA, &fulla_bar[sa_i], kb * kBK, c.l0 - g.taps / 2, c.s0);
+          if (++sa_i == C::kStagesAH) { sa_i = 0; pa ^= 1; }
+          for (int tap = 0; tap < g.taps; ++tap) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], txb);
+            tma_load_2d_cg<CG>(ringb_base + stage * C::kBBytes, &tmW, &full_bar[stage], kb * kBK,
+                               tap * g.N_w + c.n0 + rank * (BN / CG));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (uint32_t)(CG * (g.BL * g.BS * kBK * 2 + C::kBBytes));
       for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
@@ -380,6 +424,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM * CG, BN);
       uint32_t stage = 0, phase = 0;
+      uint32_t sa_i = 0, pa = 0;           // HALO: A ring position
       uint32_t acc_stage = 0, acc_phase = 0;
       for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
         ptx::mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
@@ -402,11 +447,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           first = 0;
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         };
-        for (int tap = 0; tap < g.taps; ++tap) {
-          if (!tap_active(tap, t)) continue;
-          for (int kb = 0; kb < kblocks; ++kb) consume_stage();
+        if constexpr (HALO) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ptx::mbar_wait(&fulla_bar[sa_i], pa);
+            const uint32_t sa = ptx::smem_u32(stage_base + sa_i * C::kAHBytes);
+            for (int tap = 0; tap < g.taps; ++tap) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                // tap = row offset: the 128-byte swizzle is a function of the absolute smem address
+                const uint64_t da = ptx::make_kmajor_sw128_desc(sa + (uint32_t)tap * 128u);
+                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(ringb_base + stage * C::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  umma_bf16_cg<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? (k > 0) : 1u);
+                umma_commit_cg<CG>(&empty_bar[stage]);
+                if (tap + 1 == g.taps) umma_commit_cg<CG>(&emptya_bar[sa_i]);
+              }
+              __syncwarp();
+              first = 0;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++sa_i == C::kStagesAH) { sa_i = 0; pa ^= 1; }
+          }
+        } else {
+          for (int tap = 0; tap < g.taps; ++tap) {
+            if (!tap_active(tap, t)) continue;
+            for (int kb = 0; kb < kblocks; ++kb) consume_stage();
+          }
+          for (int kb = 0; kb < kblocks2; ++kb) consume_stage();
         }
-        for (int kb = 0; kb < kblocks2; ++kb) consume_stage();
         if (lane == 0) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
         __syncwarp();
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }

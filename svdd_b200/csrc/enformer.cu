@@ -330,6 +330,20 @@ __global__ void ef_add_kernel(const float* __restrict__ a, const float* __restri
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// zero rows {0, 1, Lp-2, Lp-1} of every sequence of a bf16 [rows, Lp, C] buffer (HALO layout pads)
+__global__ void ef_zero_pads_kernel(__nv_bfloat16* __restrict__ buf, int64_t rows, int Lp, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = C / 8;                      // 16-byte vectors per row
+  if (i >= rows * 4 * cv) return;
+  const int v = (int)(i % cv);
+  const int r4 = (int)((i / cv) % 4);
+  const int64_t s = i / ((int64_t)cv * 4);
+  const int l = r4 < 2 ? r4 : Lp - 4 + r4;
+  reinterpret_cast<uint4*>(buf + ((size_t)s * Lp + l) * C)[v] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // relk[blk][h][p][d] = sum_f W[blk][(h*dk+d)][f] * pos[p][f]
 __global__ void ef_relk_kernel(const float* __restrict__ w, const float* __restrict__ pos,
                                float* __restrict__ relk, int H, int dk, int F, int P) {
@@ -627,6 +641,15 @@ bool pool2_enabled() {
   if (v < 0) { const char* e = getenv("SVDD_POOL2"); v = e ? atoi(e) : 1; }
   return v != 0;
 }
+bool halo_enabled() {
+  static int v = -1;
+  // off by default: measured on the c2 step the padded flat layout is SLOWER (L=100 conv 578 vs
+  // 525 us, L=50 394 vs 369 us): the k5 convs already run at the sustained tensor peak (~63 % of
+  // nominal under the power cap), so removing the per-tap re-fetch of A buys nothing and the pad
+  // rows cost 4-8 % more MMA work.  Kept (SVDD_HALO=1) with its parity test.
+  if (v < 0) { const char* e = getenv("SVDD_HALO"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
 bool stem_concat_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SVDD_STEM_CONCAT"); v = e ? atoi(e) : 1; }
@@ -642,7 +665,7 @@ size_t ef_carve(const svdd_enformer* h, Workspace& W, int64_t rows, int L, EfWs*
   size_t big = 0;
   int len = L;
   for (int i = 0; i < h->n_stage; ++i) {
-    const size_t need = (size_t)rows * len * h->f[i];
+    const size_t need = (size_t)rows * (len + 4) * h->f[i];      // + the pad rows of the HALO layout
     if (need > big) big = need;
     len = (len + 1) / 2;
   }
@@ -743,14 +766,29 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
       }
     }
     int len = L;
+    bool halo_prev = false;              // the previous stage ran in the padded flat layout
     for (int i = 0; i < h->n_stage; ++i) {
       const int fi = h->f[i];
+      const int lo = (len + 1) / 2;
+      const bool pair_path = pool2_enabled() && fi % 128 == 0 && (len % 2 == 0 || len + 1 <= 128);
+      // HALO layout of stage i (its k5 conv, residual 1x1 conv and the pool's inputs): every
+      // sequence carries 2 zero rows either side ([rows, len + 4, C] flat), so the conv's five taps
+      // are five row offsets into ONE shared-memory copy of the activation tile instead of five
+      // TMA fetches through L2 -- the k5 convs at L = 100 / 50 were bound by the L2 -> SM fabric.
+      const bool halo = i > 0 && halo_prev;
+      const int Lp = len + 4;
       if (i > 0) {
         // z = Conv_k5(a) + b ; a' = GELU(BN_{i.1}(z)).  `a` holds GELU(BN_{i.0}(pooled)).
         const int fp = h->f[i - 1];
         GemmShape g;
-        g.S = (int)rows; g.L = len; g.L_in = len; g.K = fp; g.N = fi; g.taps = 5; g.dil = 1;
-        choose_row_tiling(len, 5, &g);
+        g.K = fp; g.N = fi; g.taps = 5; g.dil = 1;
+        if (halo) {
+          g.S = 1; g.L = (int)(rows * Lp); g.L_in = g.L; g.BL = 128; g.BS = 1; g.halo = 1;
+          g.useful_rows = rows * len;
+        } else {
+          g.S = (int)rows; g.L = len; g.L_in = len;
+          choose_row_tiling(len, 5, &g);
+        }
         EpiParams ep;
         ep.bias = h->b5[i];
         ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = fi;
@@ -763,24 +801,29 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         }
         __nv_bfloat16* t = a; a = y; y = t;          // a <- a' ; old a is free (now y)
       }
+      // does the NEXT stage take the padded layout?  (its input length lo must be even and long
+      // enough for the 4 pad rows to be cheap; the debug dumps keep the dense layout)
+      const bool halo_next = halo_enabled() && pair_path && i + 1 < h->n_stage && lo % 2 == 0 && lo >= 32 &&
+                             h->f[i + 1] % 128 == 0 && !debug_dump_enabled();
       // Attention pooling needs only the difference of the two logits of a pair, and
       // Wp.y[2j+1] - Wp.y[2j] = Wp.(y[2j+1] - y[2j]): the 1x1 conv's epilogue emits y0 = y[2j] and
       // yd = y[2j+1] - y[2j] at half length (EPI_PAIR) and the pool is ONE GEMM over yd (EPI_POOL2)
       // instead of two over y.  Odd lengths: whole-sequence tiles padded to an even BL, yd = 0 for
       // the unpaired tail (= the reference's -inf logit on the padded slot).
-      const int lo = (len + 1) / 2;
-      const bool pair_path = pool2_enabled() && fi % 128 == 0 && (len % 2 == 0 || len + 1 <= 128);
       if (pair_path) {
+        const int len_p = halo ? Lp : len;           // rows per sequence in the layout of x / a'
+        const int lo_p = len_p / 2 + (len_p & 1);    // ... and of y0 / yd
         __nv_bfloat16* y0 = y;
-        __nv_bfloat16* yd = y + (size_t)rows * lo * fi;
+        __nv_bfloat16* yd = y + (size_t)rows * lo_p * fi;
         {
           GemmShape g;
           g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
-          if (len % 2 == 0) {
-            g.S = 1; g.L = (int)(rows * len); g.L_in = g.L; g.BL = 128; g.BS = 1;
+          if (len_p % 2 == 0) {
+            g.S = 1; g.L = (int)(rows * len_p); g.L_in = g.L; g.BL = 128; g.BS = 1;
           } else {
             g.S = (int)rows; g.L = len; g.L_in = len; g.BL = len + 1; g.BS = 128 / (len + 1);
           }
+          g.useful_rows = rows * len;
           EpiParams ep;
           if (i == 0 && stem_concat) {
             g.K2 = kStemK;
@@ -800,18 +843,39 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         }
         {
           GemmShape g;
-          g.S = 1; g.L = (int)(rows * lo); g.L_in = g.L; g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
-          g.BL = 128; g.BS = 1;
+          g.K = fi; g.N = fi; g.taps = 1; g.dil = 1;
           EpiParams ep;
-          ep.res = y0; ep.res_dtype = DT_BF16; ep.ld_res = fi;
-          ep.res2 = yd; ep.ld_res2 = fi;
+          const __nv_bfloat16* y0v = y0;
+          const __nv_bfloat16* ydv = yd;
+          if (halo || halo_next) {
+            // per-sequence tiles: the inputs skip the pad pair of a padded stage, the output lands
+            // between the zero rows of the next stage's padded operand
+            g.S = (int)rows; g.L = lo; g.L_in = lo;
+            choose_row_tiling(lo, 1, &g);
+            if (halo) {
+              y0v += (size_t)fi; ydv += (size_t)fi;              // valid pairs start at row 1 of lo_p
+              g.a_pitch = lo_p; ep.res_pitch = lo_p; ep.res2_pitch = lo_p;
+            }
+          } else {
+            g.S = 1; g.L = (int)(rows * lo); g.L_in = g.L; g.BL = 128; g.BS = 1;
+          }
+          ep.res = y0v; ep.res_dtype = DT_BF16; ep.ld_res = fi;
+          ep.res2 = ydv; ep.ld_res2 = fi;
           if (i + 1 < h->n_stage) {
             ep.out2 = a; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
             ep.scale2 = h->bn5_s[i + 1]; ep.shift2 = h->bn5_t[i + 1]; ep.act2 = ACT_GELU;
+            if (halo_next) {
+              const unsigned zg = (unsigned)ceil_div<int64_t>(rows * 4 * (fi / 8), 256);
+              launch_k(ef_zero_pads_kernel, dim3(zg), dim3(256), 0, st, 1, a, rows, lo + 4, fi);
+              count_launch();
+              SVDD_LAUNCH_CHECK();
+              ep.out2 = a + (size_t)2 * fi;
+              ep.out2_pitch = lo + 4;
+            }
           } else {
             ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
           }
-          SVDD_TRY(launch_conv_gemm(yd, h->wp[i], g, EPI_POOL2, ep, st));
+          SVDD_TRY(launch_conv_gemm(ydv, h->wp[i], g, EPI_POOL2, ep, st));
         }
       } else {
         {  // y = Conv_1x1(a) + b + x     (residual ConvBlock, Enformer.py:1836-1838 / 1866-1868)
@@ -844,6 +908,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         else
           debug_dump("ef_xt_in", b.xt, (size_t)rows * lo * fi * 4, st);
       }
+      halo_prev = halo_next;
       len = lo;
     }
     // ---- transformer tower ------------------------------------------------------------------

@@ -95,12 +95,12 @@ __device__ __forceinline__ int gumbel_argmax5_checked(const float* q, const floa
   return ok ? best : gumbel_argmax5(q, u);
 }
 
-// Candidates per warp: blockIdx.y selects a chunk of kCandChunk candidates, so the M draws of
-// a position are spread over M / kCandChunk warps (each recomputes the 5 q values from the
-// L2-resident logits).  All noise loads of a chunk are issued before the first draw: 20 x 128 B
-// per warp in flight, and enough warps to cover the HBM latency-bandwidth product even at
-// B*L = 10^5 positions.
-constexpr int kCandChunk = 4;
+// One warp owns 32 positions and loops over the M candidates (q is computed once per
+// position: the accurate expf/logf of the SUBS step are a third of the kernel's instructions,
+// and the kernel is issue-bound, not DRAM-bound, once enough loads are in flight).  The noise
+// of kNoiseGroup candidates (kNoiseGroup x 640 B per warp) is in flight while the previous
+// group's draws are computed from shared memory.
+constexpr int kNoiseGroup = 4;
 
 template <typename Tok, bool kInjected, bool kFast>
 __global__ void __launch_bounds__(kThreads)
@@ -112,16 +112,15 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                    float* __restrict__ q_out, int64_t BL, int L, int M) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float s_stage[kWarpsPerBlock][32 * kVocab];
+  __shared__ float s_stage[kWarpsPerBlock][kNoiseGroup][32 * kVocab];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pos0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 32;
   if (pos0 >= BL) return;
   const int64_t pos = pos0 + lane;
   const bool valid = pos < BL;
+  const bool full = pos0 + 32 <= BL;           // warp-uniform: no bounds checks on the fast path
   const int64_t n_el = BL * kVocab;
-  float* stage = s_stage[warp];
-  const int m_begin = blockIdx.y * kCandChunk;
-  const int m_end = (m_begin + kCandChunk < M) ? m_begin + kCandChunk : M;
+  float* stage = s_stage[warp][0];
 
   // coalesced load of this warp's 32x5 logits (transposed through smem below)
   const int64_t e0 = pos0 * kVocab;
@@ -129,7 +128,7 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
 #pragma unroll
   for (int k = 0; k < kVocab; ++k) {
     const int64_t e = e0 + k * 32 + lane;
-    lraw[k] = (e < n_el) ? __ldg(logits + e) : 0.0f;
+    lraw[k] = (full || e < n_el) ? __ldg(logits + e) : 0.0f;
   }
   const int tok = valid ? load_tok(x, pos) : 0;
   const bool masked = valid && tok == kMaskIndex;
@@ -137,23 +136,20 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
   // masked positions never touches the noise.
   const unsigned any_masked = __ballot_sync(0xffffffffu, masked);
 
-  // this chunk's noise (the long-latency loads) is in flight while q is computed
-  float pre[kCandChunk][kVocab];
-  if (kInjected && any_masked != 0u) {
+  float pre[kNoiseGroup][kVocab];
+  const float* up = U + e0 + lane;             // candidate m: up + m * n_el (+ k * 32)
+  auto prefetch = [&](int m0) {
 #pragma unroll
-    for (int gi = 0; gi < kCandChunk; ++gi) {
-      const int m = m_begin + gi;
-      if (m < m_end) {
-        const int64_t b0 = ((int64_t)m * BL + pos0) * kVocab;
-        const int64_t lim = ((int64_t)m + 1) * n_el;
+    for (int gi = 0; gi < kNoiseGroup; ++gi) {
+      if (m0 + gi < M) {
+        const float* p = up + (int64_t)(m0 + gi) * n_el;
 #pragma unroll
-        for (int k = 0; k < kVocab; ++k) {
-          const int64_t e = b0 + k * 32 + lane;
-          pre[gi][k] = (e < lim) ? __ldcs(U + e) : 0.5f;
-        }
+        for (int k = 0; k < kVocab; ++k)
+          pre[gi][k] = (full || e0 + k * 32 + lane < n_el) ? __ldcs(p + k * 32) : 0.5f;
       }
     }
-  }
+  };
+  if (kInjected && any_masked != 0u) prefetch(0);
 
 #pragma unroll
   for (int k = 0; k < kVocab; ++k) stage[k * 32 + lane] = lraw[k];
@@ -170,7 +166,7 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
 #pragma unroll
   for (int v = 0; v < kVocab; ++v) q[v] = __fmul_rn(expf(logp[v]), d);
   q[kMaskIndex] = mc_s;
-  if (q_out != nullptr && blockIdx.y == 0) {
+  if (q_out != nullptr) {
 #pragma unroll
     for (int v = 0; v < kVocab; ++v) stage[lane * kVocab + v] = q[v];
     __syncwarp();
@@ -182,37 +178,43 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
     __syncwarp();
   }
 
+  Tok* cp = cand + pos;                        // candidate m: cp + m * BL
   if (any_masked == 0u) {
     if (valid)
-      for (int m = m_begin; m < m_end; ++m) store_tok(cand, (size_t)m * BL + pos, tok);
+      for (int m = 0; m < M; ++m) cp[(size_t)m * BL] = (Tok)tok;
     return;
   }
 
   if (kInjected) {
+    for (int m0 = 0; m0 < M; m0 += kNoiseGroup) {
 #pragma unroll
-    for (int gi = 0; gi < kCandChunk; ++gi) {
-      const int m = m_begin + gi;
-      if (m < m_end) {                       // warp-uniform
+      for (int gi = 0; gi < kNoiseGroup; ++gi)
 #pragma unroll
-        for (int k = 0; k < kVocab; ++k) stage[k * 32 + lane] = pre[gi][k];
-        __syncwarp();
-        int draw = tok;
-        if (masked) {
-          float u[kVocab];
+        for (int k = 0; k < kVocab; ++k) s_stage[warp][gi][k * 32 + lane] = pre[gi][k];
+      __syncwarp();
+      prefetch(m0 + kNoiseGroup);              // next group's loads fly during the draws below
 #pragma unroll
-          for (int v = 0; v < kVocab; ++v) u[v] = stage[lane * kVocab + v];
-          draw = kFast ? gumbel_argmax5_checked(q, u) : gumbel_argmax5(q, u);
+      for (int gi = 0; gi < kNoiseGroup; ++gi) {
+        const int m = m0 + gi;
+        if (m < M && valid) {
+          int draw = tok;
+          if (masked) {
+            float u[kVocab];
+#pragma unroll
+            for (int v = 0; v < kVocab; ++v) u[v] = s_stage[warp][gi][lane * kVocab + v];
+            draw = kFast ? gumbel_argmax5_checked(q, u) : gumbel_argmax5(q, u);
+          }
+          cp[(size_t)m * BL] = (Tok)draw;
         }
-        __syncwarp();
-        if (valid) store_tok(cand, (size_t)m * BL + pos, draw);
       }
+      __syncwarp();
     }
   } else {
     const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
     const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32);
     const uint32_t row = (uint32_t)(row_offset + pos / L);
     const uint32_t l = (uint32_t)(pos % L);
-    for (int m = m_begin; m < m_end; ++m) {
+    for (int m = 0; m < M; ++m) {
       if (!valid) continue;
       int draw = tok;
       if (masked) {
@@ -223,7 +225,7 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
                                  philox_uniform(e.x)};
         draw = kFast ? gumbel_argmax5_checked(q, u) : gumbel_argmax5(q, u);
       }
-      store_tok(cand, (size_t)m * BL + pos, draw);
+      cp[(size_t)m * BL] = (Tok)draw;
     }
   }
 }
@@ -429,7 +431,7 @@ int subs_sample_impl(const float* logits, int is_log_p, const void* x, int tok_d
   const unsigned grid = (unsigned)ceil_div<int64_t>(BL, kThreads);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(Tok, INJ, FAST)                                                        \
-  launch_k((subs_sample_kernel<Tok, INJ, FAST>), dim3(grid, (unsigned)ceil_div(M, kCandChunk)), dim3(kThreads), 0, st, 1,                       \
+  launch_k((subs_sample_kernel<Tok, INJ, FAST>), dim3(grid), dim3(kThreads), 0, st, 1,                       \
       logits, is_log_p, (const Tok*)x, U, seed, seed_dev, (uint32_t)step, row_offset, \
       mc_t, mc_s, (Tok*)cand, q_out, BL, L, M)
 #define LAUNCH2(Tok, INJ) do { if (fast) LAUNCH(Tok, INJ, true); else LAUNCH(Tok, INJ, false); } while (0)

@@ -162,6 +162,38 @@ EPI_CASES = [
 ]
 
 
+@pytest.mark.parametrize('S,L,K,N,taps', [(7, 100, 256, 256, 5), (40, 50, 128, 896, 5), (3, 25, 64, 128, 5),
+                                          (130, 100, 768, 768, 5), (5, 30, 64, 256, 9)])
+def test_halo_conv_rows_as_descriptor_offsets(cuda, S, L, K, N, taps):
+  """HALO mode: activations laid out as flat rows with taps/2 zero rows either side of every
+  sequence; the A tile is fetched once per K block with taps-1 extra rows and each tap is a
+  row offset of the UMMA shared-memory descriptor.  Valid rows must equal conv1d with zero
+  padding; two outputs (z and GELU(BN(z))) as the Enformer tower uses it."""
+  g = torch.Generator().manual_seed(S * 31 + L)
+  pad = taps // 2
+  Lp = L + 2 * pad
+  A = torch.randn(S, L, K, generator=g).bfloat16()
+  W = (torch.randn(taps, N, K, generator=g) * (K * taps) ** -0.5).bfloat16()
+  bias = torch.randn(N, generator=g)
+  scale2 = torch.rand(N, generator=g) + 0.5
+  shift2 = torch.randn(N, generator=g) * 0.1
+  Ap = torch.zeros(S, Lp, K, dtype=torch.bfloat16)
+  Ap[:, pad:pad + L] = A
+  out = torch.empty(S * Lp, N, dtype=torch.bfloat16, device=cuda)
+  out2 = torch.empty(S * Lp, N, dtype=torch.bfloat16, device=cuda)
+  _lib.selftest_gemm_epilogue(Ap.reshape(1, S * Lp, K).to(cuda), W.to(cuda), taps=taps, flat=2, bias=bias.to(cuda),
+                              out=out, out2=out2, scale2=scale2.to(cuda), shift2=shift2.to(cuda), act2=2)
+  ref = F.conv1d(A.float().transpose(1, 2), W.float().permute(1, 2, 0), bias, padding=pad).transpose(1, 2)
+  got = out.float().cpu().reshape(S, Lp, N)[:, pad:pad + L]
+  err = float((got - ref).abs().max()) / float(ref.abs().max())
+  assert err < 1e-2, err
+  v = ref * scale2 + shift2
+  ref2 = v * torch.sigmoid(1.702 * v)
+  got2 = out2.float().cpu().reshape(S, Lp, N)[:, pad:pad + L]
+  err2 = float((got2 - ref2).abs().max()) / float(ref2.abs().max())
+  assert err2 < 2e-2, err2
+
+
 @pytest.mark.parametrize('S,L,K,N,taps,flat,odt,use_res,dual,act,aar,use_scale', EPI_CASES)
 def test_gemm_fused_epilogues(cuda, S, L, K, N, taps, flat, odt, use_res, dual, act, aar, use_scale):
   """Every epilogue combination the networks use (bias / BN affine / activation / residual /
