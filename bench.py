@@ -279,17 +279,43 @@ def main():
     torch.cuda.synchronize()
     _lib.profile_begin()
     scorer.score(cand)
-    den.forward(cand[:B], 0.0)
     torch.cuda.synchronize()
     gemm_ms, gemm_n, gemm_flops = _lib.profile_end()
+    top = _lib.profile_top()
+    # the denoiser is one fused tcgen05 kernel (den_fused_kernel): timed with its own event pair
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record(); den.forward(cand[:B], 0.0); d1.record()
+    torch.cuda.synchronize()
+    den_ms = d0.elapsed_time(d1)
+    gemm_ms += den_ms
+    gemm_n += 1
+    gemm_flops += B * F_DEN
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     step_ms = ms_per_step / NUM_STEPS       # one reverse step (the +1 denoiser forward is <0.1%)
-    roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one '
-                'reverse step: value net on B*M candidates + denoiser on B',
+    try:
+      with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        traffic = json.load(f)
+    except Exception:
+      traffic = {}
+    top_ach = top['flops'] / (top['ms'] * 1e-3) / 1e12 if top['ms'] > 0 else None
+    roofline = {'bound': 'tensor', 'kernel': 'tcgen05 GEMM family (gemm2_kernel implicit-GEMM launches of the value net on '
+                'B*M candidates + the fused denoiser kernel on B): every tensor-core launch of one reverse step',
                 'achieved': achieved, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tf_sust'], 'traffic': None, 'peak_source': pk['src'] + ', sustained',
+                'frac': achieved / pk['tf_sust'],
+                'traffic': traffic.get('gemm_family_dram_bytes_per_step'),
+                'traffic_source': traffic.get('source'),
+                'peak_source': pk['src'] + ', sustained',
                 'launches': gemm_n, 'flops_per_step': gemm_flops, 'gemm_ms_per_step': gemm_ms,
-                'share_of_step': gemm_ms / step_ms if step_ms > 0 else None}
+                'denoiser_ms': den_ms,
+                'share_of_step': gemm_ms / step_ms if step_ms > 0 else None,
+                'flop_count': 'nominal dense 2*MAC incl. zero-padding taps (SURVEY 8(d)); pair-difference pooling '
+                              'counts its one GEMM, not the reference formulation\'s two',
+                'dominant_launch': {
+                    'shape': top, 'ms': top['ms'], 'achieved': top_ach,
+                    'frac': (top_ach / pk['tf_sust']) if top_ach else None,
+                    'traffic': (traffic.get('dominant_launch') or {}).get('dram_bytes'),
+                    'algorithmic_bytes': (traffic.get('dominant_launch') or {}).get('algorithmic_bytes'),
+                    'ncu_tensor_pipe_pct': (traffic.get('dominant_launch') or {}).get('tensor_pipe_pct')}}
     # HBM-bound stages at BASELINE config 4 (B=4096, M=20): the whole batch on one GPU and the
     # per-GPU shard at N=8; algorithmic bytes in the reference's dtypes
     sched_mc = (0.5, 0.49)

@@ -75,6 +75,9 @@ int64_t svdd_launch_count(void);
  * time, the number of launches and their nominal dense FLOPs. */
 int svdd_profile_begin(void);
 int svdd_profile_end(double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+/* The longest single GEMM launch of the last svdd_profile_begin/end window: its device time,
+ * nominal FLOPs and shape (rows = S*L, K, N, taps, epilogue mode). */
+int svdd_profile_top(double* ms, double* flops, int64_t* rows, int* K, int* N, int* taps, int* mode);
 
 /* ---- stage 2: SUBS + move-chance mixing + Gumbel-max draw + carry-over ----
  * Replaces, fused into one kernel:

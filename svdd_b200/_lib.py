@@ -103,6 +103,16 @@ def profile_begin():
   check(lib().svdd_profile_begin())
 
 
+def profile_top():
+  """Longest GEMM launch of the last profile window: dict(ms, flops, rows, K, N, taps, mode)."""
+  ms, fl = ctypes.c_double(), ctypes.c_double()
+  rows = ctypes.c_int64()
+  K, N, taps, mode = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+  check(lib().svdd_profile_top(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(rows), ctypes.byref(K),
+                               ctypes.byref(N), ctypes.byref(taps), ctypes.byref(mode)))
+  return dict(ms=ms.value, flops=fl.value, rows=rows.value, K=K.value, N=N.value, taps=taps.value, mode=mode.value)
+
+
 def profile_end():
   """-> (ms summed over conv_gemm launches, number of launches, nominal dense FLOPs)."""
   ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()

@@ -281,7 +281,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int tiles_s = ceil_div(g.S, g.BS);
   const int64_t m_tiles = (int64_t)tiles_l * tiles_s;
   const int64_t mp_tiles = (m_tiles + CG - 1) / CG;
-  const int n_tiles = g.N / BN;
+  const int n_tiles = (g.N + BN - 1) / BN;   // the last tile may be ragged (N % BN != 0): TMA clips / zero-fills
+  const int n_end = g.n_off + g.N;
   const int64_t total_tiles = mp_tiles * n_tiles;
   const int kblocks = g.K / kBK;
   const int kblocks2 = g.K2 / kBK;         // K-concatenated second operand (0 = none)
@@ -504,10 +505,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
       float* P = s_param + acc_stage * (kParamVecs * BN);
       for (int i = etid; i < BN; i += kEpiThreads) {
-        if (ep.bias) P[P_BIAS * BN + i] = ep.bias[n0 + i];
-        if (ep.scale) { P[P_SCALE * BN + i] = ep.scale[n0 + i]; P[P_SHIFT * BN + i] = ep.shift[n0 + i]; }
-        if (ep.scale2) { P[P_SCALE2 * BN + i] = ep.scale2[n0 + i]; P[P_SHIFT2 * BN + i] = ep.shift2[n0 + i]; }
-        if (MODE == EPI_HEADDOT) P[P_HEADW * BN + i] = ep.head_w[n0 + i];
+        const bool in_n = n0 + i < n_end;
+        if (ep.bias) P[P_BIAS * BN + i] = in_n ? ep.bias[n0 + i] : 0.0f;
+        if (ep.scale) { P[P_SCALE * BN + i] = in_n ? ep.scale[n0 + i] : 0.0f; P[P_SHIFT * BN + i] = in_n ? ep.shift[n0 + i] : 0.0f; }
+        if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? ep.shift2[n0 + i] : 0.0f; }
+        if (MODE == EPI_HEADDOT) P[P_HEADW * BN + i] = in_n ? ep.head_w[n0 + i] : 0.0f;
       }
       gemm_detail::epi_bar_sync();
 
@@ -554,7 +556,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             v[i] = fmaf(w1, yd[i], pv[i]);
           }
           if (ep.out != nullptr) {         // last stage: fp32 transformer stream, direct
-            if (valid) gemm_detail::store_row32(ep.out, DT_F32, row * ep.ld_out + n0 + c0, v);
+            if (valid && n0 + c0 < n_end) gemm_detail::store_row32(ep.out, DT_F32, row * ep.ld_out + n0 + c0, v);
           }
           if (ep.out2 != nullptr) {
             if (ep.scale2 != nullptr) {
@@ -584,7 +586,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (has_res || (kPair && ep.res != nullptr)) {
           if (has_out || kPair) {
             slab_read(buf0, x7, out_f32, cis, pv);
-          } else if (valid) {            // HEADDOT with a residual: direct (unused by the nets)
+          } else if (valid && n0 + c0 < n_end) {   // HEADDOT with a residual: direct (unused by the nets)
             gemm_detail::load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n0 + c0, pv);
           }
 #pragma unroll
@@ -621,7 +623,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           act32(v, ep.act2);
           if (out2_staged) {
             slab_write(has_out ? buf1 : buf0, x7, out_f32, cis, v);
-          } else if (valid) {            // residual + second output (one launch per pass): direct
+          } else if (valid && n0 + c0 < n_end) {   // residual + second output (one launch per pass): direct
             gemm_detail::store_row32(ep.out2, ep.out2_dtype, row * ep.ld_out2 + n0 + c0, v);
           }
         }
