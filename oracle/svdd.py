@@ -306,3 +306,36 @@ def sample_with_mid(denoiser, B, L, num_steps=128, eps=1e-5, noise=None):
     if i != num_steps - 1:
       mid.append(x.clone())
   return noise_removal(denoiser, x), mid
+
+
+def sample_ddpm_cache(denoiser, B, L, num_steps=128, eps=1e-5, noise=None, time_conditioning=False,
+                      log_p_fn=None):
+  """Diffusion._sample with sampling.predictor == 'ddpm_cache' (diffusion_gosai.py:755-773,
+  :858-865): the move chances are t and t - dt themselves (no noise schedule), and the
+  post-SUBS probabilities p_x0 are reused for the next step while the whole batch is
+  unchanged (and time conditioning is off).  Returns (x, mid, number of denoiser forwards
+  incl. noise removal).  `log_p_fn(x)` may replace SUBS(denoiser(x)) (the GPU tests feed
+  the engine's own log-probabilities)."""
+  noise = noise or TorchNoise()
+  fwd = log_p_fn if log_p_fn is not None else (lambda x: forward_log_p(denoiser, x))
+  ts = torch.linspace(1, eps, num_steps + 1)              # :835-836
+  dt = (1 - eps) / num_steps                                # :837
+  x = torch.full((B, L), MASK_INDEX, dtype=torch.int64)
+  mid, p_cache, n_fwd = [], None, 0
+  for i in range(num_steps):
+    t = ts[i] * torch.ones(B, 1)
+    mc_t = t[:, None, :]                                    # :761 move_chance_t = t[:, None, None]
+    mc_s = (t - dt)[:, None, :]                             # :762
+    if p_cache is None:
+      p_cache = fwd(x).exp()                                # :765
+      n_fwd += 1
+    q = p_cache * (mc_t - mc_s)                             # :768
+    q[:, :, MASK_INDEX] = mc_s[:, :, 0]                     # :769
+    x_next = draw_candidates(x, q, noise.draws(i, 1, B, L))[0]
+    if not torch.equal(x_next, x) or time_conditioning:     # :861-864 (allclose on integers)
+      p_cache = None
+    x = x_next
+    if i != num_steps - 1:
+      mid.append(x.clone())
+  x = fwd(x)[:, :, :-1].argmax(dim=-1)                      # noise removal :872-880
+  return x, mid, n_fwd + 1

@@ -212,16 +212,17 @@ class Diffusion(nn.Module):
     return final, x, q, (x != self.mask_index).to(x.dtype)
 
   # -- the engine: whole-trajectory loops ------------------------------------------------------
-  def _resolve(self, num_steps, eval_sp_size):
+  def _resolve(self, num_steps, eval_sp_size, predictors=('ddpm',)):
     B = self.config.loader.eval_batch_size if eval_sp_size is None else eval_sp_size
     if self.parameterization == 'ar':
       raise NotImplementedError('autoregressive sampling is not on the decode path')
     if num_steps is None:
       num_steps = self.config.sampling.steps
-    if self.sampler != 'ddpm':
+    if predictors is not None and self.sampler not in predictors:
       raise NotImplementedError(
-          f"sampling.predictor='{self.sampler}': the decode path is built for 'ddpm' "
-          '(configs_gosai*/config_gosai.yaml:36)')
+          f"sampling.predictor='{self.sampler}': this entry point supports {predictors} "
+          "(the SVDD decode path is built for 'ddpm', configs_gosai*/config_gosai.yaml:36; "
+          "'ddpm_cache' exists in _sample only, diffusion_gosai.py:858)")
     return int(B), int(num_steps)
 
   def _trajectory(self, mode, B, num_steps, eps, M=1, scorer=None, tweedie=True, alpha=0.0,
@@ -361,15 +362,64 @@ class Diffusion(nn.Module):
     num_steps-1 intermediate states."""
     if cdq:
       raise NotImplementedError('cdq rollouts belong to value-function training')
-    B, num_steps = self._resolve(num_steps, eval_sp_size)
-    x, mids = self._trajectory('plain', B, num_steps, eps, noise=noise, collect_mid=True)
+    B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=('ddpm', 'ddpm_cache'))
+    if self.sampler == 'ddpm_cache':
+      x, mids = self._sample_ddpm_cache(B, num_steps, eps, noise=noise)
+    else:
+      x, mids = self._trajectory('plain', B, num_steps, eps, noise=noise, collect_mid=True)
     return x.long(), [m.long() for m in mids]
+
+  def _sample_ddpm_cache(self, B, num_steps, eps, noise=None):
+    """predictor 'ddpm_cache' (diffusion_gosai.py:755-773 and :858-865): the move chances are t
+    and t - dt themselves, and the post-SUBS log-probabilities are reused for the next step while
+    no token of the batch changed (and time conditioning is off) -- the denoiser forward, i.e.
+    all of stage 1, is skipped on those steps.  Like the reference (torch.allclose per step) the
+    change test is a host-side decision, so this loop is not graph-captured.
+    ``self.last_denoiser_forwards`` records how many forwards the run needed."""
+    dev = self.device
+    if dev.type != 'cuda':
+      raise _lib.SvddError('move the model to a CUDA device (svdd_b200 has no CPU path)')
+    L = int(self.config.model.length)
+    den = self.backbone.packed()
+    tc = self.time_conditioning
+    seed = self._seed_for_call()
+    ts = torch.linspace(1, eps, num_steps + 1)                   # :835-836 (fp32)
+    dt = (1 - eps) / num_steps                                   # :837
+    u8 = torch.uint8
+    x = torch.full((B, L), self.mask_index, dtype=u8, device=dev)
+    x2 = torch.empty((B, L), dtype=u8, device=dev)
+    logits = torch.empty((B, L, 5), dtype=torch.float32, device=dev)
+    log_p, n_fwd, mids = None, 0, []
+    for i in range(num_steps):
+      t = ts[i].reshape(1, 1)
+      mc_t, mc_s = float(t), float(t - dt)                       # :761-762, fp32 tensor arithmetic
+      if log_p is None:
+        sigma_t = float(self.noise(t)[0]) if tc else 0.0
+        den.forward(x, sigma_t, out=logits)
+        log_p = _lib.subs_log_p(logits, x)                       # p_x0 = forward(x).exp() (:765)
+        n_fwd += 1
+      _lib.subs_sample(log_p, x, 1, mc_t, mc_s, U=None if noise is None else noise.draws(i),
+                       step=i, is_log_p=True, out=x2[None], seed=seed)
+      if tc or bool((x2 != x).any()):                            # :861-864
+        log_p = None
+      x, x2 = x2, x
+      if i != num_steps - 1:
+        mids.append(x.clone())
+    if self.config.sampling.noise_removal:
+      sigma_last = float(self.noise(ts[-1].reshape(1, 1))[0]) if tc else 0.0
+      den.forward(x, sigma_last, out=logits)
+      n_fwd += 1
+      x = _lib.x0_argmax(logits, x, out=x2)
+    self.last_denoiser_forwards = n_fwd
+    return x, mids
 
   @torch.no_grad()
   def decode_sample(self, num_steps=None, eps=1e-5, eval_sp_size=None, cdq=False, noise=None,
                     row_offset=0, trace=None):
     """Plain ancestral sampling, the "pre-trained" baseline (diffusion_gosai.py:889-936)."""
-    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=('ddpm', 'ddpm_cache'))
+    if self.sampler == 'ddpm_cache':                           # diffusion_gosai.py:912-919
+      return self._sample_ddpm_cache(B, num_steps, eps, noise=noise)[0].long()
     return self._trajectory('plain', B, num_steps, eps, noise=noise, row_offset=row_offset,
                             trace=trace).long()
 
@@ -379,7 +429,7 @@ class Diffusion(nn.Module):
                         trace=None, x_init=None):
     """SVDD-MC (diffusion_gosai.py:1022-1061).  ``alpha``/``noise``/``row_offset``/``trace``
     are additions: alpha=0 is the reference's argmax selection."""
-    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=None)   # :1040 / :1124 ignore the predictor
     scorer = _as_scorer(pre_scorer_embedding, pre_scorer_head)
     return self._trajectory('mc', B, num_steps, eps, M=int(sample_M), scorer=scorer, alpha=alpha,
                             noise=noise, row_offset=row_offset, trace=trace, x_init=x_init).long()
@@ -392,7 +442,7 @@ class Diffusion(nn.Module):
     x0-prediction is used only when ``options`` equals the STRING "True" (:1414)."""
     if task == 'rna_saluki':
       raise NotImplementedError('rna_saluki needs a private .npy the reference does not ship')
-    B, num_steps = self._resolve(num_steps, eval_sp_size)
+    B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=None)   # :1040 / :1124 ignore the predictor
     scorer = (reward_model if hasattr(reward_model, 'score')
               else _as_scorer(reward_model.embedding, reward_model.head))
     return self._trajectory('pm', B, num_steps, eps, M=int(sample_M), scorer=scorer,

@@ -264,9 +264,29 @@ def gen_trajectories():
   save('trajectories.npz', **out)
 
 
+def gen_ddpm_cache():
+  """_sample with predictor 'ddpm_cache' (diffusion_gosai.py:755-773, 858-865): many small steps
+  so that most steps leave the batch unchanged and reuse the cached p_x0."""
+  d = ref_diffusion(50)
+  d.sampler = 'ddpm_cache'
+  calls = [0]
+  orig = d.backbone.forward
+  def counted(*a, **k):
+    calls[0] += 1
+    return orig(*a, **k)
+  d.backbone.forward = counted
+  B, steps = 2, 160
+  torch.manual_seed(77)
+  with RandLikeTap() as tap, torch.no_grad():
+    x, mid = d._sample(num_steps=steps, eval_sp_size=B)
+  save('ddpm_cache.npz', tokens=x, mid=torch.stack(mid), U=torch.stack(tap.record).reshape(steps, 1, B, 50, 5),
+       n_forward=np.int64(calls[0]))
+
+
 if __name__ == '__main__':
   gen_schedule()
   gen_stage_kats()
   gen_denoiser()
   gen_value_nets()
   gen_trajectories()
+  gen_ddpm_cache()

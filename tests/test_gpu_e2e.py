@@ -139,6 +139,49 @@ def test_plain_and_sample_with_reference_logits(cuda):
   np.testing.assert_array_equal(out.cpu().numpy(), g['plain_tokens'])
 
 
+def test_ddpm_cache_predictor(cuda):
+  """sampling.predictor == 'ddpm_cache' (diffusion_gosai.py:755-773, 858-865) in _sample:
+  (1) replaying the reference's fp32 logits call by call reproduces the golden tokens, every
+  intermediate state and the number of denoiser forwards (78 of 161: the cache skips stage 1
+  while the batch is unchanged); (2) with the tensor-core denoiser in the loop every
+  transition is the oracle's given the engine's own log-probabilities."""
+  g = helpers.load_golden('ddpm_cache.npz')
+  denoiser, _, _ = _oracle_fns()
+  U = T(g['U'])
+  seq = []
+
+  def recording_log_p(x):
+    lg = denoiser(x)
+    seq.append(lg.to(cuda))
+    return svdd.subs_parameterization(lg, x)
+  with torch.no_grad():
+    x_o, mid_o, n_o = svdd.sample_ddpm_cache(None, 2, 50, 160, noise=svdd.ArrayNoise(g['U']),
+                                             log_p_fn=recording_log_p)
+  np.testing.assert_array_equal(x_o.numpy(), g['tokens'])
+  m = _rna_model(cuda)
+  m.sampler = 'ddpm_cache'
+  fake = ReplayDenoiser(seq)
+  m.backbone.packed = lambda: fake
+  out, mids = m._sample(num_steps=160, eval_sp_size=2, noise=diffusion_gosai.InjectedNoise(U.to(cuda)))
+  np.testing.assert_array_equal(out.cpu().numpy(), g['tokens'])
+  np.testing.assert_array_equal(torch.stack(mids).cpu().numpy(), g['mid'])
+  assert m.last_denoiser_forwards == int(g['n_forward']) == len(seq)
+  fake.i = 0                                            # decode_sample takes the same branch (:912-919)
+  out_d = m.decode_sample(num_steps=160, eval_sp_size=2, noise=diffusion_gosai.InjectedNoise(U.to(cuda)))
+  np.testing.assert_array_equal(out_d.cpu().numpy(), g['tokens'])
+
+  m2 = _rna_model(cuda)
+  m2.sampler = 'ddpm_cache'
+  out2, mids2 = m2._sample(num_steps=160, eval_sp_size=2, noise=diffusion_gosai.InjectedNoise(U.to(cuda)))
+  sig = torch.zeros(2, device=cuda)
+  with torch.no_grad():
+    x_e, mid_e, n_e = svdd.sample_ddpm_cache(None, 2, 50, 160, noise=svdd.ArrayNoise(g['U']),
+                                             log_p_fn=lambda x: m2.forward(x.to(cuda), sig).cpu())
+  np.testing.assert_array_equal(out2.cpu().numpy(), x_e.numpy())
+  np.testing.assert_array_equal(torch.stack(mids2).cpu().numpy(), torch.stack(mid_e).numpy())
+  assert m2.last_denoiser_forwards == n_e < 161
+
+
 @pytest.mark.parametrize('mode', ['mc', 'pm', 'pm_raw'])
 def test_real_networks_every_transition_matches_oracle(cuda, mode):
   """With the tensor-core networks in the loop, every reverse-step transition is the

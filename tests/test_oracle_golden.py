@@ -153,4 +153,11 @@ def test_trajectories_bit_exact():
     x, mid = svdd.sample_with_mid(denoiser, B=2, L=50, num_steps=8)
     np.testing.assert_array_equal(x.numpy(), g['sample_tokens'])
     np.testing.assert_array_equal(torch.stack(mid).numpy(), g['sample_mid'])
+    # predictor 'ddpm_cache' (diffusion_gosai.py:755-773): tokens, every intermediate state and
+    # the number of denoiser forwards the cache saved (78 of 161) are the reference's
+    gc = helpers.load_golden('ddpm_cache.npz')
+    x, mid, n_fwd = svdd.sample_ddpm_cache(denoiser, B=2, L=50, num_steps=160, noise=svdd.ArrayNoise(gc['U']))
+    np.testing.assert_array_equal(x.numpy(), gc['tokens'])
+    np.testing.assert_array_equal(torch.stack(mid).numpy(), gc['mid'])
+    assert n_fwd == int(gc['n_forward']) and n_fwd < 161
   assert int(x.max()) <= 3
