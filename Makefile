@@ -4,7 +4,7 @@
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall \
-             --expt-relaxed-constexpr -Xptxas -v
+             --expt-relaxed-constexpr -Xptxas -v $(EXTRA_NVCCFLAGS)
 CSRC      := svdd_b200/csrc
 SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))

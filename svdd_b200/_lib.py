@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsvdd_b200.so')
+# SVDD_LIB_PATH: an alternative build of the same library (A/B experiments)
+LIB_PATH = os.environ.get('SVDD_LIB_PATH') or os.path.join(_HERE, 'libsvdd_b200.so')
 
 SVDD_TOK_I64, SVDD_TOK_U8 = 0, 1
 

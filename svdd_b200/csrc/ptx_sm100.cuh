@@ -45,8 +45,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef SVDD_MBAR_HINT_NS
+#define SVDD_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SVDD_MBAR_HINT_NS > 0
+  // suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+  // expires) instead of returning to the polling loop
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SVDD_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -54,6 +68,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Spins on try_wait (which suspends in hardware between polls).  A pipeline bug
@@ -62,8 +77,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#if SVDD_MBAR_HINT_NS == 0
     __nanosleep(16);   // do not steal issue slots from the epilogue warps while waiting
-    if (++spins == (1u << 24)) {
+#endif
+    if (++spins == ((1u << 24) >> (SVDD_MBAR_HINT_NS > 0 ? 6 : 0))) {
       printf("svdd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
              (int)threadIdx.x);
       __trap();
