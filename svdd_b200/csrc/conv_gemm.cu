@@ -156,8 +156,23 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
   const int64_t m_tiles = (int64_t)ceil_div(g.L, g.BL) * ceil_div(g.S, g.BS);
   const int64_t tiles = ceil_div<int64_t>(m_tiles, CG) * ceil_div(g.N, BN);
   if (tiles == 0) return SVDD_OK;
+  SVDD_CHECK_ARG(m_tiles * ceil_div(g.N, BN) < ((int64_t)1 << 30), "conv_gemm: too many tiles for one launch");
   const int64_t max_clusters = num_sms() / CG;
   const int grid = (int)(tiles < max_clusters ? tiles : max_clusters) * CG;
+  static int prefetch_w = -1;
+  if (prefetch_w < 0) { const char* e = getenv("SVDD_PREFETCH_W"); prefetch_w = e ? atoi(e) : 0; }   // measured neutral-to-negative on the c2 step (195.8 vs 193.9 seq/s): off
+  GemmShape gk = g;
+  gk.prefetch_w = (prefetch_w && tiles <= 2 * max_clusters) ? 1 : 0;
+  // SVDD_TIMELINE=1 (debugging): synchronise after every launch and print CTA 0's milestones
+  static int timeline = -1;
+  static unsigned long long* tl_dev = nullptr;
+  if (timeline < 0) { const char* e = getenv("SVDD_TIMELINE"); timeline = e ? atoi(e) : 0; }
+  EpiParams epk = ep;
+  if (timeline) {
+    if (tl_dev == nullptr) SVDD_CUDA(cudaMalloc(&tl_dev, 16 * sizeof(unsigned long long)));
+    SVDD_CUDA(cudaMemsetAsync(tl_dev, 0, 16 * sizeof(unsigned long long), stream));
+    epk.timeline = tl_dev;
+  }
   ProfState& P = prof();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (P.on) {
@@ -166,7 +181,17 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     SVDD_CUDA(cudaEventRecord(e0, stream));
   }
   SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm2::kThreads), kSmem, stream, CG,
-                     tmA, tmW, tmO, tmO2, tmR, tmR2, g, ep));
+                     tmA, tmW, tmO, tmO2, tmR, tmR2, gk, epk));
+  if (timeline) {
+    unsigned long long h[16];
+    SVDD_CUDA(cudaStreamSynchronize(stream));
+    SVDD_CUDA(cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    auto d = [&](int i) { return h[i] ? (long long)(h[i] - h[0]) : -1ll; };
+    fprintf(stderr, "timeline mode %d rows %lld K %d N %d taps %d tiles %lld: setup %lld first_tma %lld last_tma_tile0 %lld "
+            "first_full %lld mma_done %lld epi_start %lld epi_end %lld stores_done %lld pre_sync %lld exit %lld (cycles)\n",
+            MODE, (long long)g.S * g.L, g.K, g.N, g.taps, (long long)tiles, d(1), d(2), d(10), d(3), d(4), d(5), d(6), d(7),
+            d(8), d(9));
+  }
   count_launch();
   if (P.on) {
     SVDD_CUDA(cudaEventRecord(e1, stream));
@@ -303,6 +328,15 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     const int bn2 = pick_bn2(g, cg, mode);
     EpiParams ep2 = ep_in;
     if (ep2.out == nullptr && ep2.out2 != nullptr) ep2.out_dtype = ep2.out2_dtype;   // slab geometry follows the staged output
+    {
+      // x += GEMM (the transformer's out-projection and second FFN linear): no residual read, the
+      // fp32 slab is accumulated into `out` by a TMA reduce-add
+      static int res_reduce = -1;
+      if (res_reduce < 0) { const char* e = getenv("SVDD_RES_REDUCE"); res_reduce = e ? atoi(e) : 1; }
+      ep2.res_reduce = (res_reduce && mode == EPI_GENERIC && ep2.res != nullptr && ep2.res == ep2.out &&
+                        ep2.out_dtype == DT_F32 && ep2.res_dtype == DT_F32 && ep2.out2 == nullptr &&
+                        !ep2.act_after_res && ep2.ld_res == ep2.ld_out) ? 1 : 0;
+    }
     CUtensorMap tA, tW, tO, tO2, tR, tR2;
     if (g.halo) {
       SVDD_CHECK_ARG(mode == EPI_GENERIC && cg == 2 && g.S == 1 && g.BS == 1 && g.BL == 128 && g.taps % 2 == 1 &&

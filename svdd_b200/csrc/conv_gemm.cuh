@@ -81,6 +81,11 @@ struct EpiParams {
   // tuning switch (set by the launcher from SVDD_EPI_PREFETCH, default on): fetch bf16
   // residual / pooled rows ahead of the accumulator wait
   int prefetch = 1;
+  // conv_gemm2, set by the launcher: `res` is `out` itself (fp32, in place) -> the residual is
+  // never loaded, the epilogue stores acc (+bias, act) with a TMA reduce-add into `out`
+  int res_reduce = 0;
+  // debugging aid (SVDD_TIMELINE=1): CTA 0 stamps clock64() at its pipeline milestones
+  unsigned long long* timeline = nullptr;
 };
 
 struct GemmShape {
@@ -100,6 +105,9 @@ struct GemmShape {
   // K block with taps-1 extra rows and each tap is a row offset of the smem descriptor.  The
   // caller guarantees `taps/2` zero rows between consecutive sequences of the flat row space.
   int halo = 0;
+  // conv_gemm2: L2-prefetch this CTA's weight slice of its first tile at kernel start (set by the
+  // launcher for launches with at most two tiles per CTA pair; SVDD_PREFETCH_W=0 disables)
+  int prefetch_w = 0;
   // rows between consecutive sequences of A when they are not densely packed (0 = L_in)
   int a_pitch = 0;
   // rows that carry real data, for the FLOP accounting of padded layouts (0 = S * L)

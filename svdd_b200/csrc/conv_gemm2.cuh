@@ -183,6 +183,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// the same box, accumulated into global memory (fp32 add performed by the memory system)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -276,23 +282,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  auto stamp = [&](int slot) {
+    if (ep.timeline != nullptr && blockIdx.x == 0) ep.timeline[slot] = (unsigned long long)clock64();
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   const int tiles_l = ceil_div(g.L, g.BL);
   const int tiles_s = ceil_div(g.S, g.BS);
-  const int64_t m_tiles = (int64_t)tiles_l * tiles_s;
-  const int64_t mp_tiles = (m_tiles + CG - 1) / CG;
+  // tile indices fit 32 bits (checked by the launcher): 64-bit div/mod is a ~150-cycle software
+  // routine and tile_coords sits on the critical path before the first TMA of every launch
+  const int m_tiles = tiles_l * tiles_s;
+  const int mp_tiles = (m_tiles + CG - 1) / CG;
   const int n_tiles = (g.N + BN - 1) / BN;   // the last tile may be ragged (N % BN != 0): TMA clips / zero-fills
   const int n_end = g.n_off + g.N;
-  const int64_t total_tiles = mp_tiles * n_tiles;
+  const int total_tiles = mp_tiles * n_tiles;
   const int kblocks = g.K / kBK;
   const int kblocks2 = g.K2 / kBK;         // K-concatenated second operand (0 = none)
-  const int64_t first_tile = blockIdx.x / CG;
-  const int64_t tile_step = gridDim.x / CG;
+  const int first_tile = (int)(blockIdx.x / CG);
+  const int tile_step = (int)(gridDim.x / CG);
 
   constexpr bool kPair = (MODE == EPI_PAIR), kPool2 = (MODE == EPI_POOL2);
   const bool out_f32 = !(kPair || kPool2) && ep.out_dtype == DT_F32;  // dtype of the staged slabs
   const bool has_out = (MODE == EPI_GENERIC) && ep.out != nullptr;
-  const bool has_res = (MODE == EPI_GENERIC || MODE == EPI_HEADDOT) && ep.res != nullptr;
+  const bool red_res = (MODE == EPI_GENERIC) && ep.res_reduce != 0;   // out += v by TMA reduce-add
+  const bool has_res = (MODE == EPI_GENERIC || MODE == EPI_HEADDOT) && ep.res != nullptr && !red_res;
   const bool out2_staged = (MODE == EPI_GENERIC) && ep.out2 != nullptr && !has_res;
   // slab buffers used per 64/32-column step: EPI_PAIR = {residual in, (yd | y0) out},
   // EPI_POOL2 = {y0 in / next operand out, yd in}
@@ -339,12 +352,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();       // everything above overlapped the previous kernel's tail
   pdl_trigger();
+  if (threadIdx.x == 0) stamp(1);
 
   // coordinates of this CTA's half of pair-tile `t` (rr = rank within the pair)
-  auto tile_coords = [&](int64_t t, int rr) {
+  auto tile_coords = [&](int t, int rr) {
     TileCoord c;
     const int nt = (int)(t % n_tiles);
-    const int64_t mt = (t / n_tiles) * CG + rr;
+    const int mt = (t / n_tiles) * CG + rr;
     c.n0 = g.n_off + nt * BN;    // global column
     c.in_range = mt < m_tiles;
     c.s0 = (int)(mt / tiles_l) * g.BS;       // >= S when out of range: TMA zero-fills / clips
@@ -352,7 +366,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     return c;
   };
   // a tap is issued when it touches real data for either CTA of the pair
-  auto tap_active = [&](int tap, int64_t t) {
+  auto tap_active = [&](int tap, int t) {
     bool any = false;
 #pragma unroll
     for (int rr = 0; rr < CG; ++rr) {
@@ -372,7 +386,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t sa_i = 0, pa = 0, stage = 0, phase = 0;
       const uint32_t txa = (uint32_t)(CG * (g.BL + g.taps - 1) * kBK * 2);
       const uint32_t txb = (uint32_t)(CG * C::kBBytes);
-      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord c = tile_coords(t, rank);
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&emptya_bar[sa_i], pa ^ 1);
@@ -391,7 +405,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (uint32_t)(CG * (g.BL * g.BS * kBK * 2 + C::kBBytes));
-      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+      // Few-tile launches (the transformer GEMMs: one tile per CTA pair) stream a weight slice
+      // nobody else has touched: through a 4-deep ring that is one DRAM round trip per 4 K
+      // blocks.  Prefetching the slice into L2 up front turns those into L2 hits.
+      if (g.prefetch_w && first_tile < total_tiles) {
+        const TileCoord c = tile_coords(first_tile, rank);
+        for (int tap = 0; tap < g.taps; ++tap)
+          for (int kb = 0; kb < kblocks; ++kb)
+            ptx::tma_prefetch_2d(&tmW, kb * kBK, tap * g.N_w + c.n0 + rank * (BN / CG));
+      }
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord c = tile_coords(t, rank);
         for (int tap = 0; tap < g.taps; ++tap) {
           if (!tap_active(tap, t)) continue;
@@ -403,6 +426,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_3d_cg<CG>(sa, &tmA, &full_bar[stage], kb * kBK, l_start, c.s0);
             tma_load_2d_cg<CG>(sb, &tmW, &full_bar[stage], kb * kBK, tap * g.N_w + c.n0 + rank * (BN / CG));
+            if (t == first_tile && tap == 0 && kb == 0) stamp(2);
+            if (t == first_tile && kb == kblocks - 1) stamp(10);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -427,7 +452,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t stage = 0, phase = 0;
       uint32_t sa_i = 0, pa = 0;           // HALO: A ring position
       uint32_t acc_stage = 0, acc_phase = 0;
-      for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         ptx::mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc_stage * BN;
@@ -435,6 +460,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         auto consume_stage = [&]() {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          if (first && lane == 0) stamp(3);
           if (lane == 0) {
             const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
             const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
@@ -479,6 +505,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kb = 0; kb < kblocks2; ++kb) consume_stage();
         }
         if (lane == 0) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
+        if (lane == 0 && t == first_tile) stamp(4);
         __syncwarp();
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
@@ -496,7 +523,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* my_rout = rout_bar + half * 2;
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t job = 0;                    // staged-slab counter of this half
-    for (int64_t t = first_tile; t < total_tiles; t += tile_step) {
+    for (int t = first_tile; t < total_tiles; t += tile_step) {
       const TileCoord tc = tile_coords(t, rank);
       const int n0 = tc.n0;
       const int s = tc.s0 + r / g.BL, l = tc.l0 + r % g.BL;
@@ -519,6 +546,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t raw[2][32];
       ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
       ptx::tc_fence_after();
+      if (t == first_tile && etid == 0) stamp(5);
       ptx::tmem_ld_32x32(taddr, raw[0]);
       uint8_t* buf0 = nullptr;           // slab of the `out` job (holds the residual on entry)
       uint8_t* buf1 = nullptr;           // slab of the staged `out2` job
@@ -641,6 +669,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (MODE == EPI_HEADDOT && valid)
         ep.partials[row * (2 * n_tiles) + 2 * ((n0 - g.n_off) / BN) + half] = head_acc;
+      if (t == first_tile && etid == 0) stamp(6);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else {
@@ -653,7 +682,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int slabs = kHalf / slab_cols;
       const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
       // job iterator: (tile, slab, buffer-of-the-step)
-      struct It { int64_t t; int slab, o; };
+      struct It { int t; int slab, o; };
       auto advance = [&](It& it) {
         if (++it.o == n_out) { it.o = 0; if (++it.slab == slabs) { it.slab = 0; it.t += tile_step; } }
       };
@@ -696,7 +725,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (cur.o == 0 && ep.out2 != nullptr) { tma_store_3d(&tmOut2, buf, col, c.l0, c.s0); stored = true; }
         } else {
           const bool second = (cur.o == 1) || !has_out;      // this job carries `out2`
-          tma_store_3d(second ? &tmOut2 : &tmOut, buf, col, c.l0, c.s0);
+          if (red_res && !second) tma_reduce_add_3d(&tmOut, buf, col, c.l0, c.s0);
+          else tma_store_3d(second ? &tmOut2 : &tmOut, buf, col, c.l0, c.s0);
           stored = true;
         }
         if (stored) {
@@ -708,16 +738,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         advance(cur);
       }
       bulk_wait_all();
+      if (half == 0) stamp(7);
     }
   }
 
   __syncwarp();
   ptx::tc_fence_before();
+  if (threadIdx.x == 0) stamp(8);
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     tmem_dealloc_cg<CG>(tmem_base, C::kTmemCols);
   }
+  if (threadIdx.x == 0) stamp(9);
 }
 
 }  // namespace gemm2
