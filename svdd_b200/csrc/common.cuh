@@ -67,8 +67,8 @@ inline int num_sms() {
 }
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------
-// Every kernel of a reverse step is launched with programmatic stream serialisation: its
-// CTAs may become resident (barrier init, TMEM allocation, tensor-map prefetch) while the
+// With SVDD_PDL=1 every kernel of a reverse step is launched with programmatic stream
+// serialisation: its CTAs may become resident (barrier init, TMEM allocation, tensor-map prefetch) while the
 // previous kernel drains, and block in pdl_wait() until that kernel's memory is visible.
 // Rule: a kernel launched through launch_k() calls pdl_wait() before its first access to
 // global memory another kernel may have written (or may still be reading).
