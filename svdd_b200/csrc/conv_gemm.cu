@@ -255,6 +255,24 @@ int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint
   return encode_bf16_map(map, base, 2, dims, str, box);
 }
 
+int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                       uint32_t box_inner, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t str[1] = {(cuuint64_t)inner * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, str, box);
+}
+
+bool gemm_prof_on() { return prof().on; }
+void gemm_prof_record(cudaEvent_t e0, cudaEvent_t e1, const GemmShape& g, int bn, int mode, double flops) {
+  ProfState& P = prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.ev.push_back(e0);
+  P.ev.push_back(e1);
+  P.flops += flops;
+  P.recs.push_back({g, bn, mode, flops});
+}
+
 int conv_gemm_n_tiles(const GemmShape& g, int mode) {
   if (mode == EPI_HEADDOT && gemm2_enabled() && g.N % 128 == 0) return 2 * (g.N / pick_bn2(g, gemm2_cg()));
   return 2 * (g.N / pick_bn(g, mode));

@@ -672,6 +672,14 @@ int conv_gemm_n_tiles(const GemmShape& shape, int mode);
 // 128B-swizzled 2-D tensor map over a row-major bf16 matrix [rows, inner] (inner contiguous).
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                         uint32_t box_inner, uint32_t box_rows);
+// the same over an fp32 matrix (box_inner * 4 bytes <= 128)
+int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                       uint32_t box_inner, uint32_t box_rows);
+
+// per-launch profile window (svdd_profile_begin / _end): kernels outside conv_gemm.cu that
+// belong to the tensor-core family record themselves here
+bool gemm_prof_on();
+void gemm_prof_record(cudaEvent_t e0, cudaEvent_t e1, const GemmShape& g, int bn, int mode, double flops);
 
 // Picks (BL, BS) for a conv over sequences of length L: whole-sequence tiles when
 // L <= 128 (several sequences per tile), else 128-position tiles.

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "conv_gemm.cuh"
+#include "tower.cuh"
 #include "weights.cuh"
 
 namespace svdd {
@@ -114,7 +115,7 @@ ef_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const flo
 // Warp-per-row variant for C % 128 == 0, C <= 128 * kLnWarpVecs: the row lives in registers as
 // float4s (coalesced 512 B per warp per load), both statistics are warp shuffles, the bf16
 // result goes out as 8-byte stores.  Same arithmetic as ef_ln_kernel (two-pass variance).
-constexpr int kLnWarpVecs = 16;    // C <= 2048
+constexpr int kLnWarpVecs = tower::kLnVecs;    // C <= 2048
 constexpr int kLnWarpsPerBlock = 8;
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 ef_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
@@ -124,43 +125,7 @@ ef_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g, cons
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int nvec = C >> 7;                       // float4s per lane
-  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
-  float4 v[kLnWarpVecs];
-  float sum = 0.0f;
-#pragma unroll
-  for (int i = 0; i < kLnWarpVecs; ++i) {
-    if (i < nvec) {
-      v[i] = xr[i * 32 + lane];
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
-  float sq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < kLnWarpVecs; ++i) {
-    if (i < nvec) {
-      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)C + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  const float4* b4 = reinterpret_cast<const float4*>(b);
-  uint2* o2 = reinterpret_cast<uint2*>(out + row * C);
-#pragma unroll
-  for (int i = 0; i < kLnWarpVecs; ++i) {
-    if (i < nvec) {
-      const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
-      const float y0 = (v[i].x - mean) * rstd * gg.x + bb.x, y1 = (v[i].y - mean) * rstd * gg.y + bb.y;
-      const float y2 = (v[i].z - mean) * rstd * gg.z + bb.z, y3 = (v[i].w - mean) * rstd * gg.w + bb.w;
-      o2[i * 32 + lane] = make_uint2(gemm_detail::pack_bf16x2(y0, y1), gemm_detail::pack_bf16x2(y2, y3));
-    }
-  }
+  tower::ln_warp_row<false>(x + row * C, g, b, out + row * C, C, lane);
 }
 
 int launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* out, int64_t rows, int C,
@@ -233,7 +198,7 @@ ef_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb
 // holds the softmax and produces dv/32 output channels per position.  One pass over qkv
 // (coalesced 128 B segments) instead of a block per sequence looping over heads.
 constexpr int kAttnSmallN = 4;     // n <= 4
-constexpr int kAttnDkPer = 4;      // dk <= 128
+constexpr int kAttnDkPer = tower::kAttnDkPer;      // dk <= 128
 constexpr int kAttnWarps = 8;
 template <int N>
 __global__ void __launch_bounds__(kAttnWarps * 32)
@@ -248,67 +213,47 @@ ef_attention_warp_kernel(const float* __restrict__ qkv, const float* __restrict_
   const int64_t seq = w / H;
   const int h = (int)(w % H);
   const int ld = 2 * H * dk + H * dv;
-  const float* base = qkv + seq * N * ld;
-  const float scale = rsqrtf((float)dk);
-  float lg[N][N];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j < N; ++j) lg[i][j] = 0.0f;
-#pragma unroll
-  for (int t = 0; t < kAttnDkPer; ++t) {
-    const int d = lane + 32 * t;
-    if (d < dk) {
-      const float cb = rcb[h * dk + d], pb = rpb[h * dk + d];
-      float q[N], k[N], rk[2 * N - 1];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        q[i] = base[i * ld + h * dk + d] * scale;
-        k[i] = base[i * ld + H * dk + h * dk + d];
-      }
-#pragma unroll
-      for (int p = 0; p < 2 * N - 1; ++p) rk[p] = relk[((size_t)h * (2 * N - 1) + p) * dk + d];
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j < N; ++j) lg[i][j] += (q[i] + cb) * k[j] + (q[i] + pb) * rk[j - i + N - 1];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lg[i][j] += __shfl_xor_sync(0xffffffffu, lg[i][j], o);
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    float mx = lg[i][0];
-#pragma unroll
-    for (int j = 1; j < N; ++j) mx = fmaxf(mx, lg[i][j]);
-    float den = 0.0f;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { lg[i][j] = __expf(lg[i][j] - mx); den += lg[i][j]; }
-    const float inv = 1.0f / den;
-#pragma unroll
-    for (int j = 0; j < N; ++j) lg[i][j] *= inv;
-  }
-  for (int d = lane; d < dv; d += 32) {
-    float vv[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) vv[j] = base[j * ld + 2 * H * dk + h * dv + d];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) acc += lg[i][j] * vv[j];
-      out[(seq * N + i) * (size_t)(H * dv) + h * dv + d] = __float2bfloat16_rn(acc);
-    }
-  }
+  tower::attn_warp_task<N, false>(qkv + seq * N * ld, ld, rcb, rpb, relk, out + seq * N * (size_t)(H * dv), h, H, dk, dv,
+                                  lane);
+}
+
+// Warp-per-sequence variant (all heads of one sequence, the q / k / v rows as float4s with every
+// load of a stage in flight; tower::attn_warp_seq): H*dk == 512, H*dv in {1536, 384}, n <= 2.
+template <int N, int T, int U>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+ef_attention_seq_kernel(const float* __restrict__ qkv, const float* __restrict__ rcb,
+                        const float* __restrict__ rpb, const float* __restrict__ relk,
+                        __nv_bfloat16* __restrict__ out, int64_t rows, int H, int dk, int dv) {
+  __shared__ float s_w[kAttnWarps][128];
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seq = (int64_t)blockIdx.x * kAttnWarps + warp;
+  if (seq >= rows) return;
+  const int ld = 2 * H * dk + H * dv;
+  tower::attn_warp_seq<N, T, U>(qkv + seq * N * ld, ld, rcb, rpb, relk, out + seq * N * (size_t)(H * dv), H, dk, dv, lane,
+                                s_w[warp]);
 }
 
 int launch_attention(const float* qkv, const float* rcb, const float* rpb, const float* relk,
                      __nv_bfloat16* out, int64_t rows, int n, int H, int dk, int dv, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div<int64_t>(rows * H, kAttnWarps);
+  {
+    const char* e = getenv("SVDD_ATTN_SEQ");
+    const bool pow2 = (dk & (dk - 1)) == 0;
+    if ((e ? atoi(e) : 1) && n <= 2 && pow2 && dk >= 4 && dk <= 128 && dv % 4 == 0 && H * dk == 512 &&
+        (H * dv == 1536 || H * dv == 384) && H * n * n <= 128) {
+      const unsigned gs = (unsigned)ceil_div<int64_t>(rows, kAttnWarps);
+      const dim3 blk(kAttnWarps * 32);
+      if (n == 1 && H * dv == 1536) launch_k(ef_attention_seq_kernel<1, 4, 12>, dim3(gs), blk, 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+      else if (n == 1) launch_k(ef_attention_seq_kernel<1, 4, 3>, dim3(gs), blk, 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+      else if (H * dv == 1536) launch_k(ef_attention_seq_kernel<2, 4, 12>, dim3(gs), blk, 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+      else launch_k(ef_attention_seq_kernel<2, 4, 3>, dim3(gs), blk, 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+      return SVDD_OK;
+    }
+  }
   if (dk <= 32 * kAttnDkPer && n == 1)
     launch_k(ef_attention_warp_kernel<1>, dim3(grid), dim3(kAttnWarps * 32), 0, st, 1, qkv, rcb, rpb, relk, out, rows, H, dk, dv);
   else if (dk <= 32 * kAttnDkPer && n == 2)
@@ -430,9 +375,12 @@ struct svdd_enformer {
   int relk_n = 0;
   float* relk = nullptr;       // [n_blocks][H][2n-1][dk]
   float* pos_dev = nullptr;
+  // persistent tower kernel (tower.cuh): per-block weight tensor maps + parameter pointers
+  tower::BlockParams* tower_blocks = nullptr;
   ~svdd_enformer() {
     if (relk) cudaFree(relk);
     if (pos_dev) cudaFree(pos_dev);
+    if (tower_blocks) cudaFree(tower_blocks);
   }
 };
 
@@ -635,6 +583,7 @@ struct EfWs {
   __nv_bfloat16* ao;
   __nv_bfloat16* u;
   float* partials;
+  unsigned* flags;       // persistent tower kernel: one counter per (phase, row tile)
 };
 bool pool2_enabled() {
   static int v = -1;
@@ -680,7 +629,160 @@ size_t ef_carve(const svdd_enformer* h, Workspace& W, int64_t rows, int L, EfWs*
   o->ao = W.take<__nv_bfloat16>(R * h->H * h->dv + 64);
   o->u = W.take<__nv_bfloat16>(R * 2 * C + 64);
   o->partials = W.take<float>(R * (2 * C / 64) + 64);
+  o->flags = W.take<unsigned>((size_t)tower::kPhasesPerBlock * kMaxBlocksT * ceil_div<size_t>(R, tower::kTileRows) + 64);
   return W.used();
+}
+}  // namespace
+
+namespace {
+// ---- persistent tower kernel: host side ---------------------------------------------------------
+int tower_enabled() {          // read per call: the tests A/B the two paths in one process
+  const char* e = getenv("SVDD_TOWER");
+  return e ? atoi(e) : 1;
+}
+bool tower_usable(const svdd_enformer* h, int n) {
+  const int C = h->C, nqkv = 2 * h->H * h->dk + h->H * h->dv;
+  return tower_enabled() && h->tower_blocks != nullptr && h->n_blocks > 0 && (n == 1 || n == 2 || n == 4) &&
+         C % 128 == 0 && C <= 128 * tower::kLnVecs && nqkv % 64 == 0 && (h->H * h->dv) % 64 == 0 &&
+         h->dk <= 32 * tower::kAttnDkPer && num_sms() >= 2;
+}
+int build_tower_params(svdd_enformer* h, int n) {
+  if (h->tower_blocks) { cudaFree(h->tower_blocks); h->tower_blocks = nullptr; }
+  const int C = h->C, H = h->H, dk = h->dk, dv = h->dv, P = 2 * n - 1;
+  const int nqkv = 2 * H * dk + H * dv;
+  if (h->n_blocks == 0 || C % 128 != 0 || (H * dv) % 64 != 0 || nqkv % 64 != 0) return SVDD_OK;
+  std::vector<tower::BlockParams> hp((size_t)h->n_blocks);
+  for (int j = 0; j < h->n_blocks; ++j) {
+    const auto& b = h->blk[j];
+    tower::BlockParams& bp = hp[(size_t)j];
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[0], b.wqkv, (uint64_t)C, (uint64_t)nqkv, 64, 128));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[1], b.wo, (uint64_t)(H * dv), (uint64_t)C, 64, 128));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[2], b.wf1, (uint64_t)C, (uint64_t)(2 * C), 64, 128));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[3], b.wf2, (uint64_t)(2 * C), (uint64_t)C, 64, 128));
+    bp.ln_g[0] = b.ln1_g; bp.ln_b[0] = b.ln1_b; bp.ln_g[1] = b.ln2_g; bp.ln_b[1] = b.ln2_b;
+    bp.bias[0] = nullptr; bp.bias[1] = b.bo; bp.bias[2] = b.bf1; bp.bias[3] = b.bf2;
+    bp.rcb = b.rcb; bp.rpb = b.rpb;
+    bp.relk = h->relk + (size_t)j * H * P * dk;
+  }
+  SVDD_CUDA(cudaMalloc(&h->tower_blocks, hp.size() * sizeof(tower::BlockParams)));
+  SVDD_CUDA(cudaMemcpy(h->tower_blocks, hp.data(), hp.size() * sizeof(tower::BlockParams), cudaMemcpyHostToDevice));
+  return SVDD_OK;
+}
+
+// All transformer blocks + the pointwise ConvBlock's BN+GELU operand in one launch:
+// in  b.xt (fp32 [R, C], the pooled conv-tower output), out b.xt (updated) and b.hn = GELU(BN(xt)).
+int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaStream_t st) {
+  using namespace tower;
+  const int C = h->C, H = h->H, dk = h->dk, dv = h->dv;
+  const int nqkv = 2 * H * dk + H * dv;
+  TowerArgs a;
+  a.R = (int)R; a.RT = (int)ceil_div<int64_t>(R, kTileRows); a.n_blocks = h->n_blocks; a.n_pos = n;
+  a.C = C; a.nqkv = nqkv; a.H = H; a.dk = dk; a.dv = dv;
+  auto gemm_phase = [&](int N, int K, int a_map, int out_kind, int w_idx) {
+    Phase p;
+    p.type = PH_GEMM; p.items_per_rt = ceil_div(N, kBN); p.n_cols = N; p.signals = 4; p.kblocks = K / 64;
+    p.a_map = a_map; p.out_kind = out_kind; p.w_idx = w_idx;
+    return p;
+  };
+  auto row_phase = [&](int type, int w_idx) {
+    Phase p;
+    p.type = type; p.items_per_rt = kSubItems; p.signals = 2; p.w_idx = w_idx;
+    return p;
+  };
+  a.ph[0] = row_phase(PH_LN, 0);
+  a.ph[1] = gemm_phase(nqkv, C, A_HN, OUT_F32_STORE, 0);
+  a.ph[2] = row_phase(PH_ATTN, 0);
+  a.ph[3] = gemm_phase(C, H * dv, A_AO, OUT_F32_REDUCE, 1);
+  a.ph[4] = row_phase(PH_LN, 1);
+  a.ph[5] = gemm_phase(2 * C, C, A_HN, OUT_BF16_RELU, 2);
+  a.ph[6] = gemm_phase(C, 2 * C, A_U, OUT_F32_REDUCE, 3);
+  a.ph[7] = row_phase(PH_BNACT, 0);
+  int start = 0;
+  for (int q = 0; q < kPhasesPerBlock; ++q) {
+    a.ph[q].start = start;
+    start += a.ph[q].items_per_rt * a.RT;
+  }
+  a.items_per_block = start;
+  a.total_items = start * a.n_blocks + kSubItems * a.RT;
+  a.blocks = h->tower_blocks;
+  a.xt = b.xt; a.hn = b.hn; a.qkv = b.qkv; a.ao = b.ao;
+  a.bn_s = h->bnpw_s; a.bn_t = h->bnpw_t;
+  a.flags = b.flags;
+  { const char* e = getenv("SVDD_TOWER_ATTN_FAST"); a.attn_fast = e ? atoi(e) : 1; }
+
+  CUtensorMap tm_hn, tm_ao, tm_u, tm_qkv, tm_xt;
+  SVDD_TRY(encode_tmap_2d_bf16(&tm_hn, b.hn, (uint64_t)C, (uint64_t)R, 64, 128));
+  SVDD_TRY(encode_tmap_2d_bf16(&tm_ao, b.ao, (uint64_t)(H * dv), (uint64_t)R, 64, 128));
+  SVDD_TRY(encode_tmap_2d_bf16(&tm_u, b.u, (uint64_t)(2 * C), (uint64_t)R, 64, 128));
+  SVDD_TRY(encode_tmap_2d_f32(&tm_qkv, b.qkv, (uint64_t)nqkv, (uint64_t)R, 32, 128));
+  SVDD_TRY(encode_tmap_2d_f32(&tm_xt, b.xt, (uint64_t)C, (uint64_t)R, 32, 128));
+
+  auto kern = n == 1 ? tower_kernel<1> : (n == 2 ? tower_kernel<2> : tower_kernel<4>);
+  static bool configured[3] = {false, false, false};
+  const int ki = n == 1 ? 0 : (n == 2 ? 1 : 2);
+  if (!configured[ki]) {
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured[ki] = true;
+  }
+  // every CTA pair must be resident (items wait on each other): at most one pair per TPC
+  static int max_pairs = -1;
+  if (max_pairs < 0) { const char* e = getenv("SVDD_TOWER_PAIRS"); max_pairs = e ? atoi(e) : 0; }
+  int pairs = num_sms() / 2;
+  if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;
+  const int widest = a.ph[5].items_per_rt > a.ph[1].items_per_rt ? a.ph[5].items_per_rt : a.ph[1].items_per_rt;
+  const int max_items_per_phase = (widest > kSubItems ? widest : kSubItems) * a.RT;
+  if (pairs > max_items_per_phase) pairs = max_items_per_phase;
+  SVDD_CUDA(cudaMemsetAsync(b.flags, 0, (size_t)kPhasesPerBlock * a.n_blocks * a.RT * sizeof(unsigned), st));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool prof = gemm_prof_on();
+  if (prof) {
+    SVDD_CUDA(cudaEventCreate(&e0));
+    SVDD_CUDA(cudaEventCreate(&e1));
+    SVDD_CUDA(cudaEventRecord(e0, st));
+  }
+  // SVDD_TOWER_TRACE=<file> (debugging): per-item timestamps of this launch, appended as CSV
+  const char* trace_path = getenv("SVDD_TOWER_TRACE");
+  unsigned long long* trace_dev = nullptr;
+  if (trace_path != nullptr && trace_path[0] != 0) {
+    SVDD_CUDA(cudaMalloc(&trace_dev, (size_t)a.total_items * 8 * sizeof(unsigned long long)));
+    SVDD_CUDA(cudaMemsetAsync(trace_dev, 0, (size_t)a.total_items * 8 * sizeof(unsigned long long), st));
+    a.trace = trace_dev;
+  }
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(kThreads), Cfg::kSmemBytes, st, 2,
+                     tm_hn, tm_ao, tm_u, tm_qkv, tm_xt, a));
+  count_launch();
+  if (trace_dev != nullptr) {
+    std::vector<unsigned long long> tr((size_t)a.total_items * 8);
+    SVDD_CUDA(cudaStreamSynchronize(st));
+    SVDD_CUDA(cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(trace_dev);
+    FILE* f = fopen(trace_path, "a");
+    if (f != nullptr) {
+      unsigned long long t0 = ~0ull;
+      for (int i = 0; i < a.total_items; ++i)
+        for (int k = 0; k < 6; ++k) if (tr[(size_t)i * 8 + k] != 0 && tr[(size_t)i * 8 + k] < t0) t0 = tr[(size_t)i * 8 + k];
+      fprintf(f, "# tower R=%d RT=%d pairs=%d items=%d items_per_block=%d\n", a.R, a.RT, pairs, a.total_items, a.items_per_block);
+      for (int i = 0; i < a.total_items; ++i) {
+        int j = i / a.items_per_block, rem = i % a.items_per_block, q = 0;
+        if (i >= a.n_blocks * a.items_per_block) { j = a.n_blocks; q = kPhasesPerBlock; rem = i - a.n_blocks * a.items_per_block; }
+        else { for (int k = 1; k < kPhasesPerBlock; ++k) q += rem >= a.ph[k].start ? 1 : 0; rem -= a.ph[q].start; }
+        const int ipr = a.ph[q].items_per_rt;
+        fprintf(f, "%d,%d,%d,%d,%d,%llu", i, j, q, rem / ipr, rem % ipr, tr[(size_t)i * 8 + 6]);
+        for (int k = 0; k < 6; ++k) fprintf(f, ",%lld", tr[(size_t)i * 8 + k] ? (long long)(tr[(size_t)i * 8 + k] - t0) : -1ll);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+  if (prof) {
+    SVDD_CUDA(cudaEventRecord(e1, st));
+    GemmShape g;
+    g.S = 1; g.L = (int)R; g.L_in = (int)R; g.K = C; g.N = nqkv + C + 4 * C; g.taps = 1;
+    const double fl = 2.0 * (double)R * h->n_blocks *
+                      ((double)nqkv * C + (double)C * (H * dv) + 2.0 * (double)(2 * C) * C);
+    gemm_prof_record(e0, e1, g, 2256, 100, fl);
+  }
+  return SVDD_OK;
 }
 }  // namespace
 
@@ -719,6 +821,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
                                                                                 H, dk, F, P);
     SVDD_LAUNCH_CHECK();
     h->relk_n = n;
+    SVDD_TRY(build_tower_params(h, n));
   }
 
   auto gemm_flat = [&](const void* A, const void* Wt, int64_t R, int K, int N, const EpiParams& ep,
@@ -913,7 +1016,9 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
     }
     // ---- transformer tower ------------------------------------------------------------------
     const int64_t R = rows * n;
-    for (int j = 0; j < h->n_blocks; ++j) {
+    const bool fused_tower = tower_usable(h, n);
+    if (fused_tower) SVDD_TRY(launch_tower(h, b, R, n, st));
+    for (int j = 0; j < h->n_blocks && !fused_tower; ++j) {
       auto& blk = h->blk[j];
       SVDD_TRY(launch_ln(b.xt, blk.ln1_g, blk.ln1_b, b.hn, R, C, st));
       {

@@ -163,6 +163,33 @@ def test_enformer_batch_independence(cuda):
   assert torch.isfinite(full).all()
 
 
+@pytest.mark.parametrize('full,n_cand', [(False, 3), (False, 70), (False, 300), (True, 128), (True, 1280)])
+def test_enformer_persistent_tower_matches_per_launch_path(cuda, full, n_cand, monkeypatch):
+  """The one-launch transformer tower (csrc/tower.cuh: flag-synchronised work items over row
+  tiles) against the launch-per-GEMM path it replaces: same GEMM k order, same LayerNorm and
+  attention arithmetic, so the scores agree to fp32 rounding of the final BN+GELU operand.
+  Row counts cover a single ragged row tile, several tiles, and the c2 size (2560 rows); the
+  small net (384 channels) has ragged column tiles, the full one (1536) is the bench network."""
+  emb, head = helpers.build_enformer(full=full)
+  emb, head = emb.to(cuda), head.to(cuda)
+  tok = helpers.random_tokens(n_cand, 200, 7 + n_cand, 0.5).to(cuda)
+  monkeypatch.setenv('SVDD_TOWER', '0')
+  ref = value_nets.score_tokens(emb, head, tok).cpu()
+  monkeypatch.setenv('SVDD_TOWER', '1')
+  before = _lib.launch_count()
+  got = value_nets.score_tokens(emb, head, tok).cpu()
+  launches = _lib.launch_count() - before
+  again = [value_nets.score_tokens(emb, head, tok).cpu() for _ in range(4)]
+  scale = float(ref.abs().max())
+  err = float((got - ref).abs().max())
+  print(f'\n[tower full={full} n_cand={n_cand}] launches={launches} max|d|={err:.3e} scale={scale:.3e}')
+  assert torch.isfinite(got).all()
+  for k, o in enumerate(again):
+    assert torch.equal(got, o), f'persistent tower is not deterministic (run {k + 1}: {int((o != got).sum())} scores differ, ' \
+                                f'max {float((o - got).abs().max()):.3e})'
+  assert err <= 2e-3 * max(scale, 1e-3)
+
+
 def test_value_rank_agreement(cuda):
   """What selection needs: the candidate the fp32 oracle prefers is (nearly always)
   the one the bf16 tensor-core net prefers.  Reported, with a weak bound."""
