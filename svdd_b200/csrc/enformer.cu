@@ -636,6 +636,11 @@ size_t ef_carve(const svdd_enformer* h, Workspace& W, int64_t rows, int L, EfWs*
 
 namespace {
 // ---- persistent tower kernel: host side ---------------------------------------------------------
+int tower_bn() {               // tile width of the tower's GEMM items (read once)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_TOWER_BN"); v = (e && atoi(e) == 128) ? 128 : 256; }
+  return v;
+}
 int tower_enabled() {          // read per call: the tests A/B the two paths in one process
   const char* e = getenv("SVDD_TOWER");
   return e ? atoi(e) : 1;
@@ -655,10 +660,10 @@ int build_tower_params(svdd_enformer* h, int n) {
   for (int j = 0; j < h->n_blocks; ++j) {
     const auto& b = h->blk[j];
     tower::BlockParams& bp = hp[(size_t)j];
-    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[0], b.wqkv, (uint64_t)C, (uint64_t)nqkv, 64, 128));
-    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[1], b.wo, (uint64_t)(H * dv), (uint64_t)C, 64, 128));
-    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[2], b.wf1, (uint64_t)C, (uint64_t)(2 * C), 64, 128));
-    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[3], b.wf2, (uint64_t)(2 * C), (uint64_t)C, 64, 128));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[0], b.wqkv, (uint64_t)C, (uint64_t)nqkv, 64, (uint32_t)(tower_bn() / 2)));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[1], b.wo, (uint64_t)(H * dv), (uint64_t)C, 64, (uint32_t)(tower_bn() / 2)));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[2], b.wf1, (uint64_t)C, (uint64_t)(2 * C), 64, (uint32_t)(tower_bn() / 2)));
+    SVDD_TRY(encode_tmap_2d_bf16(&bp.w[3], b.wf2, (uint64_t)(2 * C), (uint64_t)C, 64, (uint32_t)(tower_bn() / 2)));
     bp.ln_g[0] = b.ln1_g; bp.ln_b[0] = b.ln1_b; bp.ln_g[1] = b.ln2_g; bp.ln_b[1] = b.ln2_b;
     bp.bias[0] = nullptr; bp.bias[1] = b.bo; bp.bias[2] = b.bf1; bp.bias[3] = b.bf2;
     bp.rcb = b.rcb; bp.rpb = b.rpb;
@@ -675,12 +680,13 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   using namespace tower;
   const int C = h->C, H = h->H, dk = h->dk, dv = h->dv;
   const int nqkv = 2 * H * dk + H * dv;
+  const int bn = tower_bn();
   TowerArgs a;
   a.R = (int)R; a.RT = (int)ceil_div<int64_t>(R, kTileRows); a.n_blocks = h->n_blocks; a.n_pos = n;
   a.C = C; a.nqkv = nqkv; a.H = H; a.dk = dk; a.dv = dv;
   auto gemm_phase = [&](int N, int K, int a_map, int out_kind, int w_idx) {
     Phase p;
-    p.type = PH_GEMM; p.items_per_rt = ceil_div(N, kBN); p.n_cols = N; p.signals = 4; p.kblocks = K / 64;
+    p.type = PH_GEMM; p.items_per_rt = ceil_div(N, bn); p.n_cols = N; p.signals = 4; p.kblocks = K / 64;
     p.a_map = a_map; p.out_kind = out_kind; p.w_idx = w_idx;
     return p;
   };
@@ -717,11 +723,13 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   SVDD_TRY(encode_tmap_2d_f32(&tm_qkv, b.qkv, (uint64_t)nqkv, (uint64_t)R, 32, 128));
   SVDD_TRY(encode_tmap_2d_f32(&tm_xt, b.xt, (uint64_t)C, (uint64_t)R, 32, 128));
 
-  auto kern = n == 1 ? tower_kernel<1> : (n == 2 ? tower_kernel<2> : tower_kernel<4>);
+  auto kern = bn == 256 ? (n == 1 ? tower_kernel<1, 256> : (n == 2 ? tower_kernel<2, 256> : tower_kernel<4, 256>))
+                        : (n == 1 ? tower_kernel<1, 128> : (n == 2 ? tower_kernel<2, 128> : tower_kernel<4, 128>));
+  const int smem_bytes = bn == 256 ? Cfg<256>::kSmemBytes : Cfg<128>::kSmemBytes;
   static bool configured[3] = {false, false, false};
   const int ki = n == 1 ? 0 : (n == 2 ? 1 : 2);
   if (!configured[ki]) {
-    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured[ki] = true;
   }
   // every CTA pair must be resident (items wait on each other): at most one pair per TPC
@@ -748,7 +756,7 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
     SVDD_CUDA(cudaMemsetAsync(trace_dev, 0, (size_t)a.total_items * 8 * sizeof(unsigned long long), st));
     a.trace = trace_dev;
   }
-  SVDD_CUDA(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(kThreads), Cfg::kSmemBytes, st, 2,
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(kThreads), smem_bytes, st, 2,
                      tm_hn, tm_ao, tm_u, tm_qkv, tm_xt, a));
   count_launch();
   if (trace_dev != nullptr) {

@@ -38,7 +38,6 @@ using gemm2::kSlabBytes;
 using gemm2::kStagingBytes;
 using gemm2::kThreads;
 
-constexpr int kBN = 256;                  // tile columns per CTA pair
 constexpr int kTileRows = 2 * kBM;        // rows per CTA pair
 constexpr int kSubRows = 16;              // rows per CTA of one LN / attention / BN item
 constexpr int kSubItems = kBM / kSubRows; // such items per row tile
@@ -93,16 +92,18 @@ struct TowerArgs {
   unsigned long long* trace = nullptr;
 };
 
+template <int kBN>                         // tile columns per CTA pair: 256 or 128
 struct Cfg {
+  static_assert(kBN == 256 || kBN == 128, "tower tiles are 256 or 128 columns wide");
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB: this CTA's 128 rows
-  static constexpr int kBBytes = (kBN / 2) * kBK * 2;      // 16 KB: this CTA's half of the weight tile
+  static constexpr int kBBytes = (kBN / 2) * kBK * 2;      // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = kBN == 256 ? 4 : 5;
   static constexpr int kBiasBytes = 2 * kBN * 4;
   static constexpr int kAttnWBytes = kEpiWarps * 128 * 4;    // softmax weights of one sequence per warp (H*N*N <= 128)
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + kAttnWBytes + kBarBytes + 1024;
-  static constexpr int kTmemCols = 512;
+  static constexpr int kTmemCols = 2 * kBN;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -409,12 +410,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <int NPOS>
+template <int NPOS, int kBN>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ CUtensorMap tm_ao,
              const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_qkv,
              const __grid_constant__ CUtensorMap tm_xt, const TowerArgs a) {
+  using Cfg = tower::Cfg<kBN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kChunks = kBN / 64;                 // 32-column accumulator chunks per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -611,7 +614,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         ptx::tmem_ld_32x32(taddr, raw[0]);
         uint8_t* buf0 = nullptr;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kChunks; ++c) {
           const int cis = c % slab_chunks;
           if (cis == 0) {
             buf0 = my_bufs + (job & 1) * kSlabBytes;
@@ -619,10 +622,10 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           }
           float v[32], pv[32];
           ptx::tmem_ld_wait();
-          if (c + 1 < 4) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
+          if (c + 1 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
-          if (c + 1 == 4) {              // accumulator fully read: hand it back to the MMA warp
+          if (c + 1 == kChunks) {        // accumulator fully read: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) gemm2::mbar_arrive_leader<2>(&tempty_bar[acc_stage]);
@@ -718,7 +721,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           }
         }
         if (it.q < kPhasesPerBlock) {
-          __threadfence();
+          // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
           gemm_detail::epi_bar_sync();
           if (etid == 0) {
             stamp(id, 4);
@@ -760,7 +763,6 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         // the tile's stores are complete (not just read): publish
         gemm2::bulk_wait_all();
         fence_proxy_async_all();
-        __threadfence();
         red_release_gpu_add(own_flag(it), 1u);
         if (half == 0) stamp(id, 5);
       }
