@@ -71,25 +71,31 @@ __device__ __forceinline__ int gumbel_argmax5(const float* q, const float* u) {
 //   (cross-multiplied form of key[w] > key[v]; the last factor covers the roundings of the
 //   two products and of the exact path's division).  Exact ties and near-ties fail the test
 //   and take the exact path, so first-index tie-breaking is the reference's.
+//   The bound is applied in the looser one-FMA form  e <= 1e-6 * (g~ + 1):
+//   lo = g~ * (1 - 1e-6) - 1e-6,  hi = g~ * (1 + 1e-6) + 1e-6  (the extra 2e-7 * (g~ + 1) covers the
+//   rounding of the FMA and of its constants).  A non-positive lo[v] fails the product test by
+//   itself (q >= 0), so only the winner's lo is tested explicitly.  u + 1e-10 >= 1e-10 is a normal
+//   number: MUFU.LG2 is used directly, without __logf's denormal pre-scaling (same value).
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ int gumbel_argmax5_checked(const float* q, const float* u) {
-  float lo[kVocab], hi[kVocab], g[kVocab];
-  bool ok = true;
+  float lo[kVocab], g[kVocab];
 #pragma unroll
   for (int v = 0; v < kVocab; ++v) {
-    g[v] = 1e-10f - __logf(__fadd_rn(u[v], 1e-10f));
-    const float e = 8e-7f * fmaxf(g[v], 1.0f);
-    lo[v] = g[v] - e;
-    hi[v] = g[v] + e;
-    ok = ok && (lo[v] > 0.0f);
+    g[v] = fmaf(lg2_approx(__fadd_rn(u[v], 1e-10f)), -0.693147182f, 1e-10f);   // = 1e-10 - __logf(u + 1e-10)
+    lo[v] = fmaf(g[v], 0.999999f, -1e-6f);
   }
   int best = 0;
-  float bq = q[0], bg = g[0], bhi = hi[0];
+  float bq = q[0], bg = g[0], blo = lo[0];
 #pragma unroll
   for (int v = 1; v < kVocab; ++v) {
-    if (q[v] * bg > bq * g[v]) { best = v; bq = q[v]; bg = g[v]; bhi = hi[v]; }
+    if (q[v] * bg > bq * g[v]) { best = v; bq = q[v]; bg = g[v]; blo = lo[v]; }
   }
-  const float rhs_scale = bhi * 1.0000020f;
-  ok = ok && (bq > 1e-20f);        // keeps both products far from the subnormal range
+  const float rhs_scale = fmaf(bg, 1.000001f, 1e-6f) * 1.0000020f;
+  bool ok = (blo > 0.0f) && (bq > 1e-20f);   // the latter keeps both products far from the subnormal range
 #pragma unroll
   for (int v = 0; v < kVocab; ++v) ok = ok && (v == best || bq * lo[v] > q[v] * rhs_scale);
   return ok ? best : gumbel_argmax5(q, u);
