@@ -18,7 +18,8 @@ Enformer-style value net, synthetic (all-mask prior + counter-based noise).
   e2e       the same metric through the public API with HOST buffers: the start state
             is copied from pinned host memory and the decoded tokens are read back to
             host every step; wall clock with synchronisation on both sides.
-  roofline  the tensor-core GEMM kernel (conv_gemm_kernel, >95% of the step): summed
+  roofline  the tensor-core kernel family (gemm2_kernel launches, the persistent
+            transformer-tower kernel, the fused denoiser; >95% of the step): summed
             nominal dense FLOPs / summed CUDA-event launch time of one instrumented
             value-net + denoiser pass, against the MEASURED sustained bf16 peak.
   cpu_baseline  the CPU oracle (a port of the reference's algorithm, oracle/) timed on
@@ -298,8 +299,8 @@ def main():
     except Exception:
       traffic = {}
     top_ach = top['flops'] / (top['ms'] * 1e-3) / 1e12 if top['ms'] > 0 else None
-    roofline = {'bound': 'tensor', 'kernel': 'tcgen05 GEMM family (gemm2_kernel implicit-GEMM launches of the value net on '
-                'B*M candidates + the fused denoiser kernel on B): every tensor-core launch of one reverse step',
+    roofline = {'bound': 'tensor', 'kernel': 'tcgen05 GEMM family (gemm2_kernel implicit-GEMM launches + the persistent transformer-tower '
+                'kernel of the value net on B*M candidates + the fused denoiser kernel on B): every tensor-core launch of one reverse step',
                 'achieved': achieved, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['tf_sust'],
                 'traffic': traffic.get('gemm_family_dram_bytes_per_step'),
@@ -347,6 +348,19 @@ def main():
             'algorithmic_bytes': nb, 'ms': t,
             'size': f'B={Bc} L={L} M={Mc} int64 tokens, injected noise, L2 evicted by a 256 MB read, one launch'}
       del U, lg, xs, sc, cand64
+    # stage 4 alone at a size where the launch is no longer latency-dominated (config 4 moves only
+    # 13 MB per launch): what the kernel itself sustains
+    for tag, Bc, Mc in (('large_B65536', 65536, 20),):
+      sc = torch.randn(Mc, Bc, device=device)
+      cand64 = torch.randint(0, 4, (Mc, Bc, L), device=device, dtype=torch.int64)
+      t4 = timed(lambda: _lib.select_gather(sc, cand64))
+      nb = Bc * (4 * Mc + 16 * L)
+      ach = nb / (t4 * 1e-3) / 1e9
+      stage_rooflines[f'stage4_select_gather@{tag}'] = {
+          'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+          'algorithmic_bytes': nb, 'ms': t4,
+          'size': f'B={Bc} L={L} M={Mc} int64 tokens, L2 evicted by a 256 MB read, one launch'}
+      del sc, cand64
     del flush
 
   # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------

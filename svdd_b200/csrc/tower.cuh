@@ -131,6 +131,36 @@ __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned target) {
   }
 }
 
+// mbarrier wait of the tower's roles: most of a role's life here is waiting (the kernel is bound
+// by the dependency chain, not by issue slots), so the poll carries a suspend-time hint: the warp
+// sleeps in hardware until the phase completes or the hint expires instead of spinning
+// (171 M warp instructions per launch, mostly polls, before this).
+#ifndef SVDD_TOWER_WAIT_HINT_NS
+#define SVDD_TOWER_WAIT_HINT_NS 1000
+#endif
+__device__ __forceinline__ void twait(uint64_t* bar, uint32_t parity) {
+#if SVDD_TOWER_WAIT_HINT_NS > 0
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(ptx::smem_u32(bar)), "r"(parity), "r"((uint32_t)SVDD_TOWER_WAIT_HINT_NS)
+        : "memory");
+    if (ok) return;
+    if (++spins == (1u << 22)) {
+      printf("svdd_b200: tower mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+#else
+  ptx::mbar_wait(bar, parity);
+#endif
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -524,7 +554,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         // weights of the first ring stages: no dependency, request them before the wait
         uint32_t s2 = stage, p2 = phase;
         for (int kb = 0; kb < pre; ++kb) {
-          ptx::mbar_wait(&empty_bar[s2], p2 ^ 1);
+          twait(&empty_bar[s2], p2 ^ 1);
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s2], tx_bytes);
           gemm2::tma_load_2d_cg<2>(stage_base + s2 * Cfg::kStageBytes + Cfg::kABytes, mW, &full_bar[s2], kb * kBK, wrow0);
           if (++s2 == kStages) { s2 = 0; p2 ^= 1; }
@@ -541,7 +571,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         for (int kb = pre; kb < ph.kblocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          twait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           gemm2::tma_load_2d_cg<2>(sa, mA, &full_bar[stage], kb * kBK, row0);
@@ -559,12 +589,12 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         const Item it = decode(id);
         const Phase& ph = a.ph[it.q];
         if (ph.type != PH_GEMM) continue;
-        ptx::mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+        twait(&tempty_bar[acc_stage], acc_phase ^ 1);
         ptx::tc_fence_after();
         if (lane == 0) stamp(id, 2);
         const uint32_t tmem_d = tmem_base + acc_stage * kBN;
         for (int kb = 0; kb < ph.kblocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          twait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
@@ -608,7 +638,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         gemm_detail::epi_bar_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * kBN + half * (kBN / 2);
         uint32_t raw[2][32];
-        ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        twait(&tfull_bar[acc_stage], acc_phase);
         ptx::tc_fence_after();
         if (etid == 0) stamp(id, 3);
         ptx::tmem_ld_32x32(taddr, raw[0]);
@@ -618,7 +648,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           const int cis = c % slab_chunks;
           if (cis == 0) {
             buf0 = my_bufs + (job & 1) * kSlabBytes;
-            ptx::mbar_wait(&my_rin[job & 1], (job >> 1) & 1);
+            twait(&my_rin[job & 1], (job >> 1) & 1);
           }
           float v[32], pv[32];
           ptx::tmem_ld_wait();
@@ -751,7 +781,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         const CUtensorMap* mO = ph.out_kind == OUT_F32_STORE ? &tm_qkv : (ph.out_kind == OUT_F32_REDUCE ? &tm_xt : &tm_u);
         const int row0 = it.r * kTileRows + rank * kBM;
         for (int s = 0; s < slabs; ++s, ++j) {
-          ptx::mbar_wait(&my_rout[j & 1], (j >> 1) & 1);
+          twait(&my_rout[j & 1], (j >> 1) & 1);
           const uint8_t* buf = bufs + (j & 1) * kSlabBytes;
           const int col = it.c * kBN + half * (kBN / 2) + s * slab_cols;
           if (ph.out_kind == OUT_F32_REDUCE) tma_reduce_add_2d(mO, buf, col, row0);
