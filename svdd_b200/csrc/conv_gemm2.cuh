@@ -580,7 +580,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           slab_read(buf1, x7, false, cis, yd);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float w1 = gemm_detail::fast_rcp(1.0f + gemm_detail::fast_ex2(-1.4426950408889634f * v[i]));
+            // sigmoid(v) = 0.5 + 0.5 tanh(v / 2): one MUFU op per element instead of ex2 + rcp (the
+            // pool epilogue is MUFU-bound: sigmoid + the next layer's GELU on 128 columns per thread)
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v[i]));
+            const float w1 = fmaf(0.5f, th, 0.5f);
             v[i] = fmaf(w1, yd[i], pv[i]);
           }
           if (ep.out != nullptr) {         // last stage: fp32 transformer stream, direct
