@@ -787,11 +787,16 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           if (ph.out_kind == OUT_F32_REDUCE) tma_reduce_add_2d(mO, buf, col, row0);
           else tma_store_2d(mO, buf, col, row0);
           gemm2::bulk_commit();
-          gemm2::bulk_wait_read0();
-          ptx::mbar_arrive(&my_rin[j & 1]);
+          // two stores in flight: the PREVIOUS job's slab is free once at most one group is still
+          // reading (waiting for this job's own read here would serialise store and math)
+          if (s > 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            ptx::mbar_arrive(&my_rin[(j - 1) & 1]);
+          }
         }
-        // the tile's stores are complete (not just read): publish
+        // the tile's stores are complete (not just read): free the last slab, publish
         gemm2::bulk_wait_all();
+        ptx::mbar_arrive(&my_rin[(j - 1) & 1]);
         fence_proxy_async_all();
         red_release_gpu_add(own_flag(it), 1u);
         if (half == 0) stamp(id, 5);
