@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
   cfg, model, emb, head = build_models(torch.device('cpu'))
   vals, desc, cores, t_steps = [], '', 0, []
   for i in range(args.warmup + args.steps):
-    v, desc, cores, t_step = cpu_port_sample(model, emb, head, n_seq=2, n_steps=1)
+    v, desc, cores, t_step = cpu_port_sample(model, emb, head, n_seq=8, n_steps=4)
     if i >= args.warmup:
       vals.append(v)
       t_steps.append(t_step)
@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
   print(json.dumps({
       'impl': 'reference', 'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s',
       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-      'ms_per_step': 1000.0 * 2 / value, 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': 1000.0 * 8 / value, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': WORKLOAD, 'B_per_gpu': B_PER_GPU, 'M': M, 'L': L,
                  'denoise_steps': NUM_STEPS},
@@ -366,7 +366,7 @@ def main():
   # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    v, desc, cores, _ = cpu_port_sample(model, emb, head, n_seq=4, n_steps=3)
+    v, desc, cores, _ = cpu_port_sample(model, emb, head, n_seq=16, n_steps=8)
     cpu = {'value': v, 'unit': 'seq/s', 'cores': cores, 'kind': 'port', 'sample': desc}
 
   if rank == 0:
