@@ -141,12 +141,12 @@ int gemm2_cg() {
   return v;
 }
 
-template <int BN, int MODE, int CG, bool HALO = false>
+template <int BN, int MODE, int CG, bool HALO = false, int EW = 8>
 int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                  const CUtensorMap& tmR, const CUtensorMap& tmR2, const GemmShape& g, const EpiParams& ep,
                  cudaStream_t stream) {
   using C = gemm2::Cfg2<BN, CG>;
-  auto kern = gemm2::gemm2_kernel<BN, MODE, CG, HALO>;
+  auto kern = gemm2::gemm2_kernel<BN, MODE, CG, HALO, EW>;
   constexpr int kSmem = HALO ? C::kSmemBytesH : C::kSmemBytes;
   static bool configured = false;
   if (!configured) {
@@ -180,7 +180,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     SVDD_CUDA(cudaEventCreate(&e1));
     SVDD_CUDA(cudaEventRecord(e0, stream));
   }
-  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(gemm2::kThreads), kSmem, stream, CG,
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(64 + 32 * EW + 32 * gemm2::kStoreWarps), kSmem, stream, CG,
                      tmA, tmW, tmO, tmO2, tmR, tmR2, gk, epk));
   if (timeline) {
     unsigned long long h[16];
@@ -201,7 +201,7 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorM
     const double rows_fl = g.useful_rows > 0 ? (double)g.useful_rows : (double)g.S * g.L;
     const double fl = 2.0 * rows_fl * (double)g.N * ((double)g.K * g.taps + g.K2);
     P.flops += fl;
-    P.recs.push_back({g, BN + 1000 * CG, MODE, fl});
+    P.recs.push_back({g, BN + 1000 * CG + (EW == 16 ? 10000 : 0), MODE, fl});
   }
   return SVDD_OK;
 }
@@ -432,6 +432,23 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       SVDD_TRY(io_map(&tO2, ep2.res == nullptr ? ep2.out2 : nullptr, ep2.out2_dtype, ep2.ld_out2, g.L, g.BL));
       SVDD_TRY(io_map(&tR, ep2.res, ep2.res_dtype, ep2.ld_res, g.L, g.BL));
       tR2 = tA;
+    }
+    {
+      // 16 epilogue warps for the launches whose epilogue is the bottleneck and fits one staged bf16
+      // slab per column quarter: EPI_PAIR (in place) and single-output EPI_GENERIC without residual
+      static int epi16 = -1;
+      if (epi16 < 0) { const char* e = getenv("SVDD_EPI16"); epi16 = e ? atoi(e) : 1; }
+      const bool one_out = (ep2.out != nullptr) != (ep2.out2 != nullptr);
+      const int staged_dt = ep2.out != nullptr ? ep2.out_dtype : ep2.out2_dtype;
+      const bool gen16 = mode == EPI_GENERIC && ep2.res == nullptr && !ep2.res_reduce && one_out && staged_dt == DT_BF16 &&
+                         !ep2.act_after_res;
+      // measured on c2: the stem (K = 64, pure epilogue) 304 -> 152 us; EPI_PAIR no gain (279 -> 302 us at
+      // stage 0: with the MMA pipe busy the epilogue competes for shared-memory bandwidth, not for
+      // latency hiding), so EPI_PAIR takes this variant only with SVDD_EPI16=2
+      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && ((mode == EPI_PAIR && epi16 >= 2) || gen16)) {
+        if (mode == EPI_PAIR) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+        return launch2_impl<256, EPI_GENERIC, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      }
     }
     if (g.halo) {
       if (bn2 == 256) return launch2_impl<256, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);

@@ -253,8 +253,65 @@ __device__ __forceinline__ void slab_read(const uint8_t* row_base, int x7, bool 
 
 struct TileCoord { int n0, s0, l0; bool in_range; };
 
-template <int BN, int MODE, int CG, bool HALO = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// 16-column TMEM chunk (the EW = 16 epilogue keeps the kernel inside 102 registers)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 bf16 columns (chunk c of 4) of one row <-> its place in a 128B-swizzled slab row
+__device__ __forceinline__ void slab_write16(uint8_t* row_base, int x7, int c, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = c * 2 + u;
+    *reinterpret_cast<uint4*>(row_base + ((j ^ x7) << 4)) =
+        make_uint4(gemm_detail::pack_bf16x2(v[8 * u], v[8 * u + 1]), gemm_detail::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                   gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+  }
+}
+__device__ __forceinline__ void slab_read16(const uint8_t* row_base, int x7, int c, float* v) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = c * 2 + u;
+    const uint4 q = *reinterpret_cast<const uint4*>(row_base + ((j ^ x7) << 4));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      v[8 * u + 2 * k] = __low2float(hh);
+      v[8 * u + 2 * k + 1] = __high2float(hh);
+    }
+  }
+}
+__device__ __forceinline__ void load_param16(const float* p, float* v) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = q[i];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void act16(float* v, int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_tanh(v[i]);
+  }
+}
+
+// EW = epilogue warps: 8 (thread = row x column half, 32-column chunks, two slab buffers per half)
+// or 16 (thread = row x column quarter, 16-column chunks, ONE slab buffer per quarter; bf16 output
+// only, one staged output or EPI_PAIR in place).  The epilogue-bound launches (stem, residual 1x1)
+// are limited by two epilogue warps per scheduler not hiding their own latencies (30 % issue-active);
+// EW = 16 doubles the warps per scheduler inside the same 64 KB of staging.
+template <int BN, int MODE, int CG, bool HALO = false, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW + 32 * kStoreWarps, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes2,
@@ -329,7 +386,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull_bar[i], 1);
-        ptx::mbar_init(&tempty_bar[i], CG * kEpiWarps);
+        ptx::mbar_init(&tempty_bar[i], CG * EW);
       }
       for (int i = 0; i < 4; ++i) {
         ptx::mbar_init(&rin_bar[i], 1);
@@ -510,7 +567,103 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (EW == 16 && warp < 2 + EW) {
+    // ===================== epilogue math, 16 warps: thread = (row, column quarter) =====================
+    if constexpr (EW == 16) {
+      static_assert(EW != 16 || (BN == 256 && !HALO && (MODE == EPI_GENERIC || MODE == EPI_PAIR)), "EW = 16 variants");
+      const int ew = warp - 2;
+      const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+      const int grp = ew >> 2;             // column quarter
+      const int etid = threadIdx.x - 64;
+      const int r = quad * 32 + lane;
+      const int x7 = r & 7;
+      uint8_t* buf = staging + grp * kSlabBytes + r * 128;
+      uint32_t acc_stage = 0, acc_phase = 0, job = 0;
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord tc = tile_coords(t, rank);
+        const int n0 = tc.n0;
+        const int s = tc.s0 + r / g.BL, l = tc.l0 + r % g.BL;
+        const bool valid = (r < g.BL * g.BS) && (s < g.S) && (l < g.L);
+        float* P = s_param + acc_stage * (kParamVecs * BN);
+        for (int i = etid; i < BN; i += 32 * EW) {
+          const bool in_n = n0 + i < n_end;
+          if (ep.bias) P[P_BIAS * BN + i] = in_n ? ep.bias[n0 + i] : 0.0f;
+          if (ep.scale) { P[P_SCALE * BN + i] = in_n ? ep.scale[n0 + i] : 0.0f; P[P_SHIFT * BN + i] = in_n ? ep.shift[n0 + i] : 0.0f; }
+          if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? ep.shift2[n0 + i] : 0.0f; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + grp * 64;
+        uint32_t raw[2][16];
+        ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        ptx::tc_fence_after();
+        tmem_ld_32x16(taddr, raw[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = grp * 64 + c * 16;  // column within the tile
+          if (c == 0) ptx::mbar_wait(&rin_bar[grp], job & 1);
+          float v[16], pv[16];
+          ptx::tmem_ld_wait();
+          if (c + 1 < 4) tmem_ld_32x16(taddr + (c + 1) * 16, raw[(c + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
+          if (c == 3) {                    // accumulator fully read: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
+          }
+          if (ep.scale != nullptr) {
+            float ps[16];
+            load_param16(P + P_SCALE * BN + c0, ps);
+            load_param16(P + P_SHIFT * BN + c0, pv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+          }
+          if (ep.bias != nullptr) {
+            load_param16(P + P_BIAS * BN + c0, pv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += pv[i];
+          }
+          if constexpr (MODE == EPI_PAIR) {
+            if (ep.res != nullptr) {
+              slab_read16(buf, x7, c, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pv[i];
+            }
+            const bool odd = (r & 1) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float other = __shfl_xor_sync(0xffffffffu, v[i], 1);
+              v[i] = odd ? (valid ? v[i] - other : 0.0f) : v[i];
+            }
+            const int pr = r >> 1;
+            // in place: the pair rows land on other threads' residual rows of the same columns
+            if (ep.res != nullptr) asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+            slab_write16(buf + (odd ? 0 : (kBM / 2) * 128) + pr * 128 - r * 128, pr & 7, c, v);
+          } else {
+            act16(v, ep.act);
+            if (ep.out2 != nullptr) {
+              if (ep.scale2 != nullptr) {
+                float ps[16];
+                load_param16(P + P_SCALE2 * BN + c0, ps);
+                load_param16(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+              }
+              act16(v, ep.act2);
+            }
+            slab_write16(buf, x7, c, v);
+          }
+          if (c == 3) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&rout_bar[grp]);
+            ++job;
+          }
+        }
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (EW == 8 && warp < 2 + kEpiWarps) {
     // ===================== epilogue math: thread = (row, column half) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
@@ -678,7 +831,48 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== slab store / prefetch warp (one per column half) =====================
-    const int half = warp - (2 + kEpiWarps);
+    const int half = warp - (2 + EW);
+    if constexpr (EW == 16) {
+      // one buffer per column quarter, quarters 2*half and 2*half+1 served in turn
+      if (lane == 0) {
+        const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
+        const bool load_res = kPair && ep.res != nullptr;
+        auto provision = [&](int t, int grp) {
+          if (t >= total_tiles) return;
+          if (load_res) {
+            const TileCoord c = tile_coords(t, rank);
+            ptx::mbar_arrive_expect_tx(&rin_bar[grp], res_bytes);
+            ptx::tma_load_3d(staging + grp * kSlabBytes, &tmRes, &rin_bar[grp], c.n0 + grp * 64, c.l0, c.s0);
+          } else {
+            ptx::mbar_arrive(&rin_bar[grp]);
+          }
+        };
+        provision(first_tile, 2 * half);
+        provision(first_tile, 2 * half + 1);
+        uint32_t j = 0;
+        for (int t = first_tile; t < total_tiles; t += tile_step, ++j) {
+          const TileCoord c = tile_coords(t, rank);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int grp = 2 * half + q;
+            ptx::mbar_wait(&rout_bar[grp], j & 1);
+            const uint8_t* buf = staging + grp * kSlabBytes;
+            const int col = c.n0 + grp * 64;
+            if (kPair) {                  // rows 0..63: yd, rows 64..127: y0, both at half length
+              tma_store_3d(&tmOut2, buf, col, c.l0 >> 1, c.s0);
+              tma_store_3d(&tmOut, buf + (kBM / 2) * 128, col, c.l0 >> 1, c.s0);
+            } else {
+              tma_store_3d(has_out ? &tmOut : &tmOut2, buf, col, c.l0, c.s0);
+            }
+            bulk_commit();
+          }
+          bulk_wait_read0();
+          provision(t + tile_step, 2 * half);
+          provision(t + tile_step, 2 * half + 1);
+        }
+        bulk_wait_all();
+      }
+    } else
     if (lane == 0 && n_out > 0) {
       uint8_t* bufs = staging + half * 2 * kSlabBytes;
       uint64_t* my_rin = rin_bar + half * 2;
