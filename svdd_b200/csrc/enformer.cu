@@ -641,6 +641,15 @@ int tower_bn() {               // tile width of the tower's GEMM items (read onc
   if (v < 0) { const char* e = getenv("SVDD_TOWER_BN"); v = (e && atoi(e) == 128) ? 128 : 256; }
   return v;
 }
+// epilogue warps of the tower kernel (read once).  16 (thread = row x column quarter, one row per warp
+// in the LayerNorm items, two warps per sequence in the attention items) is measured SLOWER, 1.17 vs
+// 1.07 ms: at the 102-register cap of a 640-thread CTA the row code and the GEMM epilogue spill
+// (attention 9.4 -> 8.3 us, but LayerNorm 6.1 -> 7.3 and every GEMM phase +1.5 us).  Kept with its test.
+int tower_ew() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVDD_TOWER_EW"); v = (e && atoi(e) == 16) ? 16 : 8; if (tower_bn() != 256) v = 8; }
+  return v;
+}
 int tower_enabled() {          // read per call: the tests A/B the two paths in one process
   const char* e = getenv("SVDD_TOWER");
   return e ? atoi(e) : 1;
@@ -723,7 +732,9 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   SVDD_TRY(encode_tmap_2d_f32(&tm_qkv, b.qkv, (uint64_t)nqkv, (uint64_t)R, 32, 128));
   SVDD_TRY(encode_tmap_2d_f32(&tm_xt, b.xt, (uint64_t)C, (uint64_t)R, 32, 128));
 
-  auto kern = bn == 256 ? (n == 1 ? tower_kernel<1, 256> : (n == 2 ? tower_kernel<2, 256> : tower_kernel<4, 256>))
+  const int ew = tower_ew();
+  auto kern = ew == 16 ? (n == 1 ? tower_kernel<1, 256, 16> : (n == 2 ? tower_kernel<2, 256, 16> : tower_kernel<4, 256, 16>))
+            : bn == 256 ? (n == 1 ? tower_kernel<1, 256> : (n == 2 ? tower_kernel<2, 256> : tower_kernel<4, 256>))
                         : (n == 1 ? tower_kernel<1, 128> : (n == 2 ? tower_kernel<2, 128> : tower_kernel<4, 128>));
   const int smem_bytes = bn == 256 ? Cfg<256>::kSmemBytes : Cfg<128>::kSmemBytes;
   static bool configured[3] = {false, false, false};
@@ -756,7 +767,7 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
     SVDD_CUDA(cudaMemsetAsync(trace_dev, 0, (size_t)a.total_items * 8 * sizeof(unsigned long long), st));
     a.trace = trace_dev;
   }
-  SVDD_CUDA(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(kThreads), smem_bytes, st, 2,
+  SVDD_CUDA(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(64 + 32 * ew + 64), smem_bytes, st, 2,
                      tm_hn, tm_ao, tm_u, tm_qkv, tm_xt, a));
   count_launch();
   if (trace_dev != nullptr) {

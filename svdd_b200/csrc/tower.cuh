@@ -100,7 +100,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kBN == 256 ? 4 : 5;
   static constexpr int kBiasBytes = 2 * kBN * 4;
-  static constexpr int kAttnWBytes = kEpiWarps * 128 * 4;    // softmax weights of one sequence per warp (H*N*N <= 128)
+  static constexpr int kAttnWBytes = 16 * 128 * 4;           // softmax weights of one sequence per epilogue warp (H*N*N <= 128)
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + kAttnWBytes + kBarBytes + 1024;
   static constexpr int kTmemCols = 2 * kBN;
@@ -215,6 +215,55 @@ __device__ __forceinline__ void ln_warp_row(const float* __restrict__ x_row, con
       const float y0 = (v[i].x - mean) * rstd * gg.x + bb.x, y1 = (v[i].y - mean) * rstd * gg.y + bb.y;
       const float y2 = (v[i].z - mean) * rstd * gg.z + bb.z, y3 = (v[i].w - mean) * rstd * gg.w + bb.w;
       o2[i * 32 + lane] = make_uint2(gemm_detail::pack_bf16x2(y0, y1), gemm_detail::pack_bf16x2(y2, y3));
+    }
+  }
+}
+
+// The same with C = 128 * NVEC known at compile time (exactly NVEC float4s of registers): the
+// 16-warp tower kernel runs at <= 102 registers.
+template <int NVEC, int ROWS = 1>
+__device__ __forceinline__ void ln_warp_row_n(const float* __restrict__ x_row, const float* __restrict__ g,
+                                              const float* __restrict__ b, __nv_bfloat16* __restrict__ out_row,
+                                              int lane) {
+  // ROWS consecutive rows with all their loads in flight together (one L2 round trip)
+  constexpr int C = NVEC * 128;
+  float4 v[ROWS][NVEC];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const float4* xr = reinterpret_cast<const float4*>(x_row + (size_t)r * C);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) v[r][i] = __ldcg(xr + i * 32 + lane);
+  }
+  float mean[ROWS], rstd[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean[r] = sum / (float)C;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const float d0 = v[r][i].x - mean[r], d1 = v[r][i].y - mean[r], d2 = v[r][i].z - mean[r], d3 = v[r][i].w - mean[r];
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd[r] = rsqrtf(sq / (float)C + 1e-5f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float y0 = (v[r][i].x - mean[r]) * rstd[r] * gg.x + bb.x, y1 = (v[r][i].y - mean[r]) * rstd[r] * gg.y + bb.y;
+      const float y2 = (v[r][i].z - mean[r]) * rstd[r] * gg.z + bb.z, y3 = (v[r][i].w - mean[r]) * rstd[r] * gg.w + bb.w;
+      reinterpret_cast<uint2*>(out_row + (size_t)r * C)[i * 32 + lane] =
+          make_uint2(gemm_detail::pack_bf16x2(y0, y1), gemm_detail::pack_bf16x2(y2, y3));
     }
   }
 }
@@ -342,11 +391,20 @@ __device__ __noinline__ void ln_warp_rows(const float* __restrict__ x, const flo
 // lanes of a head reduce by xor shuffles), softmax weights through `s_w` (H*N*N floats of this
 // warp), then the v rows (U = H*dv/128 float4s per lane).  Same formula as attn_warp_task; the
 // summation order over dk differs (4 consecutive channels per lane).
+// `h0` / `Hs`: the warp handles heads [h0, h0 + Hs) of the H heads (T and U count the float4s of that
+// subset: Hs*dk/128 and Hs*dv/128); the 16-warp tower gives each sequence to two warps.
 template <int N, int T, int U>
 __device__ __noinline__ void attn_warp_seq(const float* __restrict__ base, int ld, const float* __restrict__ rcb,
                                               const float* __restrict__ rpb, const float* __restrict__ relk,
                                               __nv_bfloat16* __restrict__ out_seq, int H, int dk, int dv, int lane,
-                                              float* __restrict__ s_w) {
+                                              float* __restrict__ s_w, int h0 = 0) {
+  const float* qb = base + h0 * dk;                  // q columns of the subset
+  const float* kb = base + H * dk + h0 * dk;         // k columns
+  const float* vb = base + 2 * H * dk + h0 * dv;     // v columns
+  rcb += h0 * dk; rpb += h0 * dk;
+  relk += (size_t)h0 * (2 * N - 1) * dk;
+  __nv_bfloat16* ob = out_seq + h0 * dv;
+  const int out_ld = H * dv;
   const float scale = rsqrtf((float)dk);
   const int lph = dk >> 2;                   // lanes per head
   float4 q[N][T], k[N][T];
@@ -354,8 +412,8 @@ __device__ __noinline__ void attn_warp_seq(const float* __restrict__ base, int l
   for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      q[i][t] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * ld) + lane + 32 * t);
-      k[i][t] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * ld + H * dk) + lane + 32 * t);
+      q[i][t] = __ldcg(reinterpret_cast<const float4*>(qb + (size_t)i * ld) + lane + 32 * t);
+      k[i][t] = __ldcg(reinterpret_cast<const float4*>(kb + (size_t)i * ld) + lane + 32 * t);
     }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -411,7 +469,7 @@ __device__ __noinline__ void attn_warp_seq(const float* __restrict__ base, int l
     for (int j = 0; j < N; ++j)
 #pragma unroll
       for (int u = 0; u < UC; ++u)
-        v[j][u] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * ld + 2 * H * dk) + lane + 32 * (u0 + u));
+        v[j][u] = __ldcg(reinterpret_cast<const float4*>(vb + (size_t)j * ld) + lane + 32 * (u0 + u));
 #pragma unroll
     for (int u = 0; u < UC; ++u) {
       const int f = lane + 32 * (u0 + u);
@@ -424,12 +482,25 @@ __device__ __noinline__ void attn_warp_seq(const float* __restrict__ base, int l
           const float w = s_w[(h * N + i) * N + j];
           acc.x += w * v[j][u].x; acc.y += w * v[j][u].y; acc.z += w * v[j][u].z; acc.w += w * v[j][u].w;
         }
-        reinterpret_cast<uint2*>(out_seq + (size_t)i * (H * dv))[f] =
+        reinterpret_cast<uint2*>(ob + (size_t)i * out_ld)[f] =
             make_uint2(gemm_detail::pack_bf16x2(acc.x, acc.y), gemm_detail::pack_bf16x2(acc.z, acc.w));
       }
     }
   }
   __syncwarp();
+}
+
+// out-of-line fall-backs (general channel counts / head shapes): kept out of the kernel's register
+// allocation
+__device__ __noinline__ void ln_rows_generic(const float* x, const float* g, const float* b, __nv_bfloat16* out, int C,
+                                             int rows, int lane) {
+  for (int rr = 0; rr < rows; ++rr) ln_warp_row<true>(x + (size_t)rr * C, g, b, out + (size_t)rr * C, C, lane);
+}
+template <int N>
+__device__ __noinline__ void attn_task_generic(const float* base, int ld, const float* rcb, const float* rpb,
+                                               const float* relk, __nv_bfloat16* out_seq, int h, int H, int dk, int dv,
+                                               int lane) {
+  attn_warp_task<N, true>(base, ld, rcb, rpb, relk, out_seq, h, H, dk, dv, lane);
 }
 
 struct Item { int j, q, r, c; };
@@ -440,14 +511,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <int NPOS, int kBN>
-__global__ void __launch_bounds__(kThreads, 1)
+// 16 fp32 columns (chunk `cis` of the 2 in a 32-column slab row) of one row
+__device__ __forceinline__ void slab_write16_f32(uint8_t* row_base, int x7, int cis, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(row_base + (((cis * 4 + u) ^ x7) << 4)) =
+        make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+
+// EW = epilogue warps: 8 (thread = row x column half, 32-column TMEM chunks, two slabs per half) or 16
+// (thread = row x column quarter, 16-column chunks, one slab per quarter, <= 102 registers): the
+// row phases and the GEMM epilogues are latency-bound per warp, so twice the warps per scheduler
+// shortens every hop of the dependency chain.
+template <int NPOS, int kBN, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW + 64, 1)
 tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ CUtensorMap tm_ao,
              const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_qkv,
              const __grid_constant__ CUtensorMap tm_xt, const TowerArgs a) {
   using Cfg = tower::Cfg<kBN>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kChunks = kBN / 64;                 // 32-column accumulator chunks per epilogue thread
+  constexpr int kChunks = kBN / 64;                 // 32-column accumulator chunks per epilogue thread (EW = 8)
+  static_assert(EW == 8 || (EW == 16 && kBN == 256), "16 epilogue warps need 256-wide tiles");
+  auto ebar = [] { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); };   // all epilogue threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -483,7 +568,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull_bar[i], 1);
-        ptx::mbar_init(&tempty_bar[i], 2 * kEpiWarps);
+        ptx::mbar_init(&tempty_bar[i], 2 * EW);
       }
       for (int i = 0; i < 4; ++i) {
         ptx::mbar_init(&rin_bar[i], 1);
@@ -613,11 +698,11 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + EW) {
     // ===================== epilogue math / row-wise items =====================
     const int ew = warp - 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;
+    const int half = ew >> 2;            // column half (EW = 8) / column quarter (EW = 16)
     const int etid = threadIdx.x - 64;
     const int r = quad * 32 + lane;      // tile row owned by this thread
     const int x7 = r & 7;
@@ -630,12 +715,54 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
       const Phase& ph = a.ph[it.q];
       if (ph.type == PH_GEMM) {
         const bool out_f32 = ph.out_kind != OUT_BF16_RELU;
-        const int slab_chunks = out_f32 ? 1 : 2;
         const int n0 = it.c * kBN;
         const float* bias = a.blocks[it.j].bias[ph.w_idx];
         float* P = s_bias + acc_stage * kBN;
-        for (int i = etid; i < kBN; i += kEpiThreads) P[i] = (bias != nullptr && n0 + i < ph.n_cols) ? bias[n0 + i] : 0.0f;
-        gemm_detail::epi_bar_sync();
+        for (int i = etid; i < kBN; i += 32 * EW) P[i] = (bias != nullptr && n0 + i < ph.n_cols) ? bias[n0 + i] : 0.0f;
+        ebar();
+        if constexpr (EW == 16) {
+          // quarter `half` = 64 columns: 4 chunks of 16; fp32 = two 32-column slab jobs, bf16 = one
+          uint8_t* buf = staging + half * kSlabBytes + r * 128;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * kBN + half * 64;
+          uint32_t raw[2][16];
+          twait(&tfull_bar[acc_stage], acc_phase);
+          ptx::tc_fence_after();
+          if (etid == 0) stamp(id, 3);
+          gemm2::tmem_ld_32x16(taddr, raw[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const bool job_start = out_f32 ? (c & 1) == 0 : c == 0;
+            const bool job_end = out_f32 ? (c & 1) == 1 : c == 3;
+            if (job_start) twait(&rin_bar[half], job & 1);
+            float v[16], pv[16];
+            ptx::tmem_ld_wait();
+            if (c + 1 < 4) gemm2::tmem_ld_32x16(taddr + (c + 1) * 16, raw[(c + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
+            if (c == 3) {                  // accumulator fully read: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) gemm2::mbar_arrive_leader<2>(&tempty_bar[acc_stage]);
+            }
+            gemm2::load_param16(P + half * 64 + c * 16, pv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += pv[i];
+            if (out_f32) {
+              slab_write16_f32(buf, x7, c & 1, v);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+              gemm2::slab_write16(buf, x7, c, v);
+            }
+            if (job_end) {
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&rout_bar[half]);
+              ++job;
+            }
+          }
+        } else {
+        const int slab_chunks = out_f32 ? 1 : 2;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * kBN + half * (kBN / 2);
         uint32_t raw[2][32];
         twait(&tfull_bar[acc_stage], acc_phase);
@@ -675,6 +802,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
             ++job;
           }
         }
+        }
         if (etid == 0) stamp(id, 4);
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       } else {
@@ -687,20 +815,26 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           stamp(id, 1);
           stamp(id, 6);
         }
-        gemm_detail::epi_bar_sync();
+        ebar();
         const int row_base = it.r * kTileRows + rank * kBM + it.c * kSubRows;
         if (ph.type == PH_LN) {
           const BlockParams& bp = a.blocks[it.j];
-          constexpr int kRowsPerWarp = kSubRows / kEpiWarps;          // consecutive rows of one warp
+          constexpr int kRowsPerWarp = kSubRows / EW;                 // consecutive rows of one warp
           const int row = row_base + ew * kRowsPerWarp;
           const int valid = a.R - row < kRowsPerWarp ? a.R - row : kRowsPerWarp;
           if (valid > 0) {
             const float* xr = a.xt + (size_t)row * a.C;
             __nv_bfloat16* hr = a.hn + (size_t)row * a.C;
-            {
+            if (a.C == 1536) {     // (two rows in flight together, ln_warp_row_n<12, 2>, spills 430 bytes here)
 #pragma unroll 1
               for (int rr = 0; rr < valid; ++rr)
-                ln_warp_row<true>(xr + (size_t)rr * a.C, bp.ln_g[ph.w_idx], bp.ln_b[ph.w_idx], hr + (size_t)rr * a.C, a.C, lane);
+                ln_warp_row_n<12>(xr + (size_t)rr * a.C, bp.ln_g[ph.w_idx], bp.ln_b[ph.w_idx], hr + (size_t)rr * a.C, lane);
+            } else if (a.C == 384) {
+#pragma unroll 1
+              for (int rr = 0; rr < valid; ++rr)
+                ln_warp_row_n<3>(xr + (size_t)rr * a.C, bp.ln_g[ph.w_idx], bp.ln_b[ph.w_idx], hr + (size_t)rr * a.C, lane);
+            } else {
+              ln_rows_generic(xr, bp.ln_g[ph.w_idx], bp.ln_b[ph.w_idx], hr, a.C, valid, lane);
             }
           }
         } else if (ph.type == PH_ATTN) {
@@ -709,10 +843,19 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           const bool pow2 = (a.dk & (a.dk - 1)) == 0;
           const bool fast = a.attn_fast != 0 && NPOS <= 2 && pow2 && a.dk >= 4 && a.dk <= 128 && a.dv % 4 == 0 && hdk == 512 &&
                             (hdv == 1536 || hdv == 384) && a.H * NPOS * NPOS <= 128;
-          if (fast) {
+          if (fast && EW == 16 && NPOS == 2 && hdv == 1536) {
+            // two warps per sequence, half of the heads each (32 + 48 registers of loads in flight)
+            float* sw = s_attn_w + ew * 128;
+            const int row = row_base + (ew >> 1) * NPOS;
+            if constexpr (NPOS == 2) {
+              if (row < a.R)
+                attn_warp_seq<2, 2, 6>(a.qkv + (size_t)row * a.nqkv, a.nqkv, bp.rcb, bp.rpb, bp.relk,
+                                       a.ao + (size_t)row * hdv, a.H, a.dk, a.dv, lane, sw, (ew & 1) * (a.H / 2));
+            }
+          } else if (fast) {
             float* sw = s_attn_w + ew * 128;
 #pragma unroll 1
-            for (int sl = ew; sl < kSubRows / NPOS; sl += kEpiWarps) {
+            for (int sl = ew; sl < kSubRows / NPOS; sl += EW) {
               const int row = row_base + sl * NPOS;
               if (row >= a.R) continue;
               const float* base = a.qkv + (size_t)row * a.nqkv;
@@ -725,17 +868,17 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           } else {
             const int tasks = (kSubRows / NPOS) * a.H;
 #pragma unroll 1
-            for (int t = ew; t < tasks; t += kEpiWarps) {
+            for (int t = ew; t < tasks; t += EW) {
               const int row = row_base + (t / a.H) * NPOS;
               if (row < a.R)
-                attn_warp_task<NPOS, true>(a.qkv + (size_t)row * a.nqkv, a.nqkv, bp.rcb, bp.rpb, bp.relk,
-                                           a.ao + (size_t)row * hdv, t % a.H, a.H, a.dk, a.dv, lane);
+                attn_task_generic<NPOS>(a.qkv + (size_t)row * a.nqkv, a.nqkv, bp.rcb, bp.rpb, bp.relk,
+                                        a.ao + (size_t)row * hdv, t % a.H, a.H, a.dk, a.dv, lane);
             }
           }
         } else {
           // pointwise ConvBlock operand: hn = GELU(BN(x))
 #pragma unroll 1
-          for (int rr = ew; rr < kSubRows; rr += kEpiWarps) {
+          for (int rr = ew; rr < kSubRows; rr += EW) {
             const int row = row_base + rr;
             if (row >= a.R) continue;
             const float4* xr = reinterpret_cast<const float4*>(a.xt + (size_t)row * a.C);
@@ -752,7 +895,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         }
         if (it.q < kPhasesPerBlock) {
           // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
-          gemm_detail::epi_bar_sync();
+          ebar();
           if (etid == 0) {
             stamp(id, 4);
             red_release_gpu_add(own_flag(it), 1u);
@@ -763,7 +906,47 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
     }
   } else {
     // ===================== slab store warp (one per column half) =====================
-    const int half = warp - (2 + kEpiWarps);
+    const int half = warp - (2 + EW);
+    if constexpr (EW == 16) {
+      // one slab per column quarter; this thread serves quarters 2*half and 2*half+1 in turn
+      if (lane == 0) {
+        ptx::mbar_arrive(&rin_bar[2 * half]);
+        ptx::mbar_arrive(&rin_bar[2 * half + 1]);
+        uint32_t j = 0;                    // slab jobs done per quarter
+        for (int id = pair; id < a.total_items; id += n_pairs) {
+          const Item it = decode(id);
+          const Phase& ph = a.ph[it.q];
+          if (ph.type != PH_GEMM) continue;
+          const bool out_f32 = ph.out_kind != OUT_BF16_RELU;
+          const int jobs = out_f32 ? 2 : 1;
+          const CUtensorMap* mO = ph.out_kind == OUT_F32_STORE ? &tm_qkv : (ph.out_kind == OUT_F32_REDUCE ? &tm_xt : &tm_u);
+          const int row0 = it.r * kTileRows + rank * kBM;
+          for (int sj = 0; sj < jobs; ++sj, ++j) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int grp = 2 * half + q;
+              twait(&rout_bar[grp], j & 1);
+              const int col = it.c * kBN + grp * 64 + sj * 32;
+              if (ph.out_kind == OUT_F32_REDUCE) tma_reduce_add_2d(mO, staging + grp * kSlabBytes, col, row0);
+              else tma_store_2d(mO, staging + grp * kSlabBytes, col, row0);
+              gemm2::bulk_commit();
+            }
+            if (sj + 1 < jobs) {             // the slabs are free once read; the last job waits below
+              gemm2::bulk_wait_read0();
+              ptx::mbar_arrive(&rin_bar[2 * half]);
+              ptx::mbar_arrive(&rin_bar[2 * half + 1]);
+            }
+          }
+          // the tile's stores are complete (not just read): free the slabs, publish
+          gemm2::bulk_wait_all();
+          ptx::mbar_arrive(&rin_bar[2 * half]);
+          ptx::mbar_arrive(&rin_bar[2 * half + 1]);
+          fence_proxy_async_all();
+          red_release_gpu_add(own_flag(it), 1u);
+          if (half == 0) stamp(id, 5);
+        }
+      }
+    } else
     if (lane == 0) {
       uint8_t* bufs = staging + half * 2 * kSlabBytes;
       uint64_t* my_rin = rin_bar + half * 2;
