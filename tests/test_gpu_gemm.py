@@ -172,6 +172,40 @@ EPI_CASES = [
 ]
 
 
+@pytest.mark.parametrize('rows,K,N,second,act,use_scale', [
+    (5000, 64, 768, True, 0, False),      # the stem: only a0 = GELU(BN(conv + b)) is stored
+    (4100, 256, 768, False, 1, True),     # one bf16 output, BN affine + bias + ReLU, ragged last row tile
+    (6000, 128, 1024, False, 2, False),   # GELU
+    (3300, 512, 2560, True, 1, True),
+])
+def test_gemm_sixteen_warp_epilogue(cuda, rows, K, N, second, act, use_scale):
+  """Single-output bf16 launches without residual take the 16-epilogue-warp variant of gemm2_kernel
+  (thread = row x column quarter, 16-column TMEM chunks, one slab per quarter) once there are
+  enough 256-wide tiles; same reference as the generic epilogue test."""
+  g = torch.Generator().manual_seed(rows + K + N)
+  A = torch.randn(1, rows, K, generator=g).to(cuda).bfloat16()
+  W = (torch.randn(1, N, K, generator=g) * K ** -0.5).to(cuda).bfloat16()
+  bias = torch.randn(N, generator=g).to(cuda)
+  scale = (1 + 0.2 * torch.randn(N, generator=g)).to(cuda) if use_scale else None
+  shift = (0.3 * torch.randn(N, generator=g)).to(cuda) if use_scale else None
+  scale2 = (1 + 0.2 * torch.randn(N, generator=g)).to(cuda)
+  shift2 = (0.3 * torch.randn(N, generator=g)).to(cuda)
+  dst = torch.full((rows + 3, N), 7.0, device=cuda, dtype=torch.bfloat16)     # 3 guard rows
+  _lib.selftest_gemm_epilogue(A, W, taps=1, flat=True, bias=bias, scale=scale, shift=shift, act=act,
+                              out=None if second else dst, out2=dst if second else None,
+                              scale2=scale2 if second else None, shift2=shift2 if second else None,
+                              act2=2 if second else 0)
+  torch.cuda.synchronize()
+  v = A[0].float() @ W[0].float().t()
+  if use_scale:
+    v = v * scale + shift
+  v = _act(v + bias, act)
+  if second:
+    v = _act(v * scale2 + shift2, 2)
+  assert float((dst[:rows].float() - v).abs().max()) < 3e-2 * max(1.0, float(v.abs().max()))
+  assert bool((dst[rows:] == 7.0).all()), 'rows past the end were written'
+
+
 @pytest.mark.parametrize('S,L,K,N,taps', [(7, 100, 256, 256, 5), (40, 50, 128, 896, 5), (3, 25, 64, 128, 5),
                                           (130, 100, 768, 768, 5), (5, 30, 64, 256, 9)])
 def test_halo_conv_rows_as_descriptor_offsets(cuda, S, L, K, N, taps):
