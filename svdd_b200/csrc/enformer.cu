@@ -629,7 +629,8 @@ size_t ef_carve(const svdd_enformer* h, Workspace& W, int64_t rows, int L, EfWs*
   o->ao = W.take<__nv_bfloat16>(R * h->H * h->dv + 64);
   o->u = W.take<__nv_bfloat16>(R * 2 * C + 64);
   o->partials = W.take<float>(R * (2 * C / 64) + 64);
-  o->flags = W.take<unsigned>((size_t)tower::kPhasesPerBlock * kMaxBlocksT * ceil_div<size_t>(R, tower::kTileRows) + 64);
+  o->flags = W.take<unsigned>((size_t)(tower::kPhasesPerBlock + tower::kMaxSplitTiles) * kMaxBlocksT *
+                              ceil_div<size_t>(R, tower::kTileRows) + 64);
   return W.used();
 }
 }  // namespace
@@ -711,6 +712,18 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   a.ph[4] = row_phase(PH_LN, 1);
   a.ph[5] = gemm_phase(2 * C, C, A_HN, OUT_BF16_RELU, 2);
   a.ph[6] = gemm_phase(C, 2 * C, A_U, OUT_F32_REDUCE, 3);
+  {
+    // FF2 (K = 2C, the longest item of the chain): optionally K split in two slices whose partial sums
+    // are added in order (SVDD_TOWER_SPLITK=2).  Off: measured 1.09 vs 1.07 ms -- the FF2 phase gets
+    // shorter (21.4 -> 17.9 us) but its 120 items no longer fit one round of the 74 pairs.
+    const char* e = getenv("SVDD_TOWER_SPLITK");
+    const int ks = e ? atoi(e) : 1;
+    if (ks == 2 && a.ph[6].kblocks % 2 == 0 && a.ph[6].items_per_rt <= kMaxSplitTiles) {
+      a.ph[6].ksplit = 2;
+      a.ph[6].items_per_rt *= 2;
+      a.ph[6].kblocks /= 2;
+    }
+  }
   a.ph[7] = row_phase(PH_BNACT, 0);
   int start = 0;
   for (int q = 0; q < kPhasesPerBlock; ++q) {
@@ -723,6 +736,7 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   a.xt = b.xt; a.hn = b.hn; a.qkv = b.qkv; a.ao = b.ao;
   a.bn_s = h->bnpw_s; a.bn_t = h->bnpw_t;
   a.flags = b.flags;
+  a.sk_flags = b.flags + (size_t)kPhasesPerBlock * a.n_blocks * a.RT;
   { const char* e = getenv("SVDD_TOWER_ATTN_FAST"); a.attn_fast = e ? atoi(e) : 1; }
 
   CUtensorMap tm_hn, tm_ao, tm_u, tm_qkv, tm_xt;
@@ -751,7 +765,7 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   const int widest = a.ph[5].items_per_rt > a.ph[1].items_per_rt ? a.ph[5].items_per_rt : a.ph[1].items_per_rt;
   const int max_items_per_phase = (widest > kSubItems ? widest : kSubItems) * a.RT;
   if (pairs > max_items_per_phase) pairs = max_items_per_phase;
-  SVDD_CUDA(cudaMemsetAsync(b.flags, 0, (size_t)kPhasesPerBlock * a.n_blocks * a.RT * sizeof(unsigned), st));
+  SVDD_CUDA(cudaMemsetAsync(b.flags, 0, (size_t)(kPhasesPerBlock + kMaxSplitTiles) * a.n_blocks * a.RT * sizeof(unsigned), st));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool prof = gemm_prof_on();
   if (prof) {

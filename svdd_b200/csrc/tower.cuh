@@ -42,6 +42,7 @@ constexpr int kTileRows = 2 * kBM;        // rows per CTA pair
 constexpr int kSubRows = 16;              // rows per CTA of one LN / attention / BN item
 constexpr int kSubItems = kBM / kSubRows; // such items per row tile
 constexpr int kPhasesPerBlock = 7;
+constexpr int kMaxSplitTiles = 16;        // column tiles of a split-K phase (C <= 4096)
 constexpr int kLnVecs = 16;               // C <= 2048 (float4s per lane)
 
 enum PhaseType { PH_LN = 0, PH_GEMM = 1, PH_ATTN = 2, PH_BNACT = 3 };
@@ -58,6 +59,10 @@ struct Phase {
   int out_kind = 0;       // GEMM: OutKind
   int w_idx = 0;          // GEMM: weight map of the block; LN: 0 = ln1, 1 = ln2
   int start = 0;          // first item of this phase within its block (already x RT)
+  // GEMM with a reduce-add output: K split over `ksplit` items per column tile (item c = tile *
+  // ksplit + ks).  The partial sums are added into `x` IN ORDER (slice ks waits for the stores of
+  // slice ks-1 of the same tile), so the result does not depend on timing.
+  int ksplit = 1;
 };
 
 // per transformer block, in global memory (tensor maps must be 64-byte aligned)
@@ -84,6 +89,7 @@ struct TowerArgs {
   const float* bn_s = nullptr;   // final BN (folded) + GELU -> hn
   const float* bn_t = nullptr;
   unsigned* flags = nullptr;     // [(n_blocks * 7) * RT], zeroed before the launch
+  unsigned* sk_flags = nullptr;  // split-K order: [n_blocks][RT][kMaxSplitTiles] completed-store counters, zeroed too
   int attn_fast = 1;             // per-sequence attention items (attn_warp_seq); 0 = per-(sequence, head) tasks
   // debugging aid (SVDD_TOWER_TRACE=file): per item 8 x globaltimer ns, written by the pair's even CTA:
   // [0] wait for the dependency begins (producer / row item) [1] dependency satisfied [2] MMA may start
@@ -618,6 +624,10 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
     return a.flags + (size_t)(it.j * kPhasesPerBlock + it.q) * a.RT + it.r;
   };
 
+  // split-K order flag of the item's column tile (store threads only)
+  auto sk_flag = [&](const Item& it, const Phase& ph) -> unsigned* {
+    return a.sk_flags + ((size_t)it.j * a.RT + it.r) * kMaxSplitTiles + it.c / ph.ksplit;
+  };
   auto stamp = [&](int id, int slot) {
     if (a.trace != nullptr && rank == 0) a.trace[(size_t)id * 8 + slot] = slot == 6 ? (unsigned long long)pair : globaltimer_ns();
   };
@@ -634,14 +644,15 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         const CUtensorMap* mA = ph.a_map == A_HN ? &tm_hn : (ph.a_map == A_AO ? &tm_ao : &tm_u);
         const CUtensorMap* mW = &a.blocks[it.j].w[ph.w_idx];
         const int row0 = it.r * kTileRows + rank * kBM;
-        const int wrow0 = it.c * kBN + rank * (kBN / 2);
+        const int wrow0 = (it.c / ph.ksplit) * kBN + rank * (kBN / 2);
+        const int kb0 = (it.c % ph.ksplit) * ph.kblocks;        // first K block of this slice
         const int pre = ph.kblocks < kStages ? ph.kblocks : kStages;
         // weights of the first ring stages: no dependency, request them before the wait
         uint32_t s2 = stage, p2 = phase;
         for (int kb = 0; kb < pre; ++kb) {
           twait(&empty_bar[s2], p2 ^ 1);
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s2], tx_bytes);
-          gemm2::tma_load_2d_cg<2>(stage_base + s2 * Cfg::kStageBytes + Cfg::kABytes, mW, &full_bar[s2], kb * kBK, wrow0);
+          gemm2::tma_load_2d_cg<2>(stage_base + s2 * Cfg::kStageBytes + Cfg::kABytes, mW, &full_bar[s2], (kb0 + kb) * kBK, wrow0);
           if (++s2 == kStages) { s2 = 0; p2 ^= 1; }
         }
         unsigned target = 0;
@@ -652,15 +663,15 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         stamp(id, 6);
         fence_proxy_async_all();
         for (int kb = 0; kb < pre; ++kb) {
-          gemm2::tma_load_2d_cg<2>(stage_base + stage * Cfg::kStageBytes, mA, &full_bar[stage], kb * kBK, row0);
+          gemm2::tma_load_2d_cg<2>(stage_base + stage * Cfg::kStageBytes, mA, &full_bar[stage], (kb0 + kb) * kBK, row0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         for (int kb = pre; kb < ph.kblocks; ++kb) {
           twait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          gemm2::tma_load_2d_cg<2>(sa, mA, &full_bar[stage], kb * kBK, row0);
-          gemm2::tma_load_2d_cg<2>(sa + Cfg::kABytes, mW, &full_bar[stage], kb * kBK, wrow0);
+          gemm2::tma_load_2d_cg<2>(sa, mA, &full_bar[stage], (kb0 + kb) * kBK, row0);
+          gemm2::tma_load_2d_cg<2>(sa + Cfg::kABytes, mW, &full_bar[stage], (kb0 + kb) * kBK, wrow0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -715,8 +726,8 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
       const Phase& ph = a.ph[it.q];
       if (ph.type == PH_GEMM) {
         const bool out_f32 = ph.out_kind != OUT_BF16_RELU;
-        const int n0 = it.c * kBN;
-        const float* bias = a.blocks[it.j].bias[ph.w_idx];
+        const int n0 = (it.c / ph.ksplit) * kBN;
+        const float* bias = (it.c % ph.ksplit) == 0 ? a.blocks[it.j].bias[ph.w_idx] : nullptr;   // once per tile
         float* P = s_bias + acc_stage * kBN;
         for (int i = etid; i < kBN; i += 32 * EW) P[i] = (bias != nullptr && n0 + i < ph.n_cols) ? bias[n0 + i] : 0.0f;
         ebar();
@@ -921,12 +932,17 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           const int jobs = out_f32 ? 2 : 1;
           const CUtensorMap* mO = ph.out_kind == OUT_F32_STORE ? &tm_qkv : (ph.out_kind == OUT_F32_REDUCE ? &tm_xt : &tm_u);
           const int row0 = it.r * kTileRows + rank * kBM;
+          const int ks = it.c % ph.ksplit, ctile = it.c / ph.ksplit;
+          if (ks > 0) {                      // the earlier K slices of this tile have been added
+            wait_flag(sk_flag(it, ph), 4u * (unsigned)ks);
+            fence_proxy_async_all();
+          }
           for (int sj = 0; sj < jobs; ++sj, ++j) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int grp = 2 * half + q;
               twait(&rout_bar[grp], j & 1);
-              const int col = it.c * kBN + grp * 64 + sj * 32;
+              const int col = ctile * kBN + grp * 64 + sj * 32;
               if (ph.out_kind == OUT_F32_REDUCE) tma_reduce_add_2d(mO, staging + grp * kSlabBytes, col, row0);
               else tma_store_2d(mO, staging + grp * kSlabBytes, col, row0);
               gemm2::bulk_commit();
@@ -942,6 +958,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           ptx::mbar_arrive(&rin_bar[2 * half]);
           ptx::mbar_arrive(&rin_bar[2 * half + 1]);
           fence_proxy_async_all();
+          if (ph.ksplit > 1) red_release_gpu_add(sk_flag(it, ph), 1u);
           red_release_gpu_add(own_flag(it), 1u);
           if (half == 0) stamp(id, 5);
         }
@@ -963,10 +980,15 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         const int slabs = (kBN / 2) / slab_cols;
         const CUtensorMap* mO = ph.out_kind == OUT_F32_STORE ? &tm_qkv : (ph.out_kind == OUT_F32_REDUCE ? &tm_xt : &tm_u);
         const int row0 = it.r * kTileRows + rank * kBM;
+        const int ks = it.c % ph.ksplit, ctile = it.c / ph.ksplit;
+        if (ks > 0) {                        // the earlier K slices of this tile have been added
+          wait_flag(sk_flag(it, ph), 4u * (unsigned)ks);
+          fence_proxy_async_all();
+        }
         for (int s = 0; s < slabs; ++s, ++j) {
           twait(&my_rout[j & 1], (j >> 1) & 1);
           const uint8_t* buf = bufs + (j & 1) * kSlabBytes;
-          const int col = it.c * kBN + half * (kBN / 2) + s * slab_cols;
+          const int col = ctile * kBN + half * (kBN / 2) + s * slab_cols;
           if (ph.out_kind == OUT_F32_REDUCE) tma_reduce_add_2d(mO, buf, col, row0);
           else tma_store_2d(mO, buf, col, row0);
           gemm2::bulk_commit();
@@ -981,6 +1003,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         gemm2::bulk_wait_all();
         ptx::mbar_arrive(&my_rin[(j - 1) & 1]);
         fence_proxy_async_all();
+        if (ph.ksplit > 1) red_release_gpu_add(sk_flag(it, ph), 1u);
         red_release_gpu_add(own_flag(it), 1u);
         if (half == 0) stamp(id, 5);
       }

@@ -17,6 +17,9 @@ for full in (True, False):
     os.environ['SVDD_TOWER'] = '0'
     ref = value_nets.score_tokens(emb, head, tok)
     os.environ['SVDD_TOWER'] = '1'
+    os.environ['SVDD_TOWER_SPLITK'] = os.environ.get('STRESS_SPLITK', '1')   # '1': bit-exact against the per-launch path
+    if os.environ['SVDD_TOWER_SPLITK'] != '1':
+      ref = value_nets.score_tokens(emb, head, tok)                              # split-K: compare against its own first run
     nd = 0
     for i in range(reps):
       got = value_nets.score_tokens(emb, head, tok)
