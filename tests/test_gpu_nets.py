@@ -128,6 +128,29 @@ def test_convgru_many_rows(cuda):
   assert torch.isfinite(full).all()
 
 
+def test_convgru_tensor_core_recurrence_equals_scalar_kernel(cuda, tmp_path):
+  """The mma.sync GRU recurrence (bf16 hi/lo split, fp32 accumulate) against the scalar
+  FMA-pipe kernel (SVDD_GRU_SCALAR=1, read once per process: run in a subprocess) on rows
+  that do not fill the last 16-sequence block."""
+  import os
+  import subprocess
+  import sys
+  out = str(tmp_path / 'scalar.pt')
+  code = ('import sys, torch; sys.path[:0] = [%r, %r]; import helpers; from svdd_b200 import value_nets; '
+          'd = torch.device("cuda:0"); e, h = helpers.build_convgru_value(); '
+          'tok = helpers.random_tokens(77, 50, 23, 0.4).to(d); '
+          'torch.save(value_nets.score_tokens(e.to(d), h.to(d), tok).cpu(), %r)'
+          % (helpers.ROOT, os.path.join(helpers.ROOT, 'tests'), out))
+  subprocess.run([sys.executable, '-c', code], check=True, env=dict(os.environ, SVDD_GRU_SCALAR='1'), timeout=300)
+  scalar = torch.load(out)
+  emb, head = helpers.build_convgru_value()
+  tok = helpers.random_tokens(77, 50, 23, 0.4).to(cuda)
+  got = value_nets.score_tokens(emb.to(cuda), head.to(cuda), tok).cpu()
+  err = float((got - scalar).abs().max())
+  print(f'\n[convgru mma vs scalar recurrence] max |d| = {err:.3e} (scale {float(scalar.abs().max()):.3g})')
+  assert err <= 2e-5 * max(1.0, float(scalar.abs().max()))
+
+
 def test_enformer_value(cuda):
   g = helpers.load_golden('value_nets.npz')
   tok = T(g['enformer_tokens'])
