@@ -25,7 +25,11 @@
 // block barriers per layer) were slower (0.37 ms vs 0.30 ms per B=128 pass).
 // Sequences longer than 128 use two row tiles (L <= 256); sequences of at most 64 positions
 // are processed two per CTA (one per tile; the zero gap between them exceeds every in-range
-// tap offset).
+// tap offset).  In that mode tile 1's sequence sits in tile rows 64..127, so the real rows of
+// the two tiles belong to four different TMEM lane quadrants = four epilogue warps on four
+// different schedulers; epilogue warps that own no real row skip the arithmetic and only keep
+// the barriers in step (before: all eight ran the full epilogue, the four useful ones two
+// to a scheduler).
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -73,8 +77,15 @@ __host__ __device__ inline int smem_bytes(int a_rows) {
 
 // tile m of the CTA's work item: first row in sequence coordinates
 __host__ __device__ inline int tile_seq_row0(int m, int two_seq) { return two_seq ? 0 : 128 * m; }
+// two sequences per CTA: tile 1's sequence sits in tile rows 64..127 (TMEM lane quadrants 2, 3),
+// tile 0's in rows 0..63 (quadrants 0, 1), so the four epilogue warps that own real rows sit on
+// four different warp schedulers; the other four only keep the barriers in step.
+__host__ __device__ inline int tile_lane0(int m, int two_seq) { return two_seq ? 64 * m : 0; }
+// first row of the operand planes (before pad_before) that tile m's MMA of tap offset o reads
+__host__ __device__ inline int tile_plane_row(int m, int o, int two_seq) { return 128 * m + o - tile_lane0(m, two_seq); }
 // does tap offset `o` touch real rows of tile m?
 __host__ __device__ inline bool tap_hits(int m, int o, int L, int two_seq) {
+  if (two_seq) return o > -L && o < L;
   const int lo = tile_seq_row0(m, two_seq) + o;
   return (tile_seq_row0(m, two_seq) < L) && (lo + 128 > 0) && (lo < L);
 }
@@ -221,8 +232,8 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
                 if (m == 0 ? !hit0 : !hit1) continue;
-                // rows (pad_before + 128 m + o) .. +127 of K half kb: the tap is a row offset
-                const uint32_t sa = a_base + kb * plane_bytes + (uint32_t)(a.pad_before + 128 * m + o) * 128u;
+                // 128 rows of K half kb starting at tile_plane_row: the tap is a row offset
+                const uint32_t sa = a_base + kb * plane_bytes + (uint32_t)(a.pad_before + tile_plane_row(m, o, two_seq)) * 128u;
                 const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -245,11 +256,13 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // ===================== epilogue: thread = one row of one tile =====================
     const int ew = warp - 2;
     const int quad = warp & 3;               // TMEM lane quadrant of this warp
-    const int m = ew >> 2;                   // tile
+    const int m = two_seq ? (quad >> 1) : (ew >> 2);             // tile
     const int etid = threadIdx.x - 64;
     const int r_tile = quad * 32 + lane;
-    const int row = tile_seq_row0(m, two_seq) + r_tile;          // position within the sequence
-    const int arow = a.pad_before + 128 * m + r_tile;            // row of the operand planes
+    const int row = tile_seq_row0(m, two_seq) + r_tile - tile_lane0(m, two_seq);   // position within the sequence
+    const int arow = a.pad_before + 128 * m + r_tile - tile_lane0(m, two_seq);     // row of the operand planes
+    // does this warp own any real row?  (two_seq: warps 6..9 duplicate the quadrants of 2..5)
+    const bool wact = (two_seq ? ew < 4 : true) && (row - lane < L);
     const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + m * kH;
     const uint32_t t_res = t_acc + 2 * kH;
     uint8_t* a_row0 = s_a + (size_t)arow * 128;
@@ -319,6 +332,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           P[3 * kH + i] = a.ln_b[i];
         }
         epi_bar_sync();
+        if (wact) {
         float v[kH];
         int tk[kTaps];
 #pragma unroll
@@ -356,6 +370,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         write_operand(v, P, true, valid);
         tmem_st_wait();
+        }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
@@ -369,6 +384,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         ptx::mbar_wait(tfull_bar, tphase);
         tphase ^= 1;
         ptx::tc_fence_after();
+        if (wact) {
         float v[kH];
         uint32_t racc[2][32], rres[2][32];
         ptx::tmem_ld_32x32(t_acc, racc[0]);
@@ -393,6 +409,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         write_operand(v, P, r + 1 < nl, valid);
         tmem_st_wait();
+        }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
@@ -406,6 +423,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         ptx::mbar_wait(tfull_bar, tphase);
         tphase ^= 1;
         ptx::tc_fence_after();
+        if (wact) {
         float lg[kVocab];
 #pragma unroll
         for (int j = 0; j < kVocab; ++j) lg[j] = 0.0f;
@@ -427,6 +445,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           float* o = a.logits + ((size_t)seq * L + row) * kVocab;
 #pragma unroll
           for (int j = 0; j < kVocab; ++j) o[j] = lg[j] + s_w2[kVocab * kH + j];
+        }
         }
         // the next item's embed overwrites the operand planes and the residual columns: the
         // MMAs that read them have retired (tfull), the accumulator reads above are complete

@@ -217,7 +217,7 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
       for (int m = 0; m < 2; ++m) {
         const int o = (t - kTaps / 2) * h->dil[i];
         if (!denf::tap_hits(m, o, L, a.two_seq)) continue;
-        const int start = 128 * m + o;
+        const int start = denf::tile_plane_row(m, o, a.two_seq);
         if (-start > pad_before) pad_before = -start;
         if (start + 128 > max_end) max_end = start + 128;
       }
