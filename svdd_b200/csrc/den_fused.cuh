@@ -47,7 +47,7 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kParamBytes = 2 * 4 * kH * 4;       // [parity][bias, tbias, gamma, beta][128]
 constexpr int kW2Bytes = (kVocab * kH + 8) * 4;
-constexpr int kXchBytes = 0;
+constexpr int kXchBytes = 2 * kEpiThreads * 8 * 4;   // split epilogue: [parity][thread][8] floats
 constexpr int kBarBytes = 256;
 
 struct Args {
@@ -68,6 +68,7 @@ struct Args {
   int pad_before;            // zero rows in front of the first tile
   int a_rows;                // rows of one operand plane (multiple of 8)
   int two_seq;               // L <= 64: tile m holds sequence (2*iter + m)
+  int split;                 // two_seq only: two epilogue threads per row (64 channels each)
   int dil[kMaxLayers];
 };
 
@@ -252,7 +253,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         __syncwarp();
       }
     }
-  } else {
+  } else if (!a.split) {
     // ===================== epilogue: thread = one row of one tile =====================
     const int ew = warp - 2;
     const int quad = warp & 3;               // TMEM lane quadrant of this warp
@@ -449,6 +450,217 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         // the next item's embed overwrites the operand planes and the residual columns: the
         // MMAs that read them have retired (tfull), the accumulator reads above are complete
+        ptx::tc_fence_before();
+      }
+    }
+  } else {
+    // ===================== split epilogue (two sequences per CTA) =====================
+    // Real rows occupy TMEM lane quadrants 0,1 (tile 0) and 2,3 (tile 1); each quadrant is
+    // reachable by two of the eight epilogue warps (warp & 3).  Both work on the same 32 rows:
+    // warps 2..5 on channels 0..63, warps 6..9 on channels 64..127, so a row's serial chain
+    // (TMEM loads, LayerNorm, operand write) is half as long.  The LayerNorm statistics are
+    // combined through shared memory (Chan's pairwise update of sum and centred sum of squares)
+    // with one 64-thread named barrier per layer.
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int quad = warp & 3;
+    const int m = quad >> 1;
+    const int etid = threadIdx.x - 64;
+    const int row = (quad & 1) * 32 + lane;                      // position within the sequence
+    const int arow = a.pad_before + 128 * m + row;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + m * kH + half * 64;
+    const uint32_t t_res = t_acc + 2 * kH;
+    uint8_t* a_rowh = s_a + (size_t)half * plane_bytes + (size_t)arow * 128;
+    const int x7 = arow & 7;
+    const bool wact = (row - lane) < L;
+    const int ch0 = half * 64;
+    const Tok* tokens = reinterpret_cast<const Tok*>(a.tokens);
+    uint32_t tphase = 0;
+    int xpar = 0;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
+    auto xch_mine = [&](int par) { return s_xch + ((size_t)par * kEpiThreads + etid) * 8; };
+    auto xch_peer = [&](int par) { return s_xch + ((size_t)par * kEpiThreads + (etid ^ 128)) * 8; };
+
+    auto write_operand = [&](float* v, const float* P, bool ln, bool valid) {
+      if (ln) {
+        float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float pt[32];
+          ld_param32(P + 1 * kH + ch0 + c * 32, pt);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[c * 32 + i] += pt[i]; s4[i & 3] += v[c * 32 + i]; }
+        }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        const float ml = sum * (1.0f / 64);
+        float q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { const float d = v[i] - ml; q4[i & 3] += d * d; }
+        const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        *reinterpret_cast<float2*>(xch_mine(xpar)) = make_float2(sum, m2);
+        pair_sync();
+        const float2 o = *reinterpret_cast<const float2*>(xch_peer(xpar));
+        xpar ^= 1;
+        const float mean = (sum + o.x) * (1.0f / kH);
+        const float dm = (sum - o.x) * (1.0f / 64);
+        const float rstd = rsqrtf((m2 + o.y + dm * dm * 32.0f) * (1.0f / kH) + 1e-5f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float pg[32], pb[32];
+          ld_param32(P + 2 * kH + ch0 + c * 32, pg);
+          ld_param32(P + 3 * kH + ch0 + c * 32, pb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c * 32 + i] = (v[c * 32 + i] - mean) * rstd * pg[i] + pb[i];
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)          // 16-byte chunk j of this K half's 128-byte row
+          *reinterpret_cast<uint4*>(a_rowh + ((j ^ x7) << 4)) =
+              make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                         pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+      }
+    };
+    auto stage_params = [&](int r, float* P) {
+      for (int i = etid; i < kH; i += kEpiThreads) {
+        P[i] = r < nl ? a.conv_b[r * kH + i] : a.fc0_b[i];
+        if (r + 1 < nl) {
+          P[1 * kH + i] = a.time_bias[(r + 1) * kH + i];
+          P[2 * kH + i] = a.ln_g[(r + 1) * kH + i];
+          P[3 * kH + i] = a.ln_b[(r + 1) * kH + i];
+        }
+      }
+    };
+
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t seq = 2 * it + m;
+      const bool valid = (seq < a.n_rows) && (row < L);
+      {
+        float* P = s_param;
+        for (int i = etid; i < kH; i += kEpiThreads) {
+          P[1 * kH + i] = a.time_bias[i];
+          P[2 * kH + i] = a.ln_g[i];
+          P[3 * kH + i] = a.ln_b[i];
+        }
+        epi_bar_sync();
+        if (wact) {
+          float v[64];
+          int tk[kTaps];
+#pragma unroll
+          for (int t = 0; t < kTaps; ++t) {
+            const int li = row + t - kTaps / 2;
+            tk[t] = (valid && li >= 0 && li < L) ? load_tok(tokens, (size_t)seq * L + li) : -1;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float acc[32];
+            const float4* b4 = reinterpret_cast<const float4*>(a.embed_b + ch0 + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = __ldg(b4 + i);
+              acc[4 * i] = f.x; acc[4 * i + 1] = f.y; acc[4 * i + 2] = f.z; acc[4 * i + 3] = f.w;
+            }
+#pragma unroll
+            for (int t = 0; t < kTaps; ++t) {
+              if (tk[t] >= 0) {
+                const float4* w4 = reinterpret_cast<const float4*>(a.embed_w + (t * kVocab + tk[t]) * kH + ch0 + c * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 f = __ldg(w4 + i);
+                  acc[4 * i] += f.x; acc[4 * i + 1] += f.y; acc[4 * i + 2] += f.z; acc[4 * i + 3] += f.w;
+                }
+              }
+            }
+            uint32_t raw[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[c * 32 + i] = fmaxf(acc[i], 0.0f);
+              raw[i] = __float_as_uint(v[c * 32 + i]);
+            }
+            tmem_st_32x32(t_res + c * 32, raw);
+          }
+          write_operand(v, P, true, valid);
+          tmem_st_wait();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(aready_bar);
+      }
+      for (int r = 0; r < nl; ++r) {
+        float* P = s_param + ((r + 1) & 1) * (4 * kH);
+        stage_params(r, P);
+        epi_bar_sync();
+        ptx::mbar_wait(tfull_bar, tphase);
+        tphase ^= 1;
+        ptx::tc_fence_after();
+        if (wact) {
+          float v[64];
+          uint32_t racc[2][32], rres[2][32];
+          ptx::tmem_ld_32x32(t_acc, racc[0]);
+          ptx::tmem_ld_32x32(t_res, rres[0]);
+          ptx::tmem_ld_32x32(t_acc + 32, racc[1]);
+          ptx::tmem_ld_32x32(t_res + 32, rres[1]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float pb[32];
+            ld_param32(P + ch0 + c * 32, pb);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(rres[c][i]) + fmaxf(__uint_as_float(racc[c][i]) + pb[i], 0.0f);
+              v[c * 32 + i] = f;
+              rres[c][i] = __float_as_uint(f);
+            }
+            tmem_st_32x32(t_res + c * 32, rres[c]);
+          }
+          write_operand(v, P, r + 1 < nl, valid);
+          tmem_st_wait();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(aready_bar);
+      }
+      {
+        float* P = s_param + ((nl + 1) & 1) * (4 * kH);
+        stage_params(nl, P);
+        epi_bar_sync();
+        ptx::mbar_wait(tfull_bar, tphase);
+        tphase ^= 1;
+        ptx::tc_fence_after();
+        if (wact) {
+          float lg[kVocab];
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) lg[j] = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t racc[32];
+            ptx::tmem_ld_32x32(t_acc + c * 32, racc);
+            ptx::tmem_ld_wait();
+            float pb[32];
+            ld_param32(P + ch0 + c * 32, pb);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float y = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
+#pragma unroll
+              for (int j = 0; j < kVocab; ++j) lg[j] += y * s_w2[j * kH + ch0 + c * 32 + i];
+            }
+          }
+          if (half == 1) {
+            float* x = xch_mine(xpar);
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j) x[j] = lg[j];
+          }
+          pair_sync();
+          if (half == 0 && valid) {
+            const float* x = xch_peer(xpar);
+            float* o = a.logits + ((size_t)seq * L + row) * kVocab;
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j) o[j] = (lg[j] + x[j]) + s_w2[kVocab * kH + j];
+          }
+          xpar ^= 1;
+        }
         ptx::tc_fence_before();
       }
     }

@@ -211,6 +211,8 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
   if (!enabled || L > 256 || h->n_layers > denf::kMaxLayers) return SVDD_ERR_INTERNAL;
   denf::Args a = {};
   a.two_seq = (2 * L <= 128) ? 1 : 0;
+  const char* env_split = getenv("SVDD_DEN_SPLIT");   // 0: one epilogue thread per row also for short sequences
+  a.split = (a.two_seq && !(env_split && atoi(env_split) == 0)) ? 1 : 0;
   int pad_before = 0, max_end = 256;
   for (int i = 0; i < h->n_layers; ++i)
     for (int t = 0; t < kTaps; ++t)
