@@ -357,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
             const uint32_t sb = sa + C::kABytes;
             const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
@@ -378,7 +378,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (lane == 0) ptx::umma_commit(&tfull_bar[acc_stage]);
+      if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[acc_stage]);
       __syncwarp();
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }

@@ -518,7 +518,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           if (first && lane == 0) stamp(3);
-          if (lane == 0) {
+          if (ptx::elect_one()) {      // elect.sync: ptxas keeps the descriptors in uniform registers (no per-UMMA ELECT/R2UR loop)
             const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
             const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
             const uint64_t db = ptx::make_kmajor_sw128_desc(sa + C::kABytes);
@@ -538,7 +538,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int tap = 0; tap < g.taps; ++tap) {
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tc_fence_after();
-              if (lane == 0) {
+              if (ptx::elect_one()) {
                 // tap = row offset: the 128-byte swizzle is a function of the absolute smem address
                 const uint64_t da = ptx::make_kmajor_sw128_desc(sa + (uint32_t)tap * 128u);
                 const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(ringb_base + stage * C::kBBytes));
@@ -561,7 +561,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           for (int kb = 0; kb < kblocks2; ++kb) consume_stage();
         }
-        if (lane == 0) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
+        if (ptx::elect_one()) umma_commit_cg<CG>(&tfull_bar[acc_stage]);
         if (lane == 0 && t == first_tile) stamp(4);
         __syncwarp();
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }

@@ -228,7 +228,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           for (int kb = 0; kb < 2; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
               const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
@@ -249,7 +249,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        if (lane == 0) ptx::umma_commit(tfull_bar);
+        if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
         __syncwarp();
       }
     }

@@ -692,7 +692,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         for (int kb = 0; kb < ph.kblocks; ++kb) {
           twait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
             const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
             const uint64_t db = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
@@ -704,7 +704,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (lane == 0) gemm2::umma_commit_cg<2>(&tfull_bar[acc_stage]);
+        if (ptx::elect_one()) gemm2::umma_commit_cg<2>(&tfull_bar[acc_stage]);
         __syncwarp();
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
