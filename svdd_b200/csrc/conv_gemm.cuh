@@ -313,7 +313,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (uint32_t)(kAcc * g.BL * g.BS * kBK * 2 + C::kBBytes);
       for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {

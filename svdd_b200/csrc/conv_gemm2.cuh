@@ -436,7 +436,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
-    if (lane == 0 && HALO) {
+    if (HALO && ptx::elect_one()) {
       // flat rows: one A box of BL + taps - 1 rows per K block (rows l0 - taps/2 ..; out-of-range
       // rows are zero-filled by TMA, pad rows between sequences are zero in memory), then the
       // weight tile of every tap
@@ -459,7 +459,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
-    } else if (lane == 0) {
+    } else if (!HALO && ptx::elect_one()) {   // elect.sync: TMA operands stay in uniform registers
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (uint32_t)(CG * (g.BL * g.BS * kBK * 2 + C::kBBytes));
       // Few-tile launches (the transformer GEMMs: one tile per CTA pair) stream a weight slice
@@ -834,7 +834,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int half = warp - (2 + EW);
     if constexpr (EW == 16) {
       // one buffer per column quarter, quarters 2*half and 2*half+1 served in turn
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
         const bool load_res = kPair && ep.res != nullptr;
         auto provision = [&](int t, int grp) {
@@ -873,7 +873,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         bulk_wait_all();
       }
     } else
-    if (lane == 0 && n_out > 0) {
+    if (n_out > 0 && ptx::elect_one()) {
       uint8_t* bufs = staging + half * 2 * kSlabBytes;
       uint64_t* my_rin = rin_bar + half * 2;
       uint64_t* my_rout = rout_bar + half * 2;

@@ -183,7 +183,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
   if (warp == 0) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const bool live1 = tile_live(it, 1);

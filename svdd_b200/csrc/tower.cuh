@@ -634,7 +634,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of the pair) =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
       constexpr uint32_t tx_bytes = 2u * (uint32_t)Cfg::kStageBytes;
       for (int id = pair; id < a.total_items; id += n_pairs) {
@@ -920,7 +920,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
     const int half = warp - (2 + EW);
     if constexpr (EW == 16) {
       // one slab per column quarter; this thread serves quarters 2*half and 2*half+1 in turn
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_arrive(&rin_bar[2 * half]);
         ptx::mbar_arrive(&rin_bar[2 * half + 1]);
         uint32_t j = 0;                    // slab jobs done per quarter
@@ -964,7 +964,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
         }
       }
     } else
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint8_t* bufs = staging + half * 2 * kSlabBytes;
       uint64_t* my_rin = rin_bar + half * 2;
       uint64_t* my_rout = rout_bar + half * 2;
