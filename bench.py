@@ -159,7 +159,7 @@ def cpu_port_sample(cfg_model, emb, head, n_seq=2, n_steps=2, threads=None):
   return n_seq / total, desc, threads, t_step
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
   """--impl reference: the reference's CPU implementation of the path.  The reference is
   Python/PyTorch that cannot travel to the GPU box, so this is its port (oracle/)."""
   if rank != 0:
@@ -172,7 +172,7 @@ def run_reference(args, rank, world):
       vals.append(v)
       t_steps.append(t_step)
   value = statistics.mean(vals)
-  print(json.dumps({
+  out.emit(({
       'impl': 'reference', 'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s',
       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': 1000.0 * 8 / value, 'higher_is_better': True, 'scaling': 'weak',
@@ -185,7 +185,23 @@ def run_reference(args, rank, world):
       'ms_per_denoise_step_cpu_sample': 1000.0 * statistics.mean(t_steps)}))
 
 
+class _JsonOnlyStdout:
+  """Everything this process (and the libraries it loads: NCCL prints its version line with a
+  bare printf under NCCL_DEBUG=VERSION) writes to fd 1 goes to stderr; emit() writes the one JSON
+  line to the real stdout."""
+
+  def __init__(self):
+    sys.stdout.flush()
+    self._fd = os.dup(1)
+    os.dup2(2, 1)
+
+  def emit(self, obj):
+    sys.stdout.flush()
+    os.write(self._fd, (json.dumps(obj) + '\n').encode())
+
+
 def main():
+  out = _JsonOnlyStdout()
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=5)
@@ -197,7 +213,7 @@ def main():
   world = int(os.environ.get('WORLD_SIZE', 1))
   local = int(os.environ.get('LOCAL_RANK', 0))
   if args.impl == 'reference':
-    run_reference(args, rank, world)
+    run_reference(args, rank, world, out)
     return
   os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line
   if not torch.cuda.is_available():
@@ -370,7 +386,7 @@ def main():
     cpu = {'value': v, 'unit': 'seq/s', 'cores': cores, 'kind': 'port', 'sample': desc}
 
   if rank == 0:
-    print(json.dumps({
+    out.emit(({
         'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
