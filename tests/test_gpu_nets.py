@@ -74,7 +74,8 @@ def test_denoiser_batch_shapes(cuda):
       assert torch.equal(part, full[:n]), (L, n)
 
 
-@pytest.mark.parametrize('L,n', [(200, 150), (200, 3), (50, 301), (50, 1), (64, 5), (100, 9), (130, 4), (256, 2)])
+@pytest.mark.parametrize('L,n', [(200, 150), (200, 3), (50, 301), (50, 1), (64, 5), (100, 9), (130, 4), (256, 2),
+                                 (24, 7), (33, 601), (32, 2)])
 def test_denoiser_fused_kernel_matches_layer_by_layer(cuda, L, n, monkeypatch):
   """The persistent whole-network kernel (activations in smem / TMEM, taps as descriptor row
   offsets) against the layer-by-layer conv_gemm path: same bf16 rounding points, so the two
@@ -94,6 +95,26 @@ def test_denoiser_fused_kernel_matches_layer_by_layer(cuda, L, n, monkeypatch):
   scale = float(layered.abs().max())
   err = float((fused - layered).abs().max()) / scale
   print(f'\n[denoiser fused vs layered L={L} n={n}] rel.err {err:.3e}')
+  assert err < 6e-3
+
+
+@pytest.mark.parametrize('L,n', [(50, 333), (20, 9), (64, 2)])
+def test_denoiser_split_epilogue_matches_one_thread_per_row(cuda, L, n, monkeypatch):
+  """Short sequences (two per CTA): the split epilogue (two threads per row, LayerNorm statistics
+  combined pairwise) against the one-thread-per-row epilogue (SVDD_DEN_SPLIT=0, read per call).
+  Same bf16 rounding points; the statistics differ only in summation order."""
+  m = helpers.build_denoiser(44, L).to(cuda)
+  x = helpers.random_tokens(n, L, 11, 0.5).to(cuda).to(torch.uint8)
+  den = m.packed()
+  monkeypatch.setenv('SVDD_DEN_SPLIT', '0')
+  one = den.forward(x, 0.0).clone()
+  monkeypatch.setenv('SVDD_DEN_SPLIT', '1')
+  two = den.forward(x, 0.0)
+  again = den.forward(x, 0.0).clone()
+  torch.cuda.synchronize()
+  assert torch.equal(two, again), 'split epilogue is not deterministic'
+  err = float((two - one).abs().max()) / float(one.abs().max())
+  print(f'\n[denoiser split vs single epilogue L={L} n={n}] rel.err {err:.3e}')
   assert err < 6e-3
 
 
