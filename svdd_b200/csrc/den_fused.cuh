@@ -112,13 +112,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 32 floats from SHARED memory (explicit ld.shared: through a generic pointer ptxas emits LD.E
+// plus two R2UR per load for the address-space descriptor)
 __device__ __forceinline__ void ld_param32(const float* p, float* v) {
-  const float4* q = reinterpret_cast<const float4*>(p);
+  const uint32_t a = ptx::smem_u32(p);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 f = q[i];
-    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
-  }
+  for (int i = 0; i < 8; ++i)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                 : "r"(a + 16u * i));
 }
 
 template <typename Tok>
