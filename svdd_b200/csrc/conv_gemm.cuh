@@ -229,10 +229,9 @@ __device__ __forceinline__ void load_row32(const void* base, int dtype, int64_t 
 }
 // 32 consecutive per-column parameters from shared memory (warp-uniform address -> broadcast)
 __device__ __forceinline__ void load_param32(const float* p, float* v) {
-  const float4* q = reinterpret_cast<const float4*>(p);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 f = q[i];
+    const float4 f = ptx::lds128f(p + 4 * i);
     v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
   }
 }

@@ -216,15 +216,14 @@ __device__ __forceinline__ void slab_write(uint8_t* row_base, int x7, bool f32, 
   if (f32) {
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      *reinterpret_cast<float4*>(row_base + ((u ^ x7) << 4)) =
-          make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+      ptx::sts128f(row_base + ((u ^ x7) << 4), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
   } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = chunk_in_slab * 4 + u;
-      *reinterpret_cast<uint4*>(row_base + ((j ^ x7) << 4)) =
+      ptx::sts128(row_base + ((j ^ x7) << 4),
           make_uint4(gemm_detail::pack_bf16x2(v[8 * u], v[8 * u + 1]), gemm_detail::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                     gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+                     gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7])));
     }
   }
 }
@@ -232,14 +231,14 @@ __device__ __forceinline__ void slab_read(const uint8_t* row_base, int x7, bool 
   if (f32) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 f = *reinterpret_cast<const float4*>(row_base + ((u ^ x7) << 4));
+      const float4 f = ptx::lds128f(row_base + ((u ^ x7) << 4));
       v[4 * u] = f.x; v[4 * u + 1] = f.y; v[4 * u + 2] = f.z; v[4 * u + 3] = f.w;
     }
   } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = chunk_in_slab * 4 + u;
-      const uint4 q = *reinterpret_cast<const uint4*>(row_base + ((j ^ x7) << 4));
+      const uint4 q = ptx::lds128(row_base + ((j ^ x7) << 4));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -268,16 +267,16 @@ __device__ __forceinline__ void slab_write16(uint8_t* row_base, int x7, int c, c
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int j = c * 2 + u;
-    *reinterpret_cast<uint4*>(row_base + ((j ^ x7) << 4)) =
+    ptx::sts128(row_base + ((j ^ x7) << 4),
         make_uint4(gemm_detail::pack_bf16x2(v[8 * u], v[8 * u + 1]), gemm_detail::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                   gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+                   gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7])));
   }
 }
 __device__ __forceinline__ void slab_read16(const uint8_t* row_base, int x7, int c, float* v) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int j = c * 2 + u;
-    const uint4 q = *reinterpret_cast<const uint4*>(row_base + ((j ^ x7) << 4));
+    const uint4 q = ptx::lds128(row_base + ((j ^ x7) << 4));
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -287,11 +286,10 @@ __device__ __forceinline__ void slab_read16(const uint8_t* row_base, int x7, int
     }
   }
 }
-__device__ __forceinline__ void load_param16(const float* p, float* v) {
-  const float4* q = reinterpret_cast<const float4*>(p);
+__device__ __forceinline__ void load_param16(const float* p, float* v) {   // p in shared memory
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 f = q[i];
+    const float4 f = ptx::lds128f(p + 4 * i);
     v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
   }
 }

@@ -27,6 +27,31 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- explicit shared-space 16-byte accesses ----------------------------------------------
+// Through a generic pointer ptxas emits LD.E / ST.E (plus R2UR pairs for the address-space
+// descriptor) even when the pointer provably came from the shared window; the epilogues read their
+// per-column parameters and slabs with these instead (LDS.128 / STS.128).
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ float4 lds128f(const void* p) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ void sts128(void* p, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(void* p, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
