@@ -305,9 +305,9 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {       // 16-byte chunk j of the 256-byte row
           uint8_t* base = (j < 8) ? a_row0 : a_row1;
-          *reinterpret_cast<uint4*>(base + (((j & 7) ^ x7) << 4)) =
-              make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                         pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          ptx::sts128(base + (((j & 7) ^ x7) << 4),
+                      make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7])));
         }
       }
     };
@@ -437,11 +437,15 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           ptx::tmem_ld_wait();
           float pb[32];
           ld_param32(P + c * 32, pb);
+          float y[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float y = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
+          for (int i = 0; i < 32; ++i) y[i] = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
 #pragma unroll
-            for (int j = 0; j < kVocab; ++j) lg[j] += y * s_w2[j * kH + c * 32 + i];
+          for (int j = 0; j < kVocab; ++j) {
+            float w[32];
+            ld_param32(s_w2 + j * kH + c * 32, w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lg[j] += y[i] * w[i];
           }
         }
         if (valid) {
@@ -518,9 +522,9 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)          // 16-byte chunk j of this K half's 128-byte row
-          *reinterpret_cast<uint4*>(a_rowh + ((j ^ x7) << 4)) =
-              make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                         pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          ptx::sts128(a_rowh + ((j ^ x7) << 4),
+                      make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7])));
       }
     };
     auto stage_params = [&](int r, float* P) {
@@ -642,11 +646,15 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             ptx::tmem_ld_wait();
             float pb[32];
             ld_param32(P + ch0 + c * 32, pb);
+            float y[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float y = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
 #pragma unroll
-              for (int j = 0; j < kVocab; ++j) lg[j] += y * s_w2[j * kH + ch0 + c * 32 + i];
+            for (int j = 0; j < kVocab; ++j) {
+              float w[32];
+              ld_param32(s_w2 + j * kH + ch0 + c * 32, w);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) lg[j] += y[i] * w[i];
             }
           }
           if (half == 1) {
