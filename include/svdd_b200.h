@@ -92,8 +92,9 @@ int svdd_profile_top(double* ms, double* flops, int64_t* rows, int* K, int* N, i
  * U      [M,B,L,5] fp32 uniforms in [0,1) in the reference's draw order (one
  *        rand_like per candidate, m-major), or NULL to use the in-kernel
  *        Philox4x32-10 stream keyed by (seed, step, global row = row_offset+b);
- * seed_dev optional DEVICE uint64 added to `seed` at run time, so a CUDA graph
- *        that captured this call can be replayed with fresh noise (or NULL);
+ * seed_dev optional DEVICE uint64[2] (or NULL): [0] is added to `seed` and [1] to
+ *        `row_offset` at run time, so a CUDA graph that captured this call can be
+ *        replayed with fresh noise and for another block of global rows;
  * mc_t, mc_s  fp32 move chances 1-exp(-sigma(t)), 1-exp(-sigma(t-dt)) computed
  *        on the host with the reference expression (diffusion_gosai.py:1176-1187);
  * q_out  optional [B,L,5] fp32: the q_xs tensor the reference returns (or NULL).

@@ -7,6 +7,7 @@ built (``make`` / ``__graft_entry__.build()``) or a tensor is not on a CUDA
 device, the call raises.
 """
 import ctypes
+import itertools
 import os
 import threading
 
@@ -300,12 +301,25 @@ def _tensor_table(named):
 
 
 class _Handle:
-  """Owns an opaque svdd_* handle plus a grow-only workspace."""
+  """Owns an opaque svdd_* handle plus a grow-only workspace.
+
+  ``uid`` is unique per handle for the life of the process (cache keys must not use ``id()``,
+  which is recycled).  A captured CUDA graph keeps raw pointers into the workspace and the
+  packed weights: whoever captures must hold ``keepalive()`` for as long as the graph lives
+  (Diffusion._graph_trajectory does)."""
   _net = None
+  _uids = itertools.count(1)
 
   def __init__(self):
     self._h = ctypes.c_void_p()
     self._ws = None
+    self.uid = next(_Handle._uids)
+
+  def keepalive(self):
+    """Objects a captured graph must pin: the handle itself (its packed device weights are freed
+    by __del__) and the CURRENT workspace tensor (replaced, never resized in place, when a later
+    call needs more rows)."""
+    return [self, self._ws]
 
   def _create(self, named, *extra):
     arr, keep = _tensor_table(named)
@@ -349,12 +363,18 @@ class DenoiserHandle(_Handle):
     self._tbias_cache = {}
 
   def time_bias(self, sigma):
+    """Per-layer time-conditioning rows for one sigma (host-side nn.Linear's at pack time, cached).
+    Must not miss inside a CUDA-graph capture (it would run a pageable H2D copy and cuBLAS):
+    Diffusion._graph_trajectory pre-computes every sigma of the schedule first and pins the
+    tensors with the graph."""
     key = float(sigma)
     tb = self._tbias_cache.get(key)
     if tb is None:
+      if torch.cuda.is_current_stream_capturing():
+        raise SvddError('time_bias cache miss during CUDA-graph capture (sigma=%r)' % key)
       tb = self._module.time_bias(key).float().contiguous()
-      if len(self._tbias_cache) > 512:
-        self._tbias_cache.clear()
+      if len(self._tbias_cache) > 4096:
+        self._tbias_cache.clear()       # tensors pinned by captured graphs stay alive through them
       self._tbias_cache[key] = tb
     return tb
 

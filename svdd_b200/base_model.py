@@ -109,6 +109,42 @@ class BaseModel(nn.Module):
     self._val_batch_num = val_batch_num
     self._build_eval_batches = build_eval_batches
 
+  # -- checkpoints ---------------------------------------------------------------------------
+  # Key families of a reference value-function checkpoint (``trainer.py:73-88`` saves
+  # ``BaseModel.state_dict()`` under 'model_state_dict'; decode.py:101-104 loads it strict=True):
+  #   embedding.* / head.*            the value net                        -> same names here
+  #   ref_model.backbone.*            the frozen MDLM denoiser             -> same names here
+  #   ref_model.<anything else>       Lightning metric / EMA state         -> ignored
+  #   reward_model.model.embedding.* / reward_model.model.head.*
+  #                                   gReLU LightningModel wraps its net in ``.model``
+  #                                   (Enformer.py:104-131)                -> reward_model.embedding.* / .head.*
+  #   reward_model.<anything else>    gReLU metrics / transforms           -> ignored
+  @staticmethod
+  def map_reference_keys(state_dict):
+    """Reference-layout BaseModel state_dict -> (this package's layout, ignored keys)."""
+    mapped, ignored = {}, []
+    for k, v in state_dict.items():
+      if k.startswith('reward_model.model.'):
+        mapped['reward_model.' + k[len('reward_model.model.'):]] = v
+      elif k.startswith('reward_model.') and not (k.startswith('reward_model.embedding.') or
+                                                  k.startswith('reward_model.head.')):
+        ignored.append(k)
+      elif k.startswith('ref_model.') and not k.startswith('ref_model.backbone.'):
+        ignored.append(k)
+      else:
+        mapped[k] = v
+    return mapped, ignored
+
+  def load_state_dict(self, state_dict, strict=True, assign=False):
+    """Accepts the reference's own ``model_state_dict`` (key mapping above) as well as this
+    package's.  strict=True keeps the reference's contract for everything that is on the
+    decode path: every parameter of this model must be present and no unknown key may remain;
+    only the documented bookkeeping families are dropped."""
+    mapped, ignored = self.map_reference_keys(state_dict)
+    result = super().load_state_dict(mapped, strict=strict, assign=assign)
+    self.ignored_checkpoint_keys = ignored
+    return result
+
   # -- utilities -----------------------------------------------------------------------------
   def transform_samples(self, samples, num_classes=4):
     return self.ref_model.transform_samples(samples, num_classes)

@@ -216,9 +216,11 @@ subs_sample_kernel(const float* __restrict__ logits, int is_log_p,
       __syncwarp();
     }
   } else {
-    const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
+    // seed_dev (optional, device): [0] is added to the key, [1] to the row offset -- both live in
+    // device memory so that ONE captured CUDA graph serves every (run, batch position)
+    const uint64_t key = seed + (seed_dev != nullptr ? seed_dev[0] : 0ull);
     const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32);
-    const uint32_t row = (uint32_t)(row_offset + pos / L);
+    const uint32_t row = (uint32_t)(row_offset + (seed_dev != nullptr ? (int64_t)seed_dev[1] : 0) + pos / L);
     const uint32_t l = (uint32_t)(pos % L);
     for (int m = 0; m < M; ++m) {
       if (!valid) continue;
@@ -366,9 +368,10 @@ select_gather_kernel(const float* __restrict__ scores, const Tok* __restrict__ c
           if (kInjected) {
             u = __ldg(U_sel + (size_t)b * M + m);
           } else {
-            const uint64_t key = seed + (seed_dev != nullptr ? *seed_dev : 0ull);
+            const uint64_t key = seed + (seed_dev != nullptr ? seed_dev[0] : 0ull);
             const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32);
-            const Philox4 w = philox4x32_10((uint32_t)(m >> 2), (uint32_t)(row_offset + b),
+            const int64_t row0 = row_offset + (seed_dev != nullptr ? (int64_t)seed_dev[1] : 0);
+            const Philox4 w = philox4x32_10((uint32_t)(m >> 2), (uint32_t)(row0 + b),
                                             0u, step | (1u << 24), key0, key1);
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
             u = philox_uniform(words[m & 3]);

@@ -242,12 +242,13 @@ class Diffusion(nn.Module):
     seed = self._seed_for_call() if seed is None else seed
     graphable = self.use_cuda_graph and not collect_mid and noise is None and trace is None
     if graphable:
-      # the run key lives in device memory so that a captured graph replays with fresh noise
+      # the run key AND the global row offset live in device memory (seed_dev[0], seed_dev[1]) so
+      # that one captured graph replays with fresh noise for any block of rows
       if getattr(self, '_seed_dev', None) is None or self._seed_dev.device != dev:
-        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-      skw = dict(seed=0, seed_dev=self._seed_dev)
+        self._seed_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+      skw = dict(seed=0, seed_dev=self._seed_dev, row_offset=0)
     else:
-      skw = dict(seed=seed)
+      skw = dict(seed=seed, row_offset=row_offset)
     u8 = torch.uint8
     buf = dict(
         x=torch.full((B, L), self.mask_index, dtype=u8, device=dev),
@@ -268,12 +269,10 @@ class Diffusion(nn.Module):
       den.forward(x, sigma_t if tc else 0.0, out=buf['logits'])
       U = None if noise is None else noise.draws(i)
       if mode == 'plain':
-        _lib.subs_sample(buf['logits'], x, 1, mc_t, mc_s, U=U, step=i,
-                         row_offset=row_offset, out=x2[None], **skw)
+        _lib.subs_sample(buf['logits'], x, 1, mc_t, mc_s, U=U, step=i, out=x2[None], **skw)
       else:
         cand = buf['cand']
-        _lib.subs_sample(buf['logits'], x, M, mc_t, mc_s, U=U, step=i,
-                         row_offset=row_offset, out=cand, **skw)
+        _lib.subs_sample(buf['logits'], x, M, mc_t, mc_s, U=U, step=i, out=cand, **skw)
         flat = cand.reshape(M * B, L)
         if mode == 'pm' and tweedie:
           den.forward(flat, sigma_s if tc else 0.0, out=buf['logits2'])
@@ -281,7 +280,7 @@ class Diffusion(nn.Module):
         scorer.score(flat, out=buf['scores'].reshape(-1))
         _lib.select_gather(buf['scores'], cand, alpha=alpha,
                            U_sel=None if noise is None else noise.select(i),
-                           step=i, row_offset=row_offset, out=x2, **skw)
+                           step=i, out=x2, **skw)
       if collect_mid and i != num_steps - 1:
         mids.append(x2.clone())
       if trace is not None:
@@ -309,20 +308,31 @@ class Diffusion(nn.Module):
         step(i)
       result = finish()
       return (result, mids) if collect_mid else result
-    return self._graph_trajectory(mode, B, num_steps, eps, M, scorer, tweedie, alpha,
-                                  row_offset, seed, buf, step, finish, x_init)
+    sigmas = ([s[2] for s in sched] + [s[3] for s in sched] + [sigma_last]) if tc else [0.0]
+    return self._graph_trajectory(mode, B, num_steps, eps, M, scorer, tweedie, alpha, row_offset,
+                                  seed, buf, step, finish, x_init, den, sigmas)
+
+  GRAPH_CACHE_ENTRIES = 8
 
   def _graph_trajectory(self, mode, B, num_steps, eps, M, scorer, tweedie, alpha, row_offset,
-                        seed, buf, step, finish, x_init=None):
-    """Captures the whole trajectory once per configuration and replays it.  The
-    per-run Philox key lives in device memory (`seed_dev`), so replays draw fresh
-    noise without re-capturing."""
-    key = (mode, B, num_steps, eps, M, id(scorer), tweedie, alpha, row_offset,
-           id(self.backbone.packed()))
+                        seed, buf, step, finish, x_init, den, sigmas):
+    """Captures the whole trajectory once per configuration and replays it.  The per-run Philox
+    key and the global row offset live in device memory (`seed_dev`), so replays draw fresh
+    noise for any block of rows without re-capturing.
+
+    A captured graph holds raw pointers into the state buffers, the handles' workspaces, their
+    packed weights and the time-bias rows; the cache entry pins all of them (``keep``) and is
+    keyed on the handles' process-unique ``uid`` (never ``id()``), so nothing a graph points
+    at can be freed or recycled while the graph can still be replayed.  A handle that later
+    grows its workspace gets a NEW tensor; the graph keeps using (and owning) the old one."""
+    key = (mode, B, num_steps, eps, M, getattr(scorer, 'uid', None) or id(scorer), tweedie, alpha,
+           den.uid if hasattr(den, 'uid') else id(den), str(self.device))
     entry = self._graphs.get(key)
-    def set_seed():
-      # int64 view of the unsigned 64-bit run key
-      self._seed_dev.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+
+    def set_run():
+      # int64 view of the unsigned 64-bit run key; [1] = global row offset of this block
+      self._seed_dev.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed,
+                                         int(row_offset)], dtype=torch.int64), non_blocking=False)
 
     def reset_state(b):
       if x_init is None:
@@ -331,8 +341,11 @@ class Diffusion(nn.Module):
         b['x'].copy_(x_init.to(b['x'].device).reshape(b['x'].shape))
 
     if entry is None:
-      # One eager pass sizes every workspace / lazy table outside the capture.
-      set_seed()
+      # One eager pass sizes every workspace / lazy table outside the capture, and every
+      # time-conditioning row of the schedule is computed BEFORE it (a miss inside the capture
+      # would issue a pageable copy + library GEMMs on the capturing stream).
+      set_run()
+      tbias = [den.time_bias(s) for s in sigmas] if hasattr(den, 'time_bias') else []
       for i in range(min(num_steps, 2)):
         step(i)
       finish()
@@ -345,31 +358,38 @@ class Diffusion(nn.Module):
           step(i)
         result = finish()
       self.launches_per_trajectory = _lib.launch_count() - before
-      entry = (graph, buf, result)
-      if len(self._graphs) > 8:
-        self._graphs.clear()
+      keep = [scorer, den, tbias, self._seed_dev]
+      for h in (scorer, den):
+        if hasattr(h, 'keepalive'):
+          keep.append(h.keepalive())
+      entry = (graph, buf, result, keep, self.launches_per_trajectory)
+      while len(self._graphs) >= self.GRAPH_CACHE_ENTRIES:       # evict the oldest entry (dict = insertion order)
+        self._graphs.pop(next(iter(self._graphs)))
       self._graphs[key] = entry
-    graph, gbuf, result = entry
-    set_seed()
+    else:
+      self._graphs[key] = self._graphs.pop(key)                  # most recently used last
+    graph, gbuf, result, _, self.launches_per_trajectory = entry
+    set_run()
     reset_state(gbuf)
     graph.replay()
     return result.clone()
 
   # -- reference API: samplers -------------------------------------------------------------------
   @torch.no_grad()
-  def _sample(self, num_steps=None, eps=1e-5, eval_sp_size=None, cdq=False, noise=None):
+  def _sample(self, num_steps=None, eps=1e-5, eval_sp_size=None, cdq=False, noise=None, row_offset=0):
     """diffusion_gosai.py:821-886 (cdq=False): returns (x, mid_x) with the
     num_steps-1 intermediate states."""
     if cdq:
       raise NotImplementedError('cdq rollouts belong to value-function training')
     B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=('ddpm', 'ddpm_cache'))
     if self.sampler == 'ddpm_cache':
-      x, mids = self._sample_ddpm_cache(B, num_steps, eps, noise=noise)
+      x, mids = self._sample_ddpm_cache(B, num_steps, eps, noise=noise, row_offset=row_offset)
     else:
-      x, mids = self._trajectory('plain', B, num_steps, eps, noise=noise, collect_mid=True)
+      x, mids = self._trajectory('plain', B, num_steps, eps, noise=noise, collect_mid=True,
+                                 row_offset=row_offset)
     return x.long(), [m.long() for m in mids]
 
-  def _sample_ddpm_cache(self, B, num_steps, eps, noise=None):
+  def _sample_ddpm_cache(self, B, num_steps, eps, noise=None, row_offset=0):
     """predictor 'ddpm_cache' (diffusion_gosai.py:755-773 and :858-865): the move chances are t
     and t - dt themselves, and the post-SUBS log-probabilities are reused for the next step while
     no token of the batch changed (and time conditioning is off) -- the denoiser forward, i.e.
@@ -399,7 +419,7 @@ class Diffusion(nn.Module):
         log_p = _lib.subs_log_p(logits, x)                       # p_x0 = forward(x).exp() (:765)
         n_fwd += 1
       _lib.subs_sample(log_p, x, 1, mc_t, mc_s, U=None if noise is None else noise.draws(i),
-                       step=i, is_log_p=True, out=x2[None], seed=seed)
+                       step=i, is_log_p=True, out=x2[None], seed=seed, row_offset=row_offset)
       if tc or bool((x2 != x).any()):                            # :861-864
         log_p = None
       x, x2 = x2, x
@@ -419,7 +439,7 @@ class Diffusion(nn.Module):
     """Plain ancestral sampling, the "pre-trained" baseline (diffusion_gosai.py:889-936)."""
     B, num_steps = self._resolve(num_steps, eval_sp_size, predictors=('ddpm', 'ddpm_cache'))
     if self.sampler == 'ddpm_cache':                           # diffusion_gosai.py:912-919
-      return self._sample_ddpm_cache(B, num_steps, eps, noise=noise)[0].long()
+      return self._sample_ddpm_cache(B, num_steps, eps, noise=noise, row_offset=row_offset)[0].long()
     return self._trajectory('plain', B, num_steps, eps, noise=noise, row_offset=row_offset,
                             trace=trace).long()
 

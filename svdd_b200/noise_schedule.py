@@ -36,23 +36,26 @@ def get_noise(config, dtype=torch.float32):
   return LogLinearNoise()
 
 
-def move_chance_schedule(noise, num_steps, eps):
+def move_chance_schedule(noise, num_steps, eps, device='cpu'):
   """[(mc_t, mc_s, sigma_t, sigma_s)] per reverse step as python floats holding
   fp32 values, plus sigma at the last timestep for the noise-removal forward.
 
   Follows diffusion_gosai.py:1036-1043 (timesteps = linspace(1, eps, N+1);
   dt = (1 - eps)/N; t = timesteps[i] * ones(B, 1)) and :1176-1187
-  (sigma = noise(t); mc = 1 - exp(-sigma)) on a [1, 1] CPU tensor -- every
-  sequence of a batch shares the values."""
-  timesteps = torch.linspace(1, eps, num_steps + 1)
+  (sigma = noise(t); mc = 1 - exp(-sigma)) on a [1, 1] tensor -- every sequence of
+  a batch shares the values.  The product evaluates it on the CPU (what the oracle
+  and the goldens pin); ``device`` exists so that tests can evaluate the same
+  expression sequence with the CUDA libm and compare the low bits
+  (tests/test_gpu_sampling.py::test_schedule_host_vs_device)."""
+  timesteps = torch.linspace(1, eps, num_steps + 1, device=device)
   dt = (1 - eps) / num_steps
   rows = []
   for i in range(num_steps):
-    t = timesteps[i] * torch.ones(1, 1)
+    t = timesteps[i] * torch.ones(1, 1, device=device)
     sigma_t = noise(t)[0].squeeze(-1)
     sigma_s = noise(t - dt)[0].squeeze(-1)
     mc_t = 1 - torch.exp(-sigma_t)
     mc_s = 1 - torch.exp(-sigma_s)
     rows.append((mc_t.item(), mc_s.item(), sigma_t.item(), sigma_s.item()))
-  sigma_last = noise(timesteps[-1] * torch.ones(1, 1))[0].item()
+  sigma_last = noise(timesteps[-1] * torch.ones(1, 1, device=device))[0].item()
   return rows, sigma_last

@@ -180,16 +180,21 @@ def ref_convgru_oracle():
   return E.OriBaseModel(emb, head).eval()
 
 
-def ref_enformer_small(calibrate=True):
-  """Small EnformerTrunk whose BatchNorm running statistics are CALIBRATED on a
-  batch (as training would leave them): with the constructor's (0, 1) statistics a
-  random-init trunk is so contractive that its output barely depends on the input
-  and a parity test could not see semantic errors.  The statistics are committed
-  (enformer_small_bn.npz) so the GPU box can rebuild the same net."""
-  kw = helpers.ENFORMER_SMALL_KW
+DATA = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'svdd_b200', 'data')
+
+
+def ref_enformer(full=False, calibrate=True, n_tasks=1):
+  """Reference EnformerTrunk (small: 384 ch / 2 blocks; full: decode.py:78-80's 1536 ch / 11
+  blocks) whose BatchNorm running statistics are CALIBRATED on a batch (as training would leave
+  them): with the constructor's (0, 1) statistics a random-init trunk is so contractive that
+  its output barely depends on the input and a parity test could not see semantic errors.  The
+  statistics are committed (svdd_b200/data/enformer_{small,full}_bn.npz) so that the GPU box,
+  bench.py and the tests rebuild the same net.  calibrate=False reloads the committed ones."""
+  kw = helpers.ENFORMER_FULL_KW if full else helpers.ENFORMER_SMALL_KW
+  name = 'enformer_full_bn.npz' if full else 'enformer_small_bn.npz'
   torch.manual_seed(5)
   emb = E.EnformerTrunk(**kw)
-  head = E.ConvHead(n_tasks=1, in_channels=2 * kw['channels'], act_func=None, pool_func='avg')
+  head = E.ConvHead(n_tasks=n_tasks, in_channels=2 * kw['channels'], act_func=None, pool_func='avg')
   helpers.perturb_(emb, 9)
   if calibrate:
     bns = [m for m in emb.modules() if isinstance(m, torch.nn.BatchNorm1d)]
@@ -206,8 +211,63 @@ def ref_enformer_small(calibrate=True):
       emb(d.transform_samples(cal).float())
     stats = {k: v.clone() for k, v in emb.state_dict().items()
              if k.endswith('running_mean') or k.endswith('running_var')}
-    save('enformer_small_bn.npz', **stats)
+    path = os.path.join(DATA, name)
+    np.savez_compressed(path, **{k: v.numpy() for k, v in stats.items()})
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
+  else:
+    stats = np.load(os.path.join(DATA, name))
+    sd = emb.state_dict()
+    with torch.no_grad():
+      for k in stats.files:
+        sd[k].copy_(torch.from_numpy(stats[k]))
   return emb.eval(), head.eval()
+
+
+def ref_enformer_small(calibrate=True):
+  return ref_enformer(False, calibrate)
+
+
+class ChannelsFirstTrunk(torch.nn.Module):
+  """The DNA reward oracle is gReLU's own EnformerModel (Enformer.py:104-131, oracle.py:72), whose
+  trunk consumes [N, 4, L] -- which is why the path calls reward_model(onehot.transpose(1, 2))
+  (diffusion_gosai.py:1430).  The reference's in-tree EnformerTrunk is the same network with a
+  transpose prepended (Enformer.py:1328), so the stand-in un-transposes in front of it."""
+
+  def __init__(self, trunk):
+    super().__init__()
+    self.trunk = trunk
+
+  def forward(self, x):
+    return self.trunk(x.transpose(1, 2))
+
+
+def ref_dna_reward_model(emb, seed=6):
+  """OriBaseModel(trunk [N,4,L] -> [N,3072,2], ConvHead(n_tasks=3)): output [N, 3, 1]."""
+  torch.manual_seed(seed)
+  head3 = E.ConvHead(n_tasks=3, in_channels=2 * 1536, act_func=None, pool_func='avg').eval()
+  return E.OriBaseModel(ChannelsFirstTrunk(emb), head3).eval()
+
+
+def gen_enformer_full():
+  """The headline network (decode.py:78-80: EnformerTrunk(7, 1536, 11, 8, 64) +
+  ConvHead(1, 3072)) and the DNA reward oracle's 3-task head (oracle.py:72) on SVDD-step-shaped
+  candidate sets: 32 sequences x M = 10 candidates, L = 200 (helpers.svdd_step_candidates)."""
+  d = ref_diffusion(200)
+  S, M, L = 32, 10, 200
+  x, cand = helpers.svdd_step_candidates(S, M, L, seed=2024)
+  emb, head = ref_enformer(full=True, calibrate=True)
+  orc = ref_dna_reward_model(emb)
+  vals, vals3 = [], []
+  with torch.no_grad():
+    for m in range(M):                           # the reference scores candidate by candidate (:1203-1210)
+      oh = d.transform_samples(cand[m]).float()
+      vals.append(head(emb(oh)).squeeze())                   # diffusion_gosai.py:1208-1209
+    for m in range(2):                           # reward oracle: reward_model(x.transpose(1, 2)) -> [N, 3, 1]; [:, 0] is scored (:1430)
+      oh = d.transform_samples(cand[m]).float()
+      vals3.append(orc(oh.transpose(1, 2)).squeeze(-1))
+  save('enformer_full.npz', x=x.to(torch.int8), cand=cand.to(torch.int8), values=torch.stack(vals),
+       values3=torch.stack(vals3), checksum=helpers.state_checksum(emb.state_dict()),
+       head3_checksum=helpers.state_checksum(orc.head.state_dict()))
 
 
 def gen_value_nets():
@@ -264,6 +324,46 @@ def gen_trajectories():
   save('trajectories.npz', **out)
 
 
+def gen_dna_trajectories():
+  """BASELINE configs 2 and 3 in small: the reference's own controlled_sample (SVDD-MC, full
+  Enformer value net) and controlled_sample_tweedie (SVDD-PM, 3-task Enformer reward oracle,
+  task 0 scored) at L = 200, M = 10, plus one controlled step of each kind from a half-unmasked
+  state.  The uniform tensors are INJECTED from a seeded generator (torch.rand_like patched), so
+  only seeds and tokens are stored."""
+  out = {}
+  d = ref_diffusion(200)
+  emb, head = ref_enformer(full=True, calibrate=False)
+  orc = ref_dna_reward_model(emb)
+  L, M = 200, 10
+  for tag, B, steps, seed in (('mc', 3, 4, 901), ('pm', 2, 3, 902)):
+    U = torch.rand(steps, M, B, L, 5, generator=torch.Generator().manual_seed(seed))
+    with RandLikeTap(inject=list(U.reshape(steps * M, B, L, 5))), torch.no_grad():
+      if tag == 'mc':
+        x = d.controlled_sample(emb, head, num_steps=steps, eval_sp_size=B, sample_M=M)
+      else:
+        x = d.controlled_sample_tweedie(orc, num_steps=steps, eval_sp_size=B, sample_M=M,
+                                        options='True', task='dna')
+    out[f'{tag}_tokens'], out[f'{tag}_seed'], out[f'{tag}_shape'] = x, seed, np.int64([steps, M, B, L])
+  # single controlled steps through the reference's step functions (the drop-in surface, A15)
+  timesteps = torch.linspace(1, 1e-5, 129)
+  dt = (1 - 1e-5) / 128
+  B, step = 3, 70
+  x = helpers.random_tokens(B, L, 3070, 0.5)
+  U = torch.rand(M, B, L, 5, generator=torch.Generator().manual_seed(903))
+  t = timesteps[step] * torch.ones(B, 1)
+  with torch.no_grad():
+    with RandLikeTap(inject=list(U)):
+      a, _, qa, ca = d._ddpm_update_finetune_controlled(x, t, dt, emb, head, repeats=M)
+    with RandLikeTap(inject=list(U)):
+      b, _, qb, cb = d._ddpm_update_finetune_controlled_twedie(x, t, dt, orc, repeats=M, options='True', task='dna')
+    with RandLikeTap(inject=list(U)):
+      c, _, _, _ = d._ddpm_update_finetune_controlled_twedie(x, t, dt, orc, repeats=M, options='False', task='dna')
+  assert torch.equal(qa, qb)
+  out.update(step_x=x, step_seed=903, step_index=step, step_mc_next=a, step_pm_next=b, step_pm_raw_next=c,
+             step_q=qa, step_copy_flag=ca)
+  save('dna_trajectories.npz', **out)
+
+
 def gen_ddpm_cache():
   """_sample with predictor 'ddpm_cache' (diffusion_gosai.py:755-773, 858-865): many small steps
   so that most steps leave the batch unchanged and reuse the cached p_x0."""
@@ -288,5 +388,7 @@ if __name__ == '__main__':
   gen_stage_kats()
   gen_denoiser()
   gen_value_nets()
+  gen_enformer_full()
   gen_trajectories()
+  gen_dna_trajectories()
   gen_ddpm_cache()

@@ -161,3 +161,69 @@ def test_trajectories_bit_exact():
     np.testing.assert_array_equal(torch.stack(mid).numpy(), gc['mid'])
     assert n_fwd == int(gc['n_forward']) and n_fwd < 161
   assert int(x.max()) <= 3
+
+
+def test_enformer_full_headline_network_and_dna_reward_oracle():
+  """The network the headline number is measured on (decode.py:78-80) and the 3-task DNA reward
+  oracle: the oracle's functional forward over the product's seeded containers reproduces the
+  reference modules' outputs on SVDD-step-shaped candidate sets (fp32, same torch ops)."""
+  g = helpers.load_golden('enformer_full.npz')
+  emb, head = helpers.build_enformer(full=True)
+  np.testing.assert_array_equal(helpers.state_checksum(emb.state_dict()), g['checksum'])
+  x, cand = helpers.svdd_step_candidates(32, 10, 200, seed=2024)
+  np.testing.assert_array_equal(cand.numpy(), g['cand'])
+  with torch.no_grad():
+    for m in (0, 7):       # the reference scores candidate by candidate, batch = the B sequences
+      v = nets.enformer_value(emb.state_dict(), head.state_dict(), svdd.transform_samples(cand[m]).float())
+      np.testing.assert_allclose(v.reshape(-1).numpy(), g['values'][m], rtol=0, atol=1e-6)
+    from svdd_b200 import synthetic
+    rm = synthetic.build_dna_reward_model()
+    np.testing.assert_array_equal(helpers.state_checksum(rm.head.state_dict()), g['head3_checksum'])
+    v3 = nets.enformer_value(rm.embedding.state_dict(), rm.head.state_dict(),
+                             svdd.transform_samples(cand[1]).float()).squeeze(-1)
+  np.testing.assert_allclose(v3.numpy(), g['values3'][1], rtol=0, atol=1e-6)
+  assert v3.shape == (32, 3) and float((v3[:, 0] - v3[:, 1]).abs().min()) > 0     # the tasks differ
+
+
+def dna_fns():
+  den = helpers.build_denoiser(44, 200)
+  sd = {'backbone.' + k: v for k, v in den.state_dict().items()}
+  emb, head = helpers.build_enformer(full=True)
+  from svdd_b200 import synthetic
+  rm = synthetic.build_dna_reward_model()
+  esd, hsd, h3 = emb.state_dict(), head.state_dict(), rm.head.state_dict()
+  denoiser = lambda x: nets.denoiser_logits(sd, x)
+  value = lambda tok: nets.enformer_value(esd, hsd, svdd.transform_samples(tok).float()).squeeze()
+  # reward_model(onehot.float().transpose(1, 2))[:, 0]  (diffusion_gosai.py:1430): task 0 of 3
+  reward = lambda tok: nets.enformer_value(esd, h3, svdd.transform_samples(tok).float())[:, 0].squeeze()
+  return denoiser, value, reward
+
+
+def dna_noise(g, tag):
+  steps, M, B, L = (int(v) for v in g[f'{tag}_shape'])
+  return torch.rand(steps, M, B, L, 5, generator=torch.Generator().manual_seed(int(g[f'{tag}_seed']))), (steps, M, B, L)
+
+
+def test_dna_trajectories_mc_and_pm():
+  """BASELINE configs 2 / 3 in small (L = 200, M = 10): the reference's controlled_sample with
+  the full Enformer value net and controlled_sample_tweedie with the 3-task reward oracle."""
+  g = helpers.load_golden('dna_trajectories.npz')
+  denoiser, value, reward = dna_fns()
+  with torch.no_grad():
+    U, (steps, M, B, L) = dna_noise(g, 'mc')
+    x = svdd.controlled_sample(denoiser, value, B=B, L=L, M=M, num_steps=steps, noise=svdd.ArrayNoise(U))
+    np.testing.assert_array_equal(x.numpy(), g['mc_tokens'])
+    U, (steps, M, B, L) = dna_noise(g, 'pm')
+    x = svdd.controlled_sample_tweedie(denoiser, reward, B=B, L=L, M=M, num_steps=steps, noise=svdd.ArrayNoise(U))
+    np.testing.assert_array_equal(x.numpy(), g['pm_tokens'])
+    # single steps from a half-unmasked state (the reference's three controlled step functions)
+    sched, _ = svdd.move_chances(128, 1e-5)
+    i = int(g['step_index'])
+    xs = T(g['step_x'])
+    U = torch.rand(10, 3, 200, 5, generator=torch.Generator().manual_seed(int(g['step_seed'])))
+    a = svdd.step_mc(denoiser, value, xs, float(sched[i, 0]), float(sched[i, 1]), U)
+    b = svdd.step_pm(denoiser, reward, xs, float(sched[i, 0]), float(sched[i, 1]), U, tweedie=True)
+    c = svdd.step_pm(denoiser, reward, xs, float(sched[i, 0]), float(sched[i, 1]), U, tweedie=False)
+  np.testing.assert_array_equal(a.numpy(), g['step_mc_next'])
+  np.testing.assert_array_equal(b.numpy(), g['step_pm_next'])
+  np.testing.assert_array_equal(c.numpy(), g['step_pm_raw_next'])
