@@ -655,11 +655,59 @@ int tower_enabled() {          // read per call: the tests A/B the two paths in 
   const char* e = getenv("SVDD_TOWER");
   return e ? atoi(e) : 1;
 }
+// The tower kernel variant for n positions per sequence, configured for its dynamic shared memory.
+struct TowerKernel {
+  void (*kern)(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap,
+               const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, tower::TowerArgs);
+  int smem_bytes, ew, threads;
+};
+TowerKernel tower_select(int n) {
+  using namespace tower;
+  const int bn = tower_bn(), ew = tower_ew();
+  TowerKernel t;
+  t.kern = ew == 16 ? (n == 1 ? tower_kernel<1, 256, 16> : (n == 2 ? tower_kernel<2, 256, 16> : tower_kernel<4, 256, 16>))
+         : bn == 256 ? (n == 1 ? tower_kernel<1, 256> : (n == 2 ? tower_kernel<2, 256> : tower_kernel<4, 256>))
+                     : (n == 1 ? tower_kernel<1, 128> : (n == 2 ? tower_kernel<2, 128> : tower_kernel<4, 128>));
+  t.smem_bytes = bn == 256 ? Cfg<256>::kSmemBytes : Cfg<128>::kSmemBytes;
+  t.ew = ew;
+  t.threads = 64 + 32 * ew + 64;
+  static bool configured[3] = {false, false, false};
+  const int ki = n == 1 ? 0 : (n == 2 ? 1 : 2);
+  if (!configured[ki]) {
+    if (cudaFuncSetAttribute(t.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem_bytes) == cudaSuccess)
+      configured[ki] = true;
+  }
+  return t;
+}
+// How many CTA pairs (clusters of 2) of the tower kernel the device can hold at once.  The kernel's
+// work items wait on each other through global flags, so every launched pair MUST be resident:
+// the grid never exceeds this count, and 0 (no cluster fits: e.g. shared memory carved out by
+// another context) sends the caller to the launch-per-GEMM path instead of a kernel that would
+// spin until its watchdog traps.
+int tower_resident_pairs(int n) {
+  static int cached[3] = {-1, -1, -1};
+  const int ki = n == 1 ? 0 : (n == 2 ? 1 : 2);
+  if (cached[ki] >= 0) return cached[ki];
+  TowerKernel t = tower_select(n);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (num_sms() / 2)));
+  cfg.blockDim = dim3((unsigned)t.threads);
+  cfg.dynamicSmemBytes = (size_t)t.smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, (const void*)t.kern, &cfg) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+  const int by_sm = num_sms() / 2;             // one CTA per SM (227 KB of shared memory each)
+  cached[ki] = clusters < by_sm ? clusters : by_sm;
+  return cached[ki];
+}
 bool tower_usable(const svdd_enformer* h, int n) {
   const int C = h->C, nqkv = 2 * h->H * h->dk + h->H * h->dv;
   return tower_enabled() && h->tower_blocks != nullptr && h->n_blocks > 0 && (n == 1 || n == 2 || n == 4) &&
          C % 128 == 0 && C <= 128 * tower::kLnVecs && nqkv % 64 == 0 && (h->H * h->dv) % 64 == 0 &&
-         h->dk <= 32 * tower::kAttnDkPer && num_sms() >= 2;
+         h->dk <= 32 * tower::kAttnDkPer && num_sms() >= 2 && tower_resident_pairs(n) >= 1;
 }
 int build_tower_params(svdd_enformer* h, int n) {
   if (h->tower_blocks) { cudaFree(h->tower_blocks); h->tower_blocks = nullptr; }
@@ -746,21 +794,15 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   SVDD_TRY(encode_tmap_2d_f32(&tm_qkv, b.qkv, (uint64_t)nqkv, (uint64_t)R, 32, 128));
   SVDD_TRY(encode_tmap_2d_f32(&tm_xt, b.xt, (uint64_t)C, (uint64_t)R, 32, 128));
 
-  const int ew = tower_ew();
-  auto kern = ew == 16 ? (n == 1 ? tower_kernel<1, 256, 16> : (n == 2 ? tower_kernel<2, 256, 16> : tower_kernel<4, 256, 16>))
-            : bn == 256 ? (n == 1 ? tower_kernel<1, 256> : (n == 2 ? tower_kernel<2, 256> : tower_kernel<4, 256>))
-                        : (n == 1 ? tower_kernel<1, 128> : (n == 2 ? tower_kernel<2, 128> : tower_kernel<4, 128>));
-  const int smem_bytes = bn == 256 ? Cfg<256>::kSmemBytes : Cfg<128>::kSmemBytes;
-  static bool configured[3] = {false, false, false};
-  const int ki = n == 1 ? 0 : (n == 2 ? 1 : 2);
-  if (!configured[ki]) {
-    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured[ki] = true;
-  }
+  TowerKernel tk = tower_select(n);
+  auto kern = tk.kern;
+  const int smem_bytes = tk.smem_bytes, ew = tk.ew;
   // every CTA pair must be resident (items wait on each other): at most one pair per TPC
   static int max_pairs = -1;
   if (max_pairs < 0) { const char* e = getenv("SVDD_TOWER_PAIRS"); max_pairs = e ? atoi(e) : 0; }
-  int pairs = num_sms() / 2;
+  // ... and the grid is sized from what the driver says can be co-resident for THIS kernel and
+  // shared-memory configuration (MIG slices, parts with fewer usable TPCs), not from the SM count
+  int pairs = tower_resident_pairs(n);
   if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;
   const int widest = a.ph[5].items_per_rt > a.ph[1].items_per_rt ? a.ph[5].items_per_rt : a.ph[1].items_per_rt;
   const int max_items_per_phase = (widest > kSubItems ? widest : kSubItems) * a.RT;

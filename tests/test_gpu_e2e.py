@@ -321,3 +321,327 @@ def test_base_model_tuple_and_svdd_gain(cuda):
   assert samples[0].shape == (32, 50) and v.shape == r.shape == base.shape == (32,)
   assert top.shape == (32,) and torch.allclose(v, r)
   assert float(r.mean()) > float(base.mean())
+
+
+# ---------------------------------------------------------------------------------------------
+# DNA (L = 200, M = 10): BASELINE configs 2 (SVDD-MC, Enformer value net) and 3 (SVDD-PM, 3-task
+# Enformer reward oracle).  Goldens: tests/golden/dna_trajectories.npz (reference's own code).
+# ---------------------------------------------------------------------------------------------
+
+def _dna_model(cuda):
+  cfg = config.load_config('dna')
+  torch.manual_seed(44)
+  return diffusion_gosai.Diffusion(cfg).to(cuda).eval()
+
+
+def _dna_oracle_fns():
+  from test_oracle_golden import dna_fns
+  return dna_fns()
+
+
+def _dna_noise(g, tag):
+  from test_oracle_golden import dna_noise
+  return dna_noise(g, tag)
+
+
+def test_dna_mc_trajectory_bit_exact_with_reference_logits_values_noise(cuda):
+  """c2-shaped: the reference's controlled_sample with the FULL Enformer value net produced the
+  golden tokens; the oracle trace supplies its per-step logits / values; the CUDA engine lands
+  on the same tokens."""
+  g = helpers.load_golden('dna_trajectories.npz')
+  denoiser, value, _ = _dna_oracle_fns()
+  U, (steps, M, B, L) = _dna_noise(g, 'mc')
+  trace = []
+  with torch.no_grad():
+    x_ref = svdd.controlled_sample(denoiser, value, B=B, L=L, M=M, num_steps=steps,
+                                   noise=svdd.ArrayNoise(U), trace=trace)
+    final_logits = denoiser(trace[-1]['x_next'])
+  assert np.array_equal(x_ref.numpy(), g['mc_tokens'])
+  m = _dna_model(cuda)
+  fake_den = ReplayDenoiser([t['logits'].to(cuda) for t in trace] + [final_logits.to(cuda)])
+  fake_val = ReplayScorer([t['scores'].t().contiguous().to(cuda) for t in trace])
+  m.backbone.packed = lambda: fake_den
+  x = m.controlled_sample(fake_val, None, num_steps=steps, eval_sp_size=B, sample_M=M,
+                          noise=diffusion_gosai.InjectedNoise(U.to(cuda)))
+  np.testing.assert_array_equal(x.cpu().numpy(), g['mc_tokens'])
+
+
+def test_dna_pm_trajectory_bit_exact_with_reference_logits_values_noise(cuda):
+  """c3-shaped: controlled_sample_tweedie with the 3-task reward oracle (task 0 scored)."""
+  g = helpers.load_golden('dna_trajectories.npz')
+  denoiser, _, reward = _dna_oracle_fns()
+  U, (steps, M, B, L) = _dna_noise(g, 'pm')
+  trace = []
+  with torch.no_grad():
+    x_ref = svdd.controlled_sample_tweedie(denoiser, reward, B=B, L=L, M=M, num_steps=steps,
+                                           noise=svdd.ArrayNoise(U), trace=trace)
+    assert np.array_equal(x_ref.numpy(), g['pm_tokens'])
+    den_seq = []
+    for t in trace:
+      den_seq.append(t['logits'].to(cuda))
+      den_seq.append(torch.cat([denoiser(t['cand'][k]) for k in range(M)], 0).to(cuda))
+    den_seq.append(denoiser(trace[-1]['x_next']).to(cuda))
+  m = _dna_model(cuda)
+  fake_den = ReplayDenoiser(den_seq)
+  fake_rew = ReplayScorer([t['scores'].t().contiguous().to(cuda) for t in trace])
+  m.backbone.packed = lambda: fake_den
+  x = m.controlled_sample_tweedie(fake_rew, num_steps=steps, eval_sp_size=B, sample_M=M, options='True',
+                                  task='dna', noise=diffusion_gosai.InjectedNoise(U.to(cuda)))
+  np.testing.assert_array_equal(x.cpu().numpy(), g['pm_tokens'])
+
+
+@pytest.mark.parametrize('mode', ['mc', 'pm'])
+def test_dna_real_networks_every_transition_matches_oracle(cuda, mode):
+  """c2 / c3 shaped trace (B = 8, M = 10, L = 200, 4 steps, injected noise) with the tensor-core
+  networks in the loop -- the fused denoiser and the FULL Enformer value net (mc) / 3-task
+  Enformer reward oracle (pm): every transition is the oracle's given the kernels' own logits /
+  values; x0 equals the oracle's Tweedie argmax; the scores are task 0's and sit within the
+  stated tolerance of the fp32 oracle."""
+  from svdd_b200 import synthetic
+  m = _dna_model(cuda)
+  B, M, L, steps = 8, 10, 200, 4
+  U = torch.rand(steps, M, B, L, 5, generator=torch.Generator().manual_seed(15))
+  noise = diffusion_gosai.InjectedNoise(U.to(cuda))
+  trace = []
+  if mode == 'mc':
+    emb, head = helpers.build_enformer(full=True)
+    x = m.controlled_sample(emb.to(cuda), head.to(cuda), num_steps=steps, eval_sp_size=B,
+                            sample_M=M, noise=noise, trace=trace)
+  else:
+    rm = synthetic.build_dna_reward_model().to(cuda)
+    x = m.controlled_sample_tweedie(rm, num_steps=steps, eval_sp_size=B, sample_M=M, noise=noise,
+                                    options='True', task='dna', trace=trace)
+  assert x.shape == (B, L) and int(x.max()) <= 3
+  denoiser, value, reward = _dna_oracle_fns()
+  for rec in trace[:-1]:
+    xs, lg = rec['x'].cpu().long(), rec['logits'].cpu()
+    q = svdd.build_q_xs(svdd.subs_parameterization(lg, xs), rec['mc_t'], rec['mc_s'])
+    cand = svdd.draw_candidates(xs, q, U[rec['step']])
+    assert torch.equal(cand, rec['cand'].cpu().long())
+    if mode == 'pm':
+      x0 = svdd.subs_parameterization(rec['logits2'].cpu(), cand.reshape(M * B, L)).argmax(-1)
+      assert torch.equal(x0, rec['x0'].cpu().long())
+    idx = svdd.select(rec['scores'].cpu().t().contiguous())
+    assert torch.equal(svdd.gather_selected(cand, idx), rec['x_next'].cpu().long())
+    with torch.no_grad():
+      ref = denoiser(xs)
+    assert float((lg - ref).abs().max() / ref.abs().max()) < 3e-2
+  last = trace[-1]
+  assert torch.equal(svdd.subs_parameterization(last['logits'].cpu(), last['x'].cpu().long())[:, :, :4].argmax(-1), x.cpu())
+  rec = trace[2]
+  toks = (rec['x0'] if mode == 'pm' else rec['cand']).cpu().long().reshape(M * B, L)
+  with torch.no_grad():
+    ref = (value if mode == 'mc' else reward)(toks).reshape(M, B)
+  err = float((rec['scores'].cpu() - ref).abs().max())
+  agree = float((rec['scores'].cpu().argmax(0) == ref.argmax(0)).float().mean())
+  print(f'\n[dna {mode}] step-2 scores: max|d| vs fp32 oracle {err:.3e}, argmax agreement {agree:.2f}')
+  assert err < 3.5e-2
+
+
+def test_controlled_step_functions_match_reference_known_answers(cuda):
+  """A15: _ddpm_update_finetune_controlled / _controlled_twedie -- the reference's step
+  functions, part of the drop-in surface -- return the reference's (final_samples, x, q_xs,
+  copy_flag) on the golden stage cases a-d (tests/golden/stage_kats.npz: injected logits, noise
+  and scores through the reference's own function)."""
+  g = helpers.load_golden('stage_kats.npz')
+  timesteps = torch.linspace(1, 1e-5, 129)
+  dt = (1 - 1e-5) / 128
+  for tag in 'abcd':
+    c = {k[2:]: g[k] for k in g.files if k.startswith(tag + '_')}
+    x, logits, U, scores = T(c['x']), T(c['logits']), T(c['U']), T(c['scores'])
+    B, L = x.shape
+    M = U.shape[0]
+    cfg = config.load_config('rna')
+    cfg.model.length = L
+    model = diffusion_gosai.Diffusion(cfg).to(cuda).eval()
+    t = (timesteps[int(c['step'])] * torch.ones(B, 1)).to(cuda)
+    fake = ReplayDenoiser([logits.to(cuda)])
+    model.backbone.packed = lambda: fake
+    scorer = ReplayScorer([scores.t().contiguous().to(cuda)])
+    final, x_in, q, copy_flag = model._ddpm_update_finetune_controlled(
+        x.to(cuda), t, dt, scorer, None, repeats=M, U=U.to(cuda))
+    np.testing.assert_array_equal(final.cpu().numpy(), c['x_next'], err_msg=tag)
+    np.testing.assert_array_equal(x_in.cpu().numpy(), c['x'], err_msg=tag)
+    np.testing.assert_allclose(q.cpu().numpy(), c['q'], rtol=2e-6, atol=0, err_msg=tag)
+    np.testing.assert_array_equal(copy_flag.cpu().numpy(), (c['x'] != 4).astype(np.int64), err_msg=tag)
+    assert final.dtype == torch.int64 and copy_flag.dtype == torch.int64
+    # the Tweedie variant with options='False' scores the raw candidates: same golden answer
+    fake.i, scorer.i = 0, 0
+    rm = value_nets.OriBaseModel(scorer, None)
+    final2, _, q2, _ = model._ddpm_update_finetune_controlled_twedie(
+        x.to(cuda), t, dt, rm, repeats=M, options='False', task='rna', U=U.to(cuda))
+    np.testing.assert_array_equal(final2.cpu().numpy(), c['x_next'], err_msg=tag)
+    assert torch.equal(q2, q)
+
+
+def test_controlled_step_functions_dna_golden(cuda):
+  """The same three step functions at L = 200 with the reference's REAL networks behind the
+  golden (full Enformer value net / 3-task reward oracle, options 'True' and 'False'): replaying
+  the oracle's logits and scores through the CUDA step functions reproduces the reference's
+  next state."""
+  g = helpers.load_golden('dna_trajectories.npz')
+  denoiser, value, reward = _dna_oracle_fns()
+  sched, _ = svdd.move_chances(128, 1e-5)
+  i = int(g['step_index'])
+  xs = T(g['step_x'])
+  B, L, M = 3, 200, 10
+  U = torch.rand(M, B, L, 5, generator=torch.Generator().manual_seed(int(g['step_seed'])))
+  t = (torch.linspace(1, 1e-5, 129)[i] * torch.ones(B, 1)).to(cuda)
+  dt = (1 - 1e-5) / 128
+  m = _dna_model(cuda)
+  with torch.no_grad():
+    lg = denoiser(xs)
+    cand = svdd.draw_candidates(xs, svdd.build_q_xs(svdd.subs_parameterization(lg, xs), float(sched[i, 0]),
+                                                    float(sched[i, 1])), U)
+    lg2 = torch.cat([denoiser(cand[k]) for k in range(M)], 0)
+    x0 = torch.stack([svdd.tweedie_onehot(denoiser, cand[k]) for k in range(M)])
+    s_mc = torch.stack([value(cand[k]) for k in range(M)])
+    s_pm = torch.stack([reward(x0[k]) for k in range(M)])
+    s_raw = torch.stack([reward(cand[k]) for k in range(M)])
+  for fn, den_seq, sc, key in (('mc', [lg], s_mc, 'step_mc_next'), ('True', [lg, lg2], s_pm, 'step_pm_next'),
+                               ('False', [lg], s_raw, 'step_pm_raw_next')):
+    fake = ReplayDenoiser([d.to(cuda) for d in den_seq])
+    m.backbone.packed = lambda fake=fake: fake
+    scorer = ReplayScorer([sc.to(cuda)])
+    if fn == 'mc':
+      out = m._ddpm_update_finetune_controlled(xs.to(cuda), t, dt, scorer, None, repeats=M, U=U.to(cuda))
+    else:
+      out = m._ddpm_update_finetune_controlled_twedie(xs.to(cuda), t, dt, value_nets.OriBaseModel(scorer, None),
+                                                      repeats=M, options=fn, task='dna', U=U.to(cuda))
+    np.testing.assert_array_equal(out[0].cpu().numpy(), g[key], err_msg=fn)
+    np.testing.assert_allclose(out[2].cpu().numpy(), g['step_q'], rtol=2e-6, atol=0)
+    np.testing.assert_array_equal(out[3].cpu().numpy(), g['step_copy_flag'])
+
+
+@pytest.mark.parametrize('mode,alpha', [('mc', 0.0), ('mc', 0.1), ('pm', 0.0), ('pm', 0.1), ('plain', 0.0)])
+@pytest.mark.parametrize('graph', [False, True])
+def test_shard_equivalence_on_one_gpu(cuda, mode, alpha, graph):
+  """results do not depend on how the batch is sharded.  concat(run(rows 0..3),
+  run(rows 4..7, row_offset = 4)) == run(rows 0..7) for SVDD-MC, SVDD-PM (incl. alpha > 0, whose
+  selection noise is keyed by the global row too) and plain sampling, with the in-kernel Philox
+  stream, eager and through the CUDA graph (row offset in device memory: ONE captured graph
+  serves both halves)."""
+  m = _rna_model(cuda)
+  m.use_cuda_graph = graph
+  emb, head = helpers.build_convgru_value()
+  emb, head = emb.to(cuda), head.to(cuda)
+  oe, oh = helpers.build_convgru_oracle()
+  rm = value_nets.OriBaseModel(oe.to(cuda), oh.to(cuda))
+  steps, M = 6, 4
+
+  def run(rows, off):
+    m.manual_seed(77)                          # the same run key for every shard
+    if mode == 'mc':
+      return m.controlled_sample(emb, head, num_steps=steps, eval_sp_size=rows, sample_M=M, alpha=alpha,
+                                 row_offset=off)
+    if mode == 'pm':
+      return m.controlled_sample_tweedie(rm, num_steps=steps, eval_sp_size=rows, sample_M=M, alpha=alpha,
+                                         options='True', task='rna', row_offset=off)
+    return m.decode_sample(num_steps=steps, eval_sp_size=rows, row_offset=off)
+
+  whole = run(8, 0)
+  captured = len(m._graphs)
+  halves = torch.cat([run(4, 0), run(4, 4)], 0)
+  assert torch.equal(whole, halves)
+  uneven = torch.cat([run(3, 0), run(5, 3)], 0)
+  assert torch.equal(whole, uneven)
+  assert not torch.equal(run(4, 0), run(4, 4))
+  if graph:
+    assert len(m._graphs) == captured + 3, 'one graph per batch shape, none per row offset'
+
+
+def test_graph_cache_survives_workspace_growth_and_handle_rebuild(cuda):
+  """a cached graph points into the handles' workspaces and packed weights.  Growing
+  a workspace (a larger scoring call between two decodes) or re-packing the value net must not
+  invalidate a graph that is replayed afterwards."""
+  m = _rna_model(cuda)
+  emb, head = helpers.build_convgru_value()
+  emb, head = emb.to(cuda), head.to(cuda)
+  m.manual_seed(5)
+  a = m.controlled_sample(emb, head, num_steps=6, eval_sp_size=8, sample_M=4)
+  scorer = value_nets.packed_scorer(emb, head)
+  ws_before = scorer._ws
+  big = helpers.random_tokens(40000, 50, 1, 0.5).to(cuda)
+  value_nets.score_tokens(emb, head, big)                       # grows the scorer's workspace
+  m.backbone.packed().forward(big[:20000], 0.0)                 # and the denoiser's
+  assert scorer._ws is not ws_before
+  junk = [torch.full((1 << 20,), 7, dtype=torch.uint8, device=cuda) for _ in range(64)]   # reuse freed blocks
+  m.manual_seed(5)
+  b = m.controlled_sample(emb, head, num_steps=6, eval_sp_size=8, sample_M=4)   # replay of the cached graph
+  assert torch.equal(a, b)
+  del junk
+  # re-packing (weights changed) makes a new handle with a new uid -> a new graph, the old one stays valid
+  with torch.no_grad():
+    head.channel_transform.conv.layer.bias.add_(1.0)
+  m.manual_seed(5)
+  c = m.controlled_sample(emb, head, num_steps=6, eval_sp_size=8, sample_M=4)
+  assert value_nets.packed_scorer(emb, head).uid != scorer.uid and len(m._graphs) == 2
+  assert torch.equal(a, c)                                      # a constant shift does not change the argmax
+
+
+def test_time_conditioning_graph_capture(cuda):
+  """with time_conditioning=True every step has its own sigma; the time-bias rows
+  are computed before the capture (a miss inside it raises) and pinned with the graph."""
+  cfg = config.load_config('rna')
+  cfg.time_conditioning = True
+  torch.manual_seed(44)
+  m = diffusion_gosai.Diffusion(cfg).to(cuda).eval()
+  emb, head = helpers.build_convgru_value()
+  emb, head = emb.to(cuda), head.to(cuda)
+  m.manual_seed(3)
+  m.use_cuda_graph = False
+  a = m.controlled_sample(emb, head, num_steps=9, eval_sp_size=5, sample_M=3)
+  m.manual_seed(3)
+  m.use_cuda_graph = True
+  b = m.controlled_sample(emb, head, num_steps=9, eval_sp_size=5, sample_M=3)
+  m.manual_seed(3)
+  c = m.controlled_sample(emb, head, num_steps=9, eval_sp_size=5, sample_M=3)
+  assert torch.equal(a, b) and torch.equal(a, c)
+  cfg.time_conditioning = False
+
+
+def test_build_eval_batches_and_baseline_rows_differ_across_shards(cuda):
+  """F2: BaseModel.build_eval_batches (Enformer.py:135-160): per-timestep intermediate states
+  and their final rewards.  And ADVICE r1: ddpm_cache rollouts honour row_offset, so two shards
+  do not draw the same rows."""
+  from svdd_b200.base_model import BaseModel
+  torch.manual_seed(44)
+  m = BaseModel(None, None, cdq=False, batch_size=6, val_batch_num=2, task='rna', random_init=True).to(cuda).eval()
+  m.ref_model.config.sampling.steps = 8
+  m.build_eval_batches()
+  assert len(m.eval_time_step_batches) == 8 and len(m.eval_time_step_targets) == 8
+  assert all(b.shape == (12, 50) for b in m.eval_time_step_batches)
+  assert all(t.shape == (12,) and torch.equal(t, m.eval_time_step_targets[0]) for t in m.eval_time_step_targets)
+  masked = [int((b == 4).sum()) for b in m.eval_time_step_batches]
+  assert masked == sorted(masked, reverse=True) and masked[-1] == 0       # states get less masked; last one is clean
+  m.ref_model.config.sampling.steps = 128
+  d = m.ref_model
+  d.sampler = 'ddpm_cache'
+  d.manual_seed(9)
+  a = d.decode_sample(num_steps=16, eval_sp_size=4, row_offset=0)
+  d.manual_seed(9)
+  b = d.decode_sample(num_steps=16, eval_sp_size=4, row_offset=4)
+  d.manual_seed(9)
+  w = d.decode_sample(num_steps=16, eval_sp_size=8, row_offset=0)
+  assert not torch.equal(a, b)
+  d.sampler = 'ddpm'
+
+
+def test_cli_loads_reference_layout_value_checkpoint(cuda, tmp_path):
+  """decode.py --load_checkpoint_path with a value-function .pt in the REFERENCE's key layout
+  (reward_model.model.*, Lightning metric buffers; decode.py:101-104 strict=True)."""
+  import subprocess, sys
+  from svdd_b200.base_model import BaseModel
+  torch.manual_seed(3)
+  src = BaseModel(None, None, cdq=False, batch_size=8, val_batch_num=1, task='rna', random_init=True)
+  sd = {}
+  for k, v in src.state_dict().items():
+    sd[('reward_model.model.' + k[len('reward_model.'):]) if k.startswith('reward_model.') else k] = v
+  sd['reward_model.val_metrics.mse.total'] = torch.zeros(1)
+  path = tmp_path / 'value.pt'
+  torch.save({'epoch': 1, 'model_state_dict': sd}, path)
+  cmd = [sys.executable, 'decode.py', '--task', 'rna', '--sample_M', '3', '--batch_size', '8', '--val_batch_num', '1',
+         '--reward_name', 'MRL', '--random_init', '--out_dir', str(tmp_path), '--load_checkpoint_path', str(path)]
+  r = subprocess.run(cmd, cwd=helpers.ROOT, capture_output=True, text=True, timeout=600)
+  assert r.returncode == 0, r.stdout + r.stderr
+  assert np.load(tmp_path / 'rna-MRL.npz')['decoding'].shape == (8,)

@@ -197,6 +197,98 @@ def test_enformer_value(cuda):
   assert torch.equal(got8, got)
 
 
+# Full headline network (decode.py:78-80): stated tolerances.  Scores of this seeded net are
+# O(0.1-0.5); the bf16-operand pipeline (7 conv stages + 11 transformer blocks = ~50 GEMMs deep)
+# lands within EF_TIGHT of the oracle's bf16-operand emulation and EF_LOOSE of the fp32 reference,
+# both ABSOLUTE on the score (and as a fraction of the batch's score standard deviation).
+EF_TIGHT, EF_LOOSE, EF_MEAN = 2.5e-2, 3.5e-2, 8e-3
+
+
+def test_enformer_full_headline_network_parity(cuda):
+  """A10 on the network the headline number is measured on: EnformerTrunk(7, 1536, 11, 8, 64) +
+  ConvHead(1, 3072) (decode.py:78-80), calibrated BatchNorm, perturbed to_out; 32 sequences x
+  M = 10 SVDD-step-shaped candidates at L = 200, against (1) the reference's own fp32 outputs
+  (tests/golden/enformer_full.npz) and (2) the oracle's bf16-operand emulation.  What selection
+  consumes is the per-sequence argmax over the M candidates (diffusion_gosai.py:1219-1227):
+  agreement with the fp32 reference and the regret of disagreements are reported and bounded."""
+  g = helpers.load_golden('enformer_full.npz')
+  S, M, L = 32, 10, 200
+  x, cand = helpers.svdd_step_candidates(S, M, L, seed=2024)
+  assert np.array_equal(cand.numpy(), g['cand'])
+  ref = T(g['values'])                                        # [M, S] fp32, reference modules
+  emb, head = helpers.build_enformer(full=True)
+  np.testing.assert_array_equal(helpers.state_checksum(emb.state_dict()), g['checksum'])
+  with torch.no_grad():
+    emu = nets.enformer_value(emb.state_dict(), head.state_dict(),
+                              svdd.transform_samples(cand.reshape(M * S, L)).float(), n_heads=8,
+                              emulate_bf16=True).reshape(M, S)
+  emb, head = emb.to(cuda), head.to(cuda)
+  got = value_nets.score_tokens(emb, head, cand.reshape(M * S, L).to(cuda)).cpu().reshape(M, S)
+  sd = float(ref.std())
+  e_emu, e_ref = float((got - emu).abs().max()), float((got - ref).abs().max())
+  m_ref = float((got - ref).abs().mean())
+  print(f'\n[enformer FULL 1536ch/11 blocks, {M * S} candidates] score mean {float(ref.mean()):.4f} std {sd:.4f} '
+        f'range {float(ref.max() - ref.min()):.4f}\n  max|d| vs bf16-emulating oracle {e_emu:.3e} ({e_emu / sd:.1%} of std), '
+        f'vs fp32 reference {e_ref:.3e} ({e_ref / sd:.1%} of std), mean|d| vs fp32 {m_ref:.3e}; '
+        f'(emulation vs fp32: {float((emu - ref).abs().max()):.3e})')
+  assert e_emu <= EF_TIGHT and e_ref <= EF_LOOSE and m_ref <= EF_MEAN
+  # correlation of the candidate ORDER with the reference over all candidates
+  rank_corr = float(torch.corrcoef(torch.stack([got.reshape(-1), ref.reshape(-1)]))[0, 1])
+  assert rank_corr >= 0.995, rank_corr
+  # selection: argmax over each sequence's M candidates
+  spread = ref.max(0).values - ref.min(0).values
+  pick, pick_ref, pick_emu = got.argmax(0), ref.argmax(0), emu.argmax(0)
+  regret = ref.max(0).values - ref.gather(0, pick[None])[0]
+  agree = float((pick == pick_ref).float().mean())
+  print(f'  argmax over M=10: agreement with fp32 reference {agree:.3f} (the CPU bf16 emulation: '
+        f'{float((pick_emu == pick_ref).float().mean()):.3f}); regret of disagreements max {float(regret.max()):.3e} '
+        f'mean {float(regret.mean()):.3e}; mean spread over M {float(spread.mean()):.3e}')
+  assert agree >= 0.85 and float(regret.max()) <= 0.25 * float(spread.mean())
+  assert float(regret.mean()) <= 0.03 * float(spread.mean())
+  # uint8 tokens take the same path
+  got8 = value_nets.score_tokens(emb, head, cand.reshape(M * S, L).to(cuda).to(torch.uint8)).cpu().reshape(M, S)
+  assert torch.equal(got8, got)
+
+
+def test_enformer_identical_candidates_score_identically(cuda):
+  """Late in a trajectory most of a sequence's M candidates are IDENTICAL token rows; the
+  reference then sees exact ties and argmax takes the first (diffusion_gosai.py:1224).  The
+  one-call scoring of all M*B rows must give bit-identical scores to identical rows wherever
+  they sit in the batch, or the tie-break would depend on tile placement."""
+  emb, head = helpers.build_enformer(full=True)
+  emb, head = emb.to(cuda), head.to(cuda)
+  base = helpers.random_tokens(37, 200, 91, 0.1)
+  rows = torch.cat([base, base[:5], base.flip(0), base[3:4].expand(9, -1)], 0)          # 88 rows, duplicates far apart
+  got = value_nets.score_tokens(emb, head, rows.to(cuda)).cpu()
+  assert torch.equal(got[:37], got[42:79].flip(0)) and torch.equal(got[:5], got[37:42])
+  assert bool((got[79:] == got[3]).all())
+  S, M = 16, 10
+  x, cand = helpers.svdd_step_candidates(S, M, 200, seed=7, p_masks=(0.03,))
+  sc = value_nets.score_tokens(emb, head, cand.reshape(M * S, 200).to(cuda)).cpu().reshape(M, S)
+  same = (cand == cand[:1]).all(-1)                                                   # [M, S]: identical to candidate 0
+  assert int(same.sum()) > S                                                          # the case occurs
+  assert torch.equal(sc[same], sc[:1].expand(M, S)[same])
+
+
+def test_dna_reward_oracle_scores_task_0_of_3(cuda):
+  """A12: the DNA reward oracle has 3 tasks (oracle.py:72) and the path scores
+  ``reward_model(onehot.transpose(1, 2))[:, 0]`` (diffusion_gosai.py:1430).  ConvHead(n_tasks=3)
+  through the CUDA scorer == task 0 of the reference's [N, 3] output, within the value-net
+  tolerance, and NOT tasks 1 / 2."""
+  from svdd_b200 import synthetic
+  g = helpers.load_golden('enformer_full.npz')
+  _, cand = helpers.svdd_step_candidates(32, 10, 200, seed=2024)
+  rm = synthetic.build_dna_reward_model()
+  np.testing.assert_array_equal(helpers.state_checksum(rm.head.state_dict()), g['head3_checksum'])
+  rm = rm.to(cuda)
+  tok = cand[:2].reshape(64, 200).to(cuda)
+  got = value_nets.score_tokens(rm.embedding, rm.head, tok).cpu().reshape(2, 32)
+  ref3 = T(g['values3'])                                                               # [2, 32, 3]
+  e = [float((got - ref3[..., t]).abs().max()) for t in range(3)]
+  print(f'\n[dna reward oracle] max|d| vs task 0 / 1 / 2 of the reference: {e[0]:.3e} / {e[1]:.3e} / {e[2]:.3e}')
+  assert e[0] <= EF_LOOSE and min(e[1], e[2]) > 3 * EF_LOOSE
+
+
 def test_enformer_batch_independence(cuda):
   emb, head = helpers.build_enformer()
   emb, head = emb.to(cuda), head.to(cuda)

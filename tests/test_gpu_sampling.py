@@ -200,3 +200,26 @@ def test_stage4_properties(cuda, M):
 def test_no_cpu_fallback():
   with pytest.raises(_lib.SvddError):
     _lib.subs_sample(torch.zeros(1, 2, 5), torch.zeros(1, 2, dtype=torch.int64), 1, 0.5, 0.4)
+
+
+def test_schedule_host_vs_device(cuda):
+  """the product evaluates the move-chance schedule with CPU libm (what the oracle and
+  the reference-generated goldens pin), the reference decode path evaluates the same expression
+  sequence with CUDA libm (diffusion_gosai.py:1036-1043, 1176-1187).  Measured here for every
+  schedule length the tests and BASELINE configs use: the two agree to within 1 ulp of the move
+  chances; a difference can only matter for a Gumbel draw whose two best keys are within that
+  ulp (oracle.svdd.draw_margin identifies such draws; none occur in the fixtures)."""
+  from svdd_b200 import noise_schedule
+  noise = noise_schedule.LogLinearNoise()
+  worst, differing, total = 0.0, 0, 0
+  for steps in (3, 4, 6, 8, 12, 16, 128, 160):
+    host, s_host = noise_schedule.move_chance_schedule(noise, steps, 1e-5)
+    dev, s_dev = noise_schedule.move_chance_schedule(noise.to(cuda), steps, 1e-5, device=cuda)
+    h = np.float32([r[:2] for r in host])
+    d = np.float32([r[:2] for r in dev])
+    ulp = np.abs(h.view(np.int32).astype(np.int64) - d.view(np.int32).astype(np.int64))
+    worst = max(worst, float(ulp.max()))
+    differing += int((ulp > 0).sum())
+    total += ulp.size
+  print(f'\n[schedule] host vs device move chances: {differing} of {total} values differ, worst {worst:.0f} ulp')
+  assert worst <= 1
