@@ -23,12 +23,19 @@ Enformer-style value net, synthetic (all-mask prior + counter-based noise).
             nominal dense FLOPs / summed CUDA-event launch time of one instrumented
             value-net + denoiser pass, against the MEASURED sustained bf16 peak.
   cpu_baseline  the CPU oracle (a port of the reference's algorithm, oracle/) timed on
-            this box's host cores on a bounded sample; reported, not a target.
+            this box's host cores on a bounded sample -- ONE real reverse step of the workload
+            at the full batch (B = 128, M = 10: the step cost does not depend on the step
+            index), extrapolated over the 128 steps only; reported, not a target.
+  other_configs  the other BASELINE.json configs, N-aware: c3 (DNA SVDD-PM, B = 128 per GPU),
+            c4 (DNA SVDD-MC, batch 4096 / N per rank, M = 20: strong scaling) and c5 (RNA SVDD-PM,
+            batch 8192 / N per rank, M = 50, alpha 0 and 0.1), a few reverse steps each, with
+            their own tensor roofline fraction.
 
 --impl reference times that CPU port alone (the reference itself is Python that cannot
-travel to the GPU box).
+travel to the GPU box): every bench step is one real reverse step at B = 128.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -40,16 +47,32 @@ import time
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, 'tests')):
-  if p not in sys.path:
-    sys.path.insert(0, p)
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
 
 WORKLOAD = ('c2: DNA enhancer HepG2 SVDD-MC (decode.py --task dna --sample_M 10), L=200, M=10, '
             'batch 128 per GPU, 128 denoise steps + noise removal, random-init CNN denoiser + '
             'Enformer-style value net (7 conv / 1536 ch / 11 transformer blocks)')
 B_PER_GPU, M, L, NUM_STEPS = 128, 10, 200, 128
 F_DEN = 2 * L * (5 * 128 * 9 + 20 * 128 * 128 * 9 + 128 * 128 + 128 * 5)
-F_VAL = 3.362e9
+F_VAL = 3.362e9                      # Enformer value / oracle net, per candidate
+TRAFFIC_FILE = 'r02_traffic.json'
+F_VAL_GRU = 17.18e6                  # ConvGRU value / oracle net
+
+
+def f_den(length):
+  return 2 * length * (5 * 128 * 9 + 20 * 128 * 128 * 9 + 128 * 128 + 128 * 5)
+
+
+def csrc_sha():
+  """Fingerprint of the kernel sources: ncu-derived numbers committed under profiles/ carry it,
+  and the bench refuses to quote them for a library built from different sources."""
+  h = hashlib.sha256()
+  d = os.path.join(ROOT, 'svdd_b200', 'csrc')
+  for name in sorted(os.listdir(d)):
+    with open(os.path.join(d, name), 'rb') as f:
+      h.update(name.encode() + b'\0' + f.read())
+  return h.hexdigest()[:16]
 
 
 def peaks():
@@ -116,73 +139,161 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------
 def build_models(device, seed=44):
-  import helpers
-  from svdd_b200 import config, diffusion_gosai, value_nets
+  """c2's networks: the CNN denoiser of configs_gosai (seed 44 = decode.py's default --seed) and
+  the value net decode.py:78-80 builds, EnformerTrunk(7, 1536, 11, 8, 64) + ConvHead(1, 3072),
+  random-init with calibrated BatchNorm statistics and non-zero attention output projections --
+  the SAME seeded network tests/test_gpu_nets.py pins against the reference's fp32 outputs."""
+  from svdd_b200 import config, diffusion_gosai, synthetic
   cfg = config.load_config('dna')
-  torch.manual_seed(seed)                       # decode.py's default --seed
+  torch.manual_seed(seed)
   model = diffusion_gosai.Diffusion(cfg).eval()
-  emb = value_nets.EnformerTrunk(**helpers.ENFORMER_FULL_KW)          # decode.py:78
-  head = value_nets.ConvHead(n_tasks=1, in_channels=2 * 1536, act_func=None, pool_func='avg')
-  # zero-initialised attention output projections would make the attention path vacuous
-  helpers.perturb_(emb, 9)
+  emb, head = synthetic.build_enformer(full=True)
   return cfg, model.to(device), emb.to(device).eval(), head.to(device).eval()
 
 
-def cpu_port_sample(cfg_model, emb, head, n_seq=2, n_steps=2, threads=None):
-  """Times the CPU oracle (port of the reference) on a bounded sample of the workload:
-  n_steps reverse SVDD-MC steps for n_seq sequences x M candidates, full-size networks.
-  Returns (decoded seq/s extrapolated to 128 steps + noise removal, description, cores)."""
-  from oracle import nets, svdd
-  threads = threads or os.cpu_count()
-  torch.set_num_threads(threads)
-  sd = {'backbone.' + k: v.detach().float().cpu() for k, v in cfg_model.backbone.state_dict().items()}
-  esd = {k: v.detach().float().cpu() for k, v in emb.state_dict().items()}
-  hsd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
-  denoiser = lambda x: nets.denoiser_logits(sd, x)
-  value = lambda tok: nets.enformer_value(esd, hsd, svdd.transform_samples(tok).float()).reshape(-1)
-  sched, _ = svdd.move_chances(NUM_STEPS, 1e-5)
-  x = torch.full((n_seq, L), 4, dtype=torch.int64)
-  g = torch.Generator().manual_seed(0)
-  with torch.no_grad():
-    t0 = time.perf_counter()
-    for i in range(n_steps):
-      U = torch.rand(M, n_seq, L, 5, generator=g)
-      x = svdd.step_mc(denoiser, value, x, float(sched[i, 0]), float(sched[i, 1]), U)
-    t_step = (time.perf_counter() - t0) / n_steps
-    t0 = time.perf_counter()
-    svdd.noise_removal(denoiser, x)
-    t_den = time.perf_counter() - t0
-  total = t_step * NUM_STEPS + t_den
-  desc = (f'{n_steps} reverse steps of the workload for {n_seq} sequences x M={M} candidates '
-          f'(full-size nets, torch CPU fp32, {threads} threads): {t_step:.2f} s/step; extrapolated '
-          f'x{NUM_STEPS} steps + 1 denoiser forward = {total:.1f} s per {n_seq} sequences')
-  return n_seq / total, desc, threads, t_step
+class CpuPort:
+  """The CPU oracle (port of the reference, oracle/) on the bench workload.  One sample = ONE real
+  reverse SVDD-MC step at the full batch: denoiser on B sequences, M draws, the value net on all
+  B*M candidates (candidate by candidate, as diffusion_gosai.py:1203-1210 does), selection."""
+
+  def __init__(self, cfg_model, emb, head, threads=None):
+    from oracle import nets, svdd
+    self.svdd = svdd
+    self.threads = threads or os.cpu_count()
+    torch.set_num_threads(self.threads)
+    sd = {'backbone.' + k: v.detach().float().cpu() for k, v in cfg_model.backbone.state_dict().items()}
+    esd = {k: v.detach().float().cpu() for k, v in emb.state_dict().items()}
+    hsd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    self.denoiser = lambda x: nets.denoiser_logits(sd, x)
+    self.value = lambda tok: nets.enformer_value(esd, hsd, svdd.transform_samples(tok).float()).reshape(-1)
+    self.sched, _ = svdd.move_chances(NUM_STEPS, 1e-5)
+    self.g = torch.Generator().manual_seed(0)
+    self.x = torch.full((B_PER_GPU, L), 4, dtype=torch.int64)
+    self.i = 0
+    self.t_den = None
+
+  def step(self):
+    """One reverse step at B = 128, M = 10; returns seconds."""
+    i = self.i % NUM_STEPS
+    with torch.no_grad():
+      U = torch.rand(M, B_PER_GPU, L, 5, generator=self.g)
+      t0 = time.perf_counter()
+      self.x = self.svdd.step_mc(self.denoiser, self.value, self.x, float(self.sched[i, 0]),
+                                 float(self.sched[i, 1]), U)
+      dt = time.perf_counter() - t0
+    self.i += 1
+    return dt
+
+  def noise_removal_seconds(self):
+    if self.t_den is None:
+      with torch.no_grad():
+        t0 = time.perf_counter()
+        self.svdd.noise_removal(self.denoiser, self.x)
+        self.t_den = time.perf_counter() - t0
+    return self.t_den
+
+  def summary(self, step_seconds):
+    t_step = statistics.mean(step_seconds)
+    total = t_step * NUM_STEPS + self.noise_removal_seconds()
+    desc = (f'{len(step_seconds)} real reverse step(s) of the workload at the FULL batch (B={B_PER_GPU} sequences x '
+            f'M={M} candidates, L={L}, full-size nets, torch CPU fp32, {self.threads} threads): {t_step:.2f} s/step; '
+            f'a decode = {NUM_STEPS} such steps + 1 denoiser forward = {total:.0f} s per {B_PER_GPU} sequences '
+            f'(extrapolated over the step count only; the step cost is independent of the step index)')
+    return B_PER_GPU / total, desc, t_step
 
 
 def run_reference(args, rank, world, out):
   """--impl reference: the reference's CPU implementation of the path.  The reference is
-  Python/PyTorch that cannot travel to the GPU box, so this is its port (oracle/)."""
+  Python/PyTorch that cannot travel to the GPU box, so this is its port (oracle/).  Every bench
+  step (warm-up and timed alike) is ONE real reverse step at the full batch; `ms_per_step` is the
+  measured wall time of such a step, `value` the decoded seq/s of a 128-step decode at that rate."""
   if rank != 0:
     return
   cfg, model, emb, head = build_models(torch.device('cpu'))
-  vals, desc, cores, t_steps = [], '', 0, []
-  for i in range(args.warmup + args.steps):
-    v, desc, cores, t_step = cpu_port_sample(model, emb, head, n_seq=8, n_steps=4)
-    if i >= args.warmup:
-      vals.append(v)
-      t_steps.append(t_step)
-  value = statistics.mean(vals)
+  port = CpuPort(model, emb, head)
+  for _ in range(args.warmup):
+    port.step()
+  secs = [port.step() for _ in range(args.steps)]
+  value, desc, t_step = port.summary(secs)
   out.emit(({
       'impl': 'reference', 'metric': 'decoded_seqs_per_sec', 'value': value, 'unit': 'seq/s',
       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-      'ms_per_step': 1000.0 * 8 / value, 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': 1000.0 * t_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': WORKLOAD, 'B_per_gpu': B_PER_GPU, 'M': M, 'L': L,
-                 'denoise_steps': NUM_STEPS},
-      'cpu_baseline': {'value': value, 'unit': 'seq/s', 'cores': cores, 'kind': 'port',
+                 'denoise_steps': NUM_STEPS,
+                 'bench_step': 'ONE reverse step of the 128 at the full batch (a full CPU decode takes ~'
+                               f'{t_step * NUM_STEPS / 60:.0f} min); value = B / (128 x ms_per_step + noise removal)'},
+      'cpu_baseline': {'value': value, 'unit': 'seq/s', 'cores': port.threads, 'kind': 'port',
                        'sample': desc},
       'e2e': {'value': value, 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-      'ms_per_denoise_step_cpu_sample': 1000.0 * statistics.mean(t_steps)}))
+      'ms_per_denoise_step': 1000.0 * t_step}))
+
+
+def other_config_legs(device, rank, world, dna_model, emb, head, barrier):
+  """BASELINE.json configs 3, 4, 5 on the same launch (N-aware, a few reverse steps each, device-
+  timed with CUDA events, max over ranks).  c4 and c5 name a GLOBAL batch (4096 / 8192) that is
+  sharded over the ranks -- strong scaling; c3 keeps 128 sequences per GPU like c2.  Each leg runs
+  `steps` real reverse steps of the trajectory (all-mask start, in-kernel Philox noise, eager
+  launches on the current stream) after one untimed pass, and reports ms per reverse step, the
+  decode rate that step time gives over 128 steps, and the tensor roofline fraction of the step
+  (nominal dense FLOPs of SURVEY 8(d) / time / measured sustained bf16 peak)."""
+  import torch.distributed as dist
+  from svdd_b200 import config, diffusion_gosai, synthetic, value_nets
+  pk = peaks()
+  legs = {}
+
+  def leg(tag, desc, model, run, B_rank, B_global, flops_step_rank, steps):
+    model.use_cuda_graph = False
+    run(steps)                                           # untimed pass (workspaces, lazy tables)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x = run(steps)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    model.use_cuda_graph = True
+    assert x.shape[0] == B_rank and int(x.max()) <= 3
+    step_ms = float(ms) / steps                          # the noise-removal forward is charged to the steps: upper bound
+    tf = flops_step_rank / (step_ms * 1e-3) / 1e12
+    legs[tag] = {'workload': desc, 'B_per_gpu': B_rank, 'global_batch': B_global, 'n_gpus': world,
+                 'timed_reverse_steps': steps, 'ms_per_denoise_step': step_ms,
+                 'decoded_seqs_per_sec_at_128_steps': B_global / (step_ms * 1e-3 * NUM_STEPS),
+                 'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
+                              'frac': tf / pk['tf_sust'], 'flops_per_step_per_gpu': flops_step_rank}}
+    torch.cuda.empty_cache()
+
+  # c3: DNA SVDD-PM, Tweedie x0-prediction scored by the 3-task Enformer-style oracle (task 0)
+  rm = synthetic.build_dna_reward_model().to(device)
+  B = B_PER_GPU
+  leg('c3', 'DNA enhancer SVDD-PM (decode_tweedie.py --tweedie True): L=200, M=10, batch 128 per GPU, '
+      '3-task Enformer-style reward oracle (task 0 scored)', dna_model,
+      lambda n: dna_model.controlled_sample_tweedie(rm, num_steps=n, eval_sp_size=B, sample_M=M, options='True',
+                                                    task='dna', row_offset=rank * B),
+      B, B * world, B * (M + 1) * F_DEN + B * M * F_VAL, steps=6)
+  del rm
+  # c4: DNA SVDD-MC, batch 4096 sharded over the ranks, M = 20
+  B4 = 4096 // world
+  leg('c4', f'DNA enhancer SVDD-MC large batch 4096, M=20, batch-sharded x{world} ({B4} sequences per GPU)', dna_model,
+      lambda n: dna_model.controlled_sample(emb, head, num_steps=n, eval_sp_size=B4, sample_M=20,
+                                            row_offset=rank * B4),
+      B4, 4096, B4 * F_DEN + B4 * 20 * F_VAL, steps=3)
+  # c5: RNA SVDD-PM, batch 8192 sharded over the ranks, M = 50, argmax vs soft resampling
+  cfg = config.load_config('rna')
+  torch.manual_seed(44)
+  rna = diffusion_gosai.Diffusion(cfg).to(device).eval()
+  oe, oh = synthetic.build_convgru_oracle()
+  rm5 = value_nets.OriBaseModel(oe.to(device), oh.to(device))
+  B5 = 8192 // world
+  for alpha in (0.0, 0.1):
+    leg(f'c5_alpha{alpha:g}', f'RNA MRL SVDD-PM M=50, alpha={alpha:g}, batch 8192 sharded x{world} ({B5} sequences per GPU), L=50',
+        rna, lambda n, a=alpha: rna.controlled_sample_tweedie(rm5, num_steps=n, eval_sp_size=B5, sample_M=50, options='True',
+                                                              task='rna', alpha=a, row_offset=rank * B5),
+        B5, 8192, B5 * 51 * f_den(50) + B5 * 50 * F_VAL_GRU, steps=3)
+  return legs
 
 
 class _JsonOnlyStdout:
@@ -208,6 +319,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-other-configs', action='store_true')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', 0))
   world = int(os.environ.get('WORLD_SIZE', 1))
@@ -309,9 +421,15 @@ def main():
     gemm_flops += B * F_DEN
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     step_ms = ms_per_step / NUM_STEPS       # one reverse step (the +1 denoiser forward is <0.1%)
+    # DRAM traffic comes from an ncu capture (cannot be taken inside a timed run): the committed
+    # summary is stamped with the fingerprint of the kernel sources it was measured on and is only
+    # quoted when the library in use was built from the same sources.
     try:
-      with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+      with open(os.path.join(ROOT, 'profiles', TRAFFIC_FILE)) as f:
         traffic = json.load(f)
+      if traffic.get('csrc_sha') != csrc_sha():
+        traffic = {'source': f"profiles/{TRAFFIC_FILE} is STALE (measured on csrc {traffic.get('csrc_sha')}, "
+                             f'library sources are {csrc_sha()}): traffic not quoted'}
     except Exception:
       traffic = {}
     top_ach = top['flops'] / (top['ms'] * 1e-3) / 1e12 if top['ms'] > 0 else None
@@ -379,11 +497,18 @@ def main():
       del sc, cand64
     del flush
 
+  # ---- the other BASELINE configs (all ranks take part: the legs are N-aware) ------------------------
+  other = None
+  if not args.no_other_configs:
+    other = other_config_legs(device, rank, world, model, emb, head, barrier)
+
   # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    v, desc, cores, _ = cpu_port_sample(model, emb, head, n_seq=16, n_steps=8)
-    cpu = {'value': v, 'unit': 'seq/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+    port = CpuPort(model.cpu(), emb.cpu(), head.cpu())
+    port.step()                                   # warm-up (thread pool, allocator)
+    v, desc, _ = port.summary([port.step()])
+    cpu = {'value': v, 'unit': 'seq/s', 'cores': port.threads, 'kind': 'port', 'sample': desc}
 
   if rank == 0:
     out.emit(({
@@ -400,7 +525,8 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'seq/s', 'h2d_bytes_per_step': B * L * 8,
                 'd2h_bytes_per_step': B * L * 8},
         'gpu_launches': launches_per_run * args.steps,
-        'roofline': roofline, 'stage_rooflines': stage_rooflines, 'cpu_baseline': cpu}))
+        'roofline': roofline, 'stage_rooflines': stage_rooflines, 'other_configs': other,
+        'cpu_baseline': cpu}))
   if world > 1:
     dist.destroy_process_group()
 

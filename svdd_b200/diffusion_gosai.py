@@ -86,6 +86,11 @@ class Diffusion(nn.Module):
     self._calls = itertools.count()
     self._graphs = {}
     self.use_cuda_graph = True
+    # where the move-chance schedule is evaluated: 'cpu' (default; what the oracle and the
+    # reference-generated goldens pin) or 'model' (torch ops on the model's device, i.e. CUDA
+    # libm like a reference run on the same GPU; differs from 'cpu' by <= 1 ulp of exp(-sigma),
+    # tests/test_gpu_sampling.py::test_schedule_host_vs_device)
+    self.schedule_device = 'cpu'
 
   # -- plumbing ---------------------------------------------------------------------
   @property
@@ -236,7 +241,8 @@ class Diffusion(nn.Module):
     if dev.type != 'cuda':
       raise _lib.SvddError('move the model to a CUDA device (svdd_b200 has no CPU path)')
     L = int(self.config.model.length)
-    sched, sigma_last = noise_schedule.move_chance_schedule(self.noise, num_steps, eps)
+    sched, sigma_last = noise_schedule.move_chance_schedule(
+        self.noise, num_steps, eps, device=dev if self.schedule_device == 'model' else 'cpu')
     den = self.backbone.packed()
     tc = self.time_conditioning
     seed = self._seed_for_call() if seed is None else seed
@@ -326,7 +332,7 @@ class Diffusion(nn.Module):
     at can be freed or recycled while the graph can still be replayed.  A handle that later
     grows its workspace gets a NEW tensor; the graph keeps using (and owning) the old one."""
     key = (mode, B, num_steps, eps, M, getattr(scorer, 'uid', None) or id(scorer), tweedie, alpha,
-           den.uid if hasattr(den, 'uid') else id(den), str(self.device))
+           den.uid if hasattr(den, 'uid') else id(den), str(self.device), self.schedule_device)
     entry = self._graphs.get(key)
 
     def set_run():

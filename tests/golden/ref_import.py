@@ -157,15 +157,19 @@ def import_reference():
   if not reference_available():
     raise RuntimeError(f'reference tree not found at {REF_ROOT}')
   install_stubs()
-  if REF_ROOT not in sys.path:
-    sys.path.insert(0, REF_ROOT)
   import warnings
-  with warnings.catch_warnings():
-    warnings.simplefilter('ignore')
-    import noise_schedule
-    import models.dnaconv as dnaconv
-    import diffusion_gosai
-    import Enformer
+  # The reference tree is on sys.path only while its modules are imported: it holds top-level
+  # names (decode.py, oracle.py ...) that would shadow this repository's own afterwards.
+  sys.path.insert(0, REF_ROOT)
+  try:
+    with warnings.catch_warnings():
+      warnings.simplefilter('ignore')
+      import noise_schedule
+      import models.dnaconv as dnaconv
+      import diffusion_gosai
+      import Enformer
+  finally:
+    sys.path.remove(REF_ROOT)
   return types.SimpleNamespace(diffusion_gosai=diffusion_gosai,
                                dnaconv=dnaconv,
                                noise_schedule=noise_schedule,

@@ -197,11 +197,16 @@ def test_enformer_value(cuda):
   assert torch.equal(got8, got)
 
 
-# Full headline network (decode.py:78-80): stated tolerances.  Scores of this seeded net are
-# O(0.1-0.5); the bf16-operand pipeline (7 conv stages + 11 transformer blocks = ~50 GEMMs deep)
-# lands within EF_TIGHT of the oracle's bf16-operand emulation and EF_LOOSE of the fp32 reference,
-# both ABSOLUTE on the score (and as a fraction of the batch's score standard deviation).
-EF_TIGHT, EF_LOOSE, EF_MEAN = 2.5e-2, 3.5e-2, 8e-3
+# Full headline network (decode.py:78-80): stated tolerances, ABSOLUTE on the score.  Scores of
+# this seeded net have mean 0.16, std 0.11, range 0.58 over the batch.  The bf16-operand pipeline
+# (7 conv stages + 11 transformer blocks, ~50 GEMMs deep, fp32 accumulate / normalisation /
+# residual stream) lands within EF_REF of the REFERENCE's fp32 output (measured 1.9e-2 max,
+# 3.5e-3 mean = 3 % of the std).  The oracle's CPU bf16-operand emulation is a second bf16
+# pipeline with its own rounding noise of the same size (emulation vs fp32: 2.2e-2), so kernel vs
+# emulation is bounded by the SUM (EF_EMU; measured 3.7e-2) -- at this depth it documents the
+# noise level, the fp32 bound is the parity statement.  The 384-channel / 2-block net above
+# (test_enformer_value) is where the emulation is tight enough to catch semantic errors.
+EF_REF, EF_MEAN, EF_EMU = 2.5e-2, 5e-3, 4.5e-2
 
 
 def test_enformer_full_headline_network_parity(cuda):
@@ -231,10 +236,8 @@ def test_enformer_full_headline_network_parity(cuda):
         f'range {float(ref.max() - ref.min()):.4f}\n  max|d| vs bf16-emulating oracle {e_emu:.3e} ({e_emu / sd:.1%} of std), '
         f'vs fp32 reference {e_ref:.3e} ({e_ref / sd:.1%} of std), mean|d| vs fp32 {m_ref:.3e}; '
         f'(emulation vs fp32: {float((emu - ref).abs().max()):.3e})')
-  assert e_emu <= EF_TIGHT and e_ref <= EF_LOOSE and m_ref <= EF_MEAN
-  # correlation of the candidate ORDER with the reference over all candidates
-  rank_corr = float(torch.corrcoef(torch.stack([got.reshape(-1), ref.reshape(-1)]))[0, 1])
-  assert rank_corr >= 0.995, rank_corr
+  # correlation with the reference over all candidates
+  corr = float(torch.corrcoef(torch.stack([got.reshape(-1), ref.reshape(-1)]))[0, 1])
   # selection: argmax over each sequence's M candidates
   spread = ref.max(0).values - ref.min(0).values
   pick, pick_ref, pick_emu = got.argmax(0), ref.argmax(0), emu.argmax(0)
@@ -243,6 +246,9 @@ def test_enformer_full_headline_network_parity(cuda):
   print(f'  argmax over M=10: agreement with fp32 reference {agree:.3f} (the CPU bf16 emulation: '
         f'{float((pick_emu == pick_ref).float().mean()):.3f}); regret of disagreements max {float(regret.max()):.3e} '
         f'mean {float(regret.mean()):.3e}; mean spread over M {float(spread.mean()):.3e}')
+  print(f'  correlation with the fp32 reference over the {M * S} scores: {corr:.5f}')
+  assert e_ref <= EF_REF and m_ref <= EF_MEAN and e_emu <= EF_EMU
+  assert corr >= 0.995
   assert agree >= 0.85 and float(regret.max()) <= 0.25 * float(spread.mean())
   assert float(regret.mean()) <= 0.03 * float(spread.mean())
   # uint8 tokens take the same path
@@ -286,7 +292,7 @@ def test_dna_reward_oracle_scores_task_0_of_3(cuda):
   ref3 = T(g['values3'])                                                               # [2, 32, 3]
   e = [float((got - ref3[..., t]).abs().max()) for t in range(3)]
   print(f'\n[dna reward oracle] max|d| vs task 0 / 1 / 2 of the reference: {e[0]:.3e} / {e[1]:.3e} / {e[2]:.3e}')
-  assert e[0] <= EF_LOOSE and min(e[1], e[2]) > 3 * EF_LOOSE
+  assert e[0] <= EF_REF and min(e[1], e[2]) > 3 * EF_REF
 
 
 def test_enformer_batch_independence(cuda):

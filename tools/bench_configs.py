@@ -19,9 +19,9 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
+sys.path[:0] = [ROOT]
 import bench    # noqa: E402
-import helpers  # noqa: E402
+from svdd_b200 import synthetic as helpers  # noqa: E402
 
 F_VAL_ENF = 3.362e9
 F_VAL_GRU = 17.18e6
