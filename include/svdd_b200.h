@@ -161,6 +161,33 @@ int svdd_denoiser_forward(svdd_denoiser* h, const void* tokens, int tok_dtype,
                           const float* time_bias, float* logits, int64_t n_rows,
                           int L, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- stage 1, alternative backbone: DiT (models/dit.py:214-369) -----------
+ * Replaces DIT.forward (models/dit.py:355-366: vocab_embed -> n_blocks x DDiTBlock ->
+ * DDitFinalLayer) for `backbone: dit` (diffusion_gosai.py:102-104).  Tensors, names relative
+ * to the `backbone.` prefix, shapes as in the reference:
+ *   vocab_embed.embedding[5,H]       rotary_emb.inv_freq[32]
+ *   blocks.i.attn_qkv.weight[3H,H]   blocks.i.attn_out.weight[H,H]
+ *   blocks.i.mlp.0.{weight[4H,H],bias[4H]}  blocks.i.mlp.2.weight[H,4H]
+ *   output_layer.linear.{weight[5,H],bias[5]}
+ * H = 64 * n_heads, a multiple of 128.  The conditioning c = silu(sigma_map(sigma)) is
+ * batch-constant on the decode path, so everything that depends on it -- the six
+ * adaLN_modulation vectors of each block and the two of the final layer, folded with the
+ * LayerNorm weights and mlp.2.bias -- is computed by the host and passed per call as `mod`
+ * (fp32, device, svdd_dit_mod_floats() elements; layout documented at svdd_dit_forward in
+ * csrc/dit.cu and built by svdd_b200/dit.py:DIT.modulation).
+ * Arithmetic as in the reference's autocast region (:362): bf16 GEMM operands and attention,
+ * fp32 accumulation, LayerNorm and residual stream. */
+typedef struct svdd_dit svdd_dit;
+int svdd_dit_create(const svdd_tensor* tensors, int n_tensors, int n_heads, void* stream,
+                    svdd_dit** out);
+void svdd_dit_destroy(svdd_dit* h);
+int64_t svdd_dit_mod_floats(const svdd_dit* h);
+size_t svdd_dit_workspace_bytes(const svdd_dit* h, int64_t n_rows, int L);
+/* tokens [N,L] -> logits [N,L,5] fp32 (raw, pre-SUBS); L <= 1024. */
+int svdd_dit_forward(svdd_dit* h, const void* tokens, int tok_dtype, const float* mod,
+                     float* logits, int64_t n_rows, int L, void* ws, size_t ws_bytes,
+                     void* stream);
+
 /* ---- stage 3a: RNA value net / reward oracle (ConvGRU) --------------------
  * Replaces head(embedding(transform_samples(tokens).float())).squeeze()
  * (diffusion_gosai.py:1208-1209, 1462-1470) for

@@ -321,3 +321,67 @@ def enformer_value(sd_embedding, sd_head, onehot, n_heads=8,
   onehot fp32 [N,L,4] -> fp32 [N,1,1]."""
   return conv_head(sd_head, enformer_trunk(sd_embedding, onehot, n_heads,
                                            emulate_bf16))
+
+
+# ----------------------------------------------------------------------------
+# DiT denoiser: models/dit.py:214-369
+# ----------------------------------------------------------------------------
+
+def _dit_ln(x, w):
+  """LayerNorm without bias (models/dit.py:126-134): F.layer_norm(x.float(), [dim]) * weight."""
+  return F.layer_norm(x.float(), (x.shape[-1],)) * w[None, None, :]
+
+
+def dit_logits(sd, tokens, sigma=None, n_heads=12, prefix='backbone.', emulate_bf16=False):
+  """DIT.forward body (models/dit.py:355-366; the reference's function lacks its ``return``):
+  vocab_embed -> c = silu(sigma_map(sigma)) -> DDiTBlock x n (:239-288) -> DDitFinalLayer
+  (:316-321).  tokens int64 [B,L] -> logits fp32 [B,L,V].  fp32 throughout (the reference's
+  bf16 autocast region is a GPU-only construct); ``emulate_bf16`` rounds GEMM operands, q / k / v,
+  the attention probabilities and the branch outputs to bf16 where the sm_100a kernels do."""
+  e = emulate_bf16
+  B, L = tokens.shape
+  if sigma is None:
+    sigma = torch.zeros(B, dtype=torch.float32)
+  g = lambda k: sd[prefix + k]
+  x = g('vocab_embed.embedding')[tokens]                                 # EmbeddingLayer :296-297
+  half = g('sigma_map.mlp.0.weight').shape[1] // 2
+  freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+  args = sigma[:, None].float() * freqs[None]
+  t_freq = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)         # :160-181
+  t_emb = F.linear(F.silu(F.linear(t_freq, g('sigma_map.mlp.0.weight'), g('sigma_map.mlp.0.bias'))),
+                   g('sigma_map.mlp.2.weight'), g('sigma_map.mlp.2.bias'))
+  c = F.silu(t_emb)                                                      # :357
+  inv_freq = g('rotary_emb.inv_freq')
+  fr = torch.arange(L, dtype=torch.float32)[:, None] * inv_freq[None, :]  # :88-90
+  cos, sin = fr.cos()[None, :, None, :], fr.sin()[None, :, None, :]
+  hd = x.shape[-1] // n_heads
+  i = 0
+  while prefix + f'blocks.{i}.attn_qkv.weight' in sd:
+    p = f'blocks.{i}.'
+    mod = F.linear(c, g(p + 'adaLN_modulation.weight'), g(p + 'adaLN_modulation.bias'))[:, None]
+    sh1, sc1, g1, sh2, sc2, g2 = mod.chunk(6, dim=2)                     # :245-246
+    h = _dit_ln(x, g(p + 'norm1.weight')) * (1 + sc1) + sh1              # :250
+    qkv = _q(F.linear(_q(h, e), _q(g(p + 'attn_qkv.weight'), e)), e)     # :252
+    qkv = qkv.reshape(B, L, 3, n_heads, hd)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+
+    def rot(t):
+      t1, t2 = t[..., :hd // 2], t[..., hd // 2:]
+      return _q(torch.cat([t1 * cos - t2 * sin, t1 * sin + t2 * cos], dim=-1), e)
+    q, k = rot(q), rot(k)                                                # :257-260
+    att = torch.einsum('bqhd,bkhd->bhqk', q, k) * hd ** -0.5
+    if e:       # the kernel rounds exp(s - max) to bf16 for the P V product and normalises by the sum of the ROUNDED values
+      pu = _q(torch.exp(att - att.amax(-1, keepdim=True)), True)
+      pr = pu / pu.sum(-1, keepdim=True)
+    else:
+      pr = torch.softmax(att, dim=-1)
+    a = torch.einsum('bhqk,bkhd->bqhd', pr, v).reshape(B, L, -1)         # :262-265
+    x = x + g1 * F.linear(_q(a, e), _q(g(p + 'attn_out.weight'), e))     # :267-271
+    h = _dit_ln(x, g(p + 'norm2.weight')) * (1 + sc2) + sh2
+    u = F.gelu(F.linear(_q(h, e), _q(g(p + 'mlp.0.weight'), e), g(p + 'mlp.0.bias')), approximate='tanh')
+    x = x + g2 * F.linear(_q(u, e), _q(g(p + 'mlp.2.weight'), e), g(p + 'mlp.2.bias'))   # :274-277
+    i += 1
+  mod = F.linear(c, g('output_layer.adaLN_modulation.weight'), g('output_layer.adaLN_modulation.bias'))[:, None]
+  sh, sc = mod.chunk(2, dim=2)
+  h = _dit_ln(x, g('output_layer.norm_final.weight')) * (1 + sc) + sh
+  return F.linear(h, g('output_layer.linear.weight'), g('output_layer.linear.bias'))

@@ -55,7 +55,7 @@ def _declare(lib):
   lib.svdd_selftest_rel_positions.argtypes = [i32, i32, vp]
   lib.svdd_selftest_attention.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
   tp = c.POINTER(_Tensor)
-  for net, extra in (('denoiser', [i32]), ('convgru', []), ('enformer', [i32])):
+  for net, extra in (('denoiser', [i32]), ('convgru', []), ('enformer', [i32]), ('dit', [i32])):
     create = getattr(lib, f'svdd_{net}_create', None)
     if create is None:
       continue
@@ -68,6 +68,10 @@ def _declare(lib):
   if hasattr(lib, 'svdd_denoiser_forward'):
     lib.svdd_denoiser_forward.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp,
                                           c.c_size_t, vp]
+  if hasattr(lib, 'svdd_dit_forward'):
+    lib.svdd_dit_forward.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, c.c_size_t, vp]
+    lib.svdd_dit_mod_floats.argtypes = [vp]
+    lib.svdd_dit_mod_floats.restype = i64
   for net in ('convgru', 'enformer'):
     fn = getattr(lib, f'svdd_{net}_score', None)
     if fn is not None:
@@ -389,6 +393,54 @@ class DenoiserHandle(_Handle):
     ws, need = self._workspace(N, L, tokens.device)
     check(lib().svdd_denoiser_forward(self._h, _ptr(tokens), tok_dtype(tokens), _ptr(tb),
                                       _ptr(logits), N, L, _ptr(ws), need, _stream()))
+    return logits
+
+
+class DiTHandle(_Handle):
+  """Packed DiT denoiser (svdd_dit_*), built from a ``svdd_b200.dit.DIT``.  Same call shape as
+  DenoiserHandle: ``forward(tokens, sigma, out)`` -> raw logits fp32 [N,L,5]; the adaLN
+  modulation of ``sigma`` is evaluated by the module on the host (cached per sigma) and handed
+  to the kernels as folded per-channel vectors."""
+  _net = 'dit'
+
+  def __init__(self, module):
+    super().__init__()
+    sd = module.state_dict()
+    skip = ('sigma_map.', 'adaLN_modulation', 'norm1.', 'norm2.', 'norm_final.', 'mlp.2.bias')
+    named = [(k, v) for k, v in sd.items()
+             if v.dtype.is_floating_point and not any(s in k for s in skip)]
+    dev = next(iter(sd.values())).device
+    if dev.type != 'cuda':
+      raise SvddError('move the model to a CUDA device before running it')
+    self._create(named, int(module.n_heads))
+    self._module = module
+    self._tbias_cache = {}
+    self.mod_floats = int(lib().svdd_dit_mod_floats(self._h))
+
+  def time_bias(self, sigma):
+    """The folded modulation vectors for one sigma (cached; must not miss inside a graph capture)."""
+    key = float(sigma)
+    tb = self._tbias_cache.get(key)
+    if tb is None:
+      if torch.cuda.is_current_stream_capturing():
+        raise SvddError('DiT modulation cache miss during CUDA-graph capture (sigma=%r)' % key)
+      tb = self._module.modulation(key).float().contiguous()
+      assert tb.numel() == self.mod_floats, (tb.numel(), self.mod_floats)
+      if len(self._tbias_cache) > 4096:
+        self._tbias_cache.clear()
+      self._tbias_cache[key] = tb
+    return tb
+
+  def forward(self, tokens, sigma=0.0, out=None):
+    """tokens int64/uint8 [N,L] (CUDA) -> raw logits fp32 [N,L,5]."""
+    _require_cuda(tokens)
+    tokens = tokens.contiguous()
+    N, L = tokens.shape
+    mod = self.time_bias(sigma)
+    logits = out if out is not None else torch.empty((N, L, 5), dtype=torch.float32, device=tokens.device)
+    ws, need = self._workspace(N, L, tokens.device)
+    check(lib().svdd_dit_forward(self._h, _ptr(tokens), tok_dtype(tokens), _ptr(mod), _ptr(logits), N, L,
+                                 _ptr(ws), need, _stream()))
     return logits
 
 

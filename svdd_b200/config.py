@@ -17,8 +17,16 @@ def _ns(obj):
   return obj
 
 
-def load_config(task='dna', config_dir=None, **overrides):
-  """task: 'dna' (anything that is not rna/rna_saluki, as in Enformer.py:75-89) or 'rna'."""
+# configs_gosai/model/small.yaml, the DiT the reference's `backbone: dit` branch would build
+# (`length` is the SEQUENCE length the sampler uses, so the task's value is kept)
+DIT_SMALL = dict(name='small', type='ddit', hidden_size=768, cond_dim=128, n_blocks=12, n_heads=12,
+                 scale_by_sigma=True, dropout=0.1, tie_word_embeddings=False)
+
+
+def load_config(task='dna', config_dir=None, backbone=None, **overrides):
+  """task: 'dna' (anything that is not rna/rna_saluki, as in Enformer.py:75-89) or 'rna'.
+  backbone='dit' swaps the model section for configs_gosai/model/small.yaml (hydra:
+  ``model=small backbone=dit``)."""
   name = 'rna' if task in ('rna', 'rna_saluki') else 'dna'
   if config_dir is None:
     with open(os.path.join(_HERE, 'configs', name + '.yaml')) as f:
@@ -33,6 +41,11 @@ def load_config(task='dna', config_dir=None, **overrides):
     if not isinstance(tree['noise'], dict):
       tree['noise'] = {'type': 'loglinear'}
     tree['loader'] = {'eval_batch_size': 512}
+  if backbone == 'dit':
+    tree['backbone'] = 'dit'
+    tree['model'] = dict(DIT_SMALL, length=tree['model']['length'])
+  elif backbone is not None:
+    tree['backbone'] = backbone
   for dotted, v in overrides.items():
     node = tree
     keys = dotted.split('.')

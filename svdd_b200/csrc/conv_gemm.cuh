@@ -30,7 +30,7 @@
 
 namespace svdd {
 
-enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_TANH = 3 };   // 2: enformer x*sigmoid(1.702x); 3: nn.GELU('tanh')
 enum DType { DT_NONE = 0, DT_BF16 = 1, DT_F32 = 2 };
 enum EpiMode { EPI_GENERIC = 0, EPI_DEN_LN = 1, EPI_DEN_FINAL = 2, EPI_POOL = 3, EPI_HEADDOT = 4,
                EPI_PAIR = 5, EPI_POOL2 = 6 };   // 5, 6: conv_gemm2.cuh only
@@ -170,6 +170,13 @@ __device__ __forceinline__ float fast_ex2(float x) {
 __device__ __forceinline__ float gelu_enformer(float v) {
   return v * fast_rcp(1.0f + fast_ex2(-2.4554669595930157f * v));
 }
+// nn.GELU(approximate='tanh'): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  (models/dit.py:224)
+__device__ __forceinline__ float gelu_tanh_approx(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * fmaf(0.044715f * v, v * v, v)));
+  const float h = 0.5f * v;
+  return fmaf(h, t, h);
+}
 // activation over a 32-column chunk; the kind is tested once per chunk, not per element
 __device__ __forceinline__ void apply_act32(float* v, int act) {
   if (act == ACT_RELU) {
@@ -178,6 +185,9 @@ __device__ __forceinline__ void apply_act32(float* v, int act) {
   } else if (act == ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_enformer(v[i]);
+  } else if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_approx(v[i]);
   }
 }
 

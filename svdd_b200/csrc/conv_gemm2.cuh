@@ -207,6 +207,9 @@ __device__ __forceinline__ void act32(float* v, int act) {
   } else if (act == ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+  } else if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gemm_detail::gelu_tanh_approx(v[i]);
   }
 }
 
@@ -300,6 +303,9 @@ __device__ __forceinline__ void act16(float* v, int act) {
   } else if (act == ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = gelu_tanh(v[i]);
+  } else if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gemm_detail::gelu_tanh_approx(v[i]);
   }
 }
 

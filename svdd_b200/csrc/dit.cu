@@ -1,0 +1,604 @@
+// Stage 1, alternative backbone: the DiT denoiser (reference: models/dit.py:214-369, `DDiTBlock`,
+// `DDitFinalLayer`, `DIT`; selected by `backbone: dit`, diffusion_gosai.py:102-104).
+//
+//   tokens -> vocab_embed[tok]                                   dit_embed_kernel   (fp32 residual stream x)
+//   per block:
+//     h   = LN(x) * w1 * (1 + scale_msa) + shift_msa             dit_ln_kernel      (adaLN folded to one affine)
+//     qkv = h @ Wqkv^T                                           gemm2 (tcgen05)    bf16 out
+//     a   = softmax(rot(q) rot(k)^T / sqrt(d)) v                 dit_attn_kernel    rotary + flash attention (non-causal)
+//     x  += gate_msa * (a @ Wo^T)                                gemm2, per-column scale, TMA reduce-add into x
+//     h   = LN(x) * w2 * (1 + scale_mlp) + shift_mlp             dit_ln_kernel
+//     u   = gelu_tanh(h @ W1^T + b1)                             gemm2, bias + activation, bf16 out
+//     x  += gate_mlp * (u @ W2^T + b2)                           gemm2, per-column scale/shift, reduce-add into x
+//   logits = (LN(x) * wf * (1 + scale) + shift) @ Wout^T + bout  dit_final_kernel   (N = vocab = 5: warp per row)
+//
+// The conditioning vector c = silu(sigma_map(sigma)) is the same for every sequence of a call on
+// the decode path (sigma is batch-constant, 0 without time conditioning: diffusion_gosai.py:334-335),
+// so the six adaLN vectors of each block are per-CHANNEL constants: the host evaluates
+// adaLN_modulation(c) once per sigma and hands the folded affine terms in as `mod` (layout below);
+// modulate() then costs nothing and the gates ride in the GEMM epilogues.
+//
+// Numerics follow the reference's autocast region (models/dit.py:362-366): bf16 GEMM operands with
+// fp32 accumulation, LayerNorm and the residual stream in fp32, attention probabilities and
+// q / k / v in bf16.
+#include <new>
+
+#include <math.h>
+#include <stdlib.h>
+
+#include "conv_gemm.cuh"
+#include "weights.cuh"
+
+namespace svdd {
+namespace dit {
+
+constexpr int kHd = 64;                 // head dim (hidden_size / n_heads; small.yaml: 768 / 12)
+constexpr int kMaxBlocks = 48;
+constexpr int kMaxLen = 1024;           // configs_gosai/model/small.yaml: length 1024
+constexpr int kChunkRows = 32768;       // rows (sequences * L) per pass through the workspace
+constexpr int kModPerBlock = 8;         // g1, b1, gate1, zero, g2, b2, gate2, gate2*bias2   (each [H])
+
+// ---- embedding: x[r, :] = E[tok[r], :] ------------------------------------------------------
+template <typename Tok>
+__global__ void __launch_bounds__(256)
+dit_embed_kernel(const Tok* __restrict__ tok, const float* __restrict__ emb, float* __restrict__ x,
+                 int64_t rows, int H) {
+  pdl_wait();
+  pdl_trigger();
+  const int per_row = H / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c = (int)(i % per_row);
+  const int t = load_tok(tok, (size_t)r);
+  reinterpret_cast<float4*>(x)[i] = __ldg(reinterpret_cast<const float4*>(emb + (size_t)t * H) + c);
+}
+
+// ---- LayerNorm (no affine, eps 1e-5: models/dit.py:126-134) with the folded adaLN affine -> bf16
+// One warp per row, the row in registers as float4s, two-pass variance.
+template <int NV>     // float4s per lane: H = 128 * NV
+__global__ void __launch_bounds__(256)
+dit_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+              __nv_bfloat16* __restrict__ out, int64_t rows) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int H = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * H);
+  float4 v[NV];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / H);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / H) + 1e-5f);
+  uint2* orow = reinterpret_cast<uint2*>(out + row * H);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    uint2 p;
+    p.x = gemm_detail::pack_bf16x2(fmaf(v[i].x * rstd, gg.x, bb.x), fmaf(v[i].y * rstd, gg.y, bb.y));
+    p.y = gemm_detail::pack_bf16x2(fmaf(v[i].z * rstd, gg.z, bb.z), fmaf(v[i].w * rstd, gg.w, bb.w));
+    orow[lane + 32 * i] = p;
+  }
+}
+
+// ---- final layer: LN + folded adaLN + Linear(H -> V) -----------------------------------------
+template <int NV, int V>
+__global__ void __launch_bounds__(256)
+dit_final_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                 const float* __restrict__ w /*[V][H]*/, const float* __restrict__ bias,
+                 float* __restrict__ logits, int64_t rows) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int H = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * H);
+  float4 v[NV];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / H);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / H) + 1e-5f);
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    const float h0 = fmaf(v[i].x * rstd, gg.x, bb.x), h1 = fmaf(v[i].y * rstd, gg.y, bb.y);
+    const float h2 = fmaf(v[i].z * rstd, gg.z, bb.z), h3 = fmaf(v[i].w * rstd, gg.w, bb.w);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * H) + lane + 32 * i);
+      acc[j] += (h0 * ww.x + h1 * ww.y) + (h2 * ww.z + h3 * ww.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane < V) {
+    float r = 0.0f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) r = (lane == j) ? acc[j] : r;
+    logits[row * V + lane] = r + bias[lane];
+  }
+}
+
+// ---- rotary table: cos / sin [kMaxLen][kHd/2] of t * inv_freq (models/dit.py:74-99) -----------
+__global__ void dit_rotary_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cs,
+                                        float* __restrict__ sn, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (kHd / 2)) return;
+  const float f = (float)(i / (kHd / 2)) * inv_freq[i % (kHd / 2)];
+  cs[i] = cosf(f);
+  sn[i] = sinf(f);
+}
+
+// ---- attention: rotary on q, k (first hd dims split in halves: flash_attn's non-interleaved
+// apply_rotary_emb_qkv_, models/dit.py:107-110) + softmax(q k^T / sqrt(hd)) v, non-causal over the
+// L positions of one sequence (flash_attn_varlen_qkvpacked_func with equal lengths, :262-263).
+// One CTA = 64 queries of one (sequence, head); 4 warps x 16 query rows; K / V streamed in blocks
+// of 64 keys through shared memory; S and O live in mma.sync (m16n8k16, bf16) accumulator
+// fragments with an online softmax.  Attention is ~5 % of the backbone's FLOPs (4 L hd per
+// token and head against 24 H^2 per token in the linears), so it runs on the warp-level tensor
+// path; the linears are the tcgen05 kernels.
+constexpr int kQB = 64, kKB = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// element offset of (row, 16-byte chunk c of 8) in a [64][64] bf16 tile with an XOR swizzle
+__device__ __forceinline__ int swz(int row, int c) { return row * kHd + ((c ^ (row & 7)) << 3); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __low2float(h);
+    f[2 * j + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(gemm_detail::pack_bf16x2(f[0], f[1]), gemm_detail::pack_bf16x2(f[2], f[3]),
+                    gemm_detail::pack_bf16x2(f[4], f[5]), gemm_detail::pack_bf16x2(f[6], f[7]));
+}
+
+// loads 64 rows (positions l0..l0+63 of the sequence) x 64 dims of q or k with the rotary applied;
+// rows past L are zero
+__device__ __forceinline__ void load_rot_tile(__nv_bfloat16* tile, const __nv_bfloat16* src /*row l = src + l*ld*/,
+                                              int64_t ld, int l0, int L, const float* __restrict__ cs,
+                                              const float* __restrict__ sn) {
+  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+    const int r = i >> 2, c = i & 3;          // chunk c (dims 8c..8c+7) and its partner c + 4 (dims + 32)
+    const int l = l0 + r;
+    uint4 o1 = make_uint4(0, 0, 0, 0), o2 = o1;
+    if (l < L) {
+      const uint4 u1 = *reinterpret_cast<const uint4*>(src + (int64_t)l * ld + 8 * c);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(src + (int64_t)l * ld + 8 * c + 32);
+      float x1[8], x2[8], y1[8], y2[8];
+      unpack8(u1, x1);
+      unpack8(u2, x2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float co = cs[l * (kHd / 2) + 8 * c + j], si = sn[l * (kHd / 2) + 8 * c + j];
+        y1[j] = x1[j] * co - x2[j] * si;
+        y2[j] = x1[j] * si + x2[j] * co;
+      }
+      o1 = pack8(y1);
+      o2 = pack8(y2);
+    }
+    *reinterpret_cast<uint4*>(tile + swz(r, c)) = o1;
+    *reinterpret_cast<uint4*>(tile + swz(r, c + 4)) = o2;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+dit_attn_kernel(const __nv_bfloat16* __restrict__ qkv /*[N*L][3*H]*/, __nv_bfloat16* __restrict__ out /*[N*L][H]*/,
+                const float* __restrict__ cs, const float* __restrict__ sn, int L, int H) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(16) __nv_bfloat16 sQ[kQB * kHd];
+  __shared__ __align__(16) __nv_bfloat16 sK[kKB * kHd];
+  __shared__ __align__(16) __nv_bfloat16 sV[kKB * kHd];
+  const int q0 = blockIdx.x * kQB, head = blockIdx.y;
+  const int64_t seq = blockIdx.z;
+  const int64_t ld = 3 * (int64_t)H;
+  const __nv_bfloat16* base = qkv + seq * L * ld + head * kHd;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_rot_tile(sQ, base, ld, q0, L, cs, sn);
+  __syncthreads();
+  // Q fragments of this warp's 16 rows: 4 k-steps of 16 dims
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(smem_u32(sQ + swz(warp * 16 + (lane & 15), 2 * ks + (lane >> 4))), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  const float sc = 1.4426950408889634f * rsqrtf((float)kHd);    // log2(e) / sqrt(hd)
+
+  for (int k0 = 0; k0 < L; k0 += kKB) {
+    __syncthreads();                                              // previous block's fragments are consumed
+    load_rot_tile(sK, base + H, ld, k0, L, cs, sn);
+    for (int i = threadIdx.x; i < kKB * 8; i += blockDim.x) {
+      const int r = i >> 3, c = i & 7;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (k0 + r < L) u = *reinterpret_cast<const uint4*>(base + 2 * H + (int64_t)(k0 + r) * ld + 8 * c);
+      *reinterpret_cast<uint4*>(sV + swz(r, c)) = u;
+    }
+    __syncthreads();
+    // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t b0, b1, b2, b3;     // k-steps 2*half, 2*half+1
+        ldsm_x4(smem_u32(sK + swz(8 * j + (lane & 7), 4 * half + (lane >> 3))), b0, b1, b2, b3);
+        mma_bf16(s[j], qa[2 * half], b0, b1);
+        mma_bf16(s[j], qa[2 * half + 1], b2, b3);
+      }
+    }
+    // scale, mask the keys past L, online softmax (rows g and g + 8 of the warp's 16)
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + 8 * j + 2 * t;
+      s[j][0] = key < L ? s[j][0] * sc : -INFINITY;
+      s[j][1] = key + 1 < L ? s[j][1] * sc : -INFINITY;
+      s[j][2] = key < L ? s[j][2] * sc : -INFINITY;
+      s[j][3] = key + 1 < L ? s[j][3] * sc : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);     // 0 on the first block (m = -inf)
+    m0 = mx0; m1 = mx1;
+    float r0 = 0.0f, r1 = 0.0f;
+    uint32_t pa[4][4];                                           // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(s[j][0] - m0), p1 = exp2f(s[j][1] - m0);
+      const float p2 = exp2f(s[j][2] - m1), p3 = exp2f(s[j][3] - m1);
+      // the row sums use the bf16-rounded probabilities that enter the P V product
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
+      r0 += __low2float(h01) + __high2float(h01);
+      r1 += __low2float(h23) + __high2float(h23);
+      pa[j >> 1][(j & 1) * 2] = *reinterpret_cast<const uint32_t*>(&h01);
+      pa[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+    }
+    l0 = l0 * a0 + r0;
+    l1 = l1 * a1 + r1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    // O += P V: k = key (4 steps of 16), n = dim (8 tiles of 8); V^T fragments through ldmatrix.trans
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(sV + swz(16 * ks + (lane & 15), dn + (lane >> 4))), b0, b1, b2, b3);
+        mma_bf16(o[dn], pa[ks], b0, b1);
+        mma_bf16(o[dn + 1], pa[ks], b2, b3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+  __nv_bfloat16* ob = out + seq * L * (int64_t)H + head * kHd;
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    if (row0 < L)
+      *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * H + 8 * dn + 2 * t) = gemm_detail::pack_bf16x2(o[dn][0] * i0, o[dn][1] * i0);
+    if (row1 < L)
+      *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * H + 8 * dn + 2 * t) = gemm_detail::pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
+  }
+}
+
+}  // namespace dit
+}  // namespace svdd
+
+using namespace svdd;
+
+struct svdd_dit {
+  int H = 0, n_blocks = 0, n_heads = 0, V = 0, F = 0;
+  DeviceArena arena;
+  float* emb = nullptr;                       // [V][H]
+  __nv_bfloat16* wqkv[dit::kMaxBlocks];       // [3H][H]
+  __nv_bfloat16* wo[dit::kMaxBlocks];         // [H][H]
+  __nv_bfloat16* w1[dit::kMaxBlocks];         // [F][H]
+  __nv_bfloat16* w2[dit::kMaxBlocks];         // [H][F]
+  float* b1[dit::kMaxBlocks];                 // [F]
+  float* wout = nullptr;                      // [V][H]
+  float* bout = nullptr;                      // [V]
+  float* rot_cos = nullptr;                   // [kMaxLen][32]
+  float* rot_sin = nullptr;
+};
+
+extern "C" int svdd_dit_create(const svdd_tensor* tensors, int n_tensors, int n_heads, void* stream,
+                               svdd_dit** out) {
+  SVDD_CHECK_ARG(tensors && out && n_tensors > 0, "svdd_dit_create: null argument");
+  int dev = 0;
+  SVDD_CUDA(cudaGetDevice(&dev));
+  SVDD_TRY(svdd_device_check(dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  TensorTable tt{tensors, n_tensors};
+  const int V = (int)tt.dim("vocab_embed.embedding", 0), H = (int)tt.dim("vocab_embed.embedding", 1);
+  SVDD_CHECK_ARG(V == kVocab, "svdd_dit_create: vocab_embed.embedding must have %d rows, has %d", kVocab, V);
+  SVDD_CHECK_ARG(H > 0 && H % 128 == 0 && H <= 2048, "svdd_dit_create: hidden_size %d must be a multiple of 128, <= 2048", H);
+  SVDD_CHECK_ARG(n_heads > 0 && H == n_heads * dit::kHd, "svdd_dit_create: hidden_size / n_heads must be %d", dit::kHd);
+  int nb = 0;
+  while (nb < dit::kMaxBlocks && tt.has("blocks." + std::to_string(nb) + ".attn_qkv.weight")) ++nb;
+  SVDD_CHECK_ARG(nb > 0, "svdd_dit_create: no blocks.*.attn_qkv.weight tensors");
+  const int F = (int)tt.dim("blocks.0.mlp.0.weight", 0);
+  SVDD_CHECK_ARG(F > 0 && F % 128 == 0, "svdd_dit_create: mlp width %d must be a multiple of 128", F);
+  svdd_dit* h = new (std::nothrow) svdd_dit();
+  SVDD_CHECK_ARG(h != nullptr, "out of host memory");
+  h->H = H; h->n_blocks = nb; h->n_heads = n_heads; h->V = V; h->F = F;
+  DeviceArena& A = h->arena;
+  A.reserve(sizeof(float) * V * H);
+  for (int i = 0; i < nb; ++i) {
+    A.reserve(sizeof(__nv_bfloat16) * 3 * (size_t)H * H);
+    A.reserve(sizeof(__nv_bfloat16) * (size_t)H * H);
+    A.reserve(sizeof(__nv_bfloat16) * (size_t)F * H);
+    A.reserve(sizeof(__nv_bfloat16) * (size_t)H * F);
+    A.reserve(sizeof(float) * F);
+  }
+  A.reserve(sizeof(float) * V * H);
+  A.reserve(sizeof(float) * 8);
+  A.reserve(sizeof(float) * dit::kMaxLen * (dit::kHd / 2));
+  A.reserve(sizeof(float) * dit::kMaxLen * (dit::kHd / 2));
+  int rc = A.commit();
+  if (rc != SVDD_OK) { delete h; return rc; }
+  auto fail = [&](int code) { delete h; return code; };
+#define GET_OR_FAIL(var, name, numel)               \
+  const float* var = tt.get((name), (numel));       \
+  if (var == nullptr) return fail(SVDD_ERR_MISSING_TENSOR)
+#define TRY_OR_FAIL(expr)                           \
+  do { int _rc = (expr); if (_rc != SVDD_OK) return fail(_rc); } while (0)
+  h->emb = A.take<float>((size_t)V * H);
+  GET_OR_FAIL(emb, "vocab_embed.embedding", (int64_t)V * H);
+  TRY_OR_FAIL(copy_f32(emb, h->emb, (int64_t)V * H, st));
+  for (int i = 0; i < nb; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    h->wqkv[i] = A.take<__nv_bfloat16>(3 * (size_t)H * H);
+    h->wo[i] = A.take<__nv_bfloat16>((size_t)H * H);
+    h->w1[i] = A.take<__nv_bfloat16>((size_t)F * H);
+    h->w2[i] = A.take<__nv_bfloat16>((size_t)H * F);
+    h->b1[i] = A.take<float>(F);
+    GET_OR_FAIL(wqkv, p + "attn_qkv.weight", 3 * (int64_t)H * H);
+    GET_OR_FAIL(wo, p + "attn_out.weight", (int64_t)H * H);
+    GET_OR_FAIL(w1, p + "mlp.0.weight", (int64_t)F * H);
+    GET_OR_FAIL(b1, p + "mlp.0.bias", F);
+    GET_OR_FAIL(w2, p + "mlp.2.weight", (int64_t)H * F);
+    TRY_OR_FAIL(pack_conv_weight(wqkv, h->wqkv[i], 3 * H, H, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(wo, h->wo[i], H, H, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(w1, h->w1[i], F, H, 1, st));
+    TRY_OR_FAIL(pack_conv_weight(w2, h->w2[i], H, F, 1, st));
+    TRY_OR_FAIL(copy_f32(b1, h->b1[i], F, st));
+  }
+  h->wout = A.take<float>((size_t)V * H);
+  h->bout = A.take<float>(8);
+  h->rot_cos = A.take<float>(dit::kMaxLen * (dit::kHd / 2));
+  h->rot_sin = A.take<float>(dit::kMaxLen * (dit::kHd / 2));
+  GET_OR_FAIL(wout, "output_layer.linear.weight", (int64_t)V * H);
+  GET_OR_FAIL(bout, "output_layer.linear.bias", V);
+  GET_OR_FAIL(invf, "rotary_emb.inv_freq", dit::kHd / 2);
+  TRY_OR_FAIL(copy_f32(wout, h->wout, (int64_t)V * H, st));
+  TRY_OR_FAIL(copy_f32(bout, h->bout, V, st));
+  dit::dit_rotary_table_kernel<<<ceil_div(dit::kMaxLen * (dit::kHd / 2), 256), 256, 0, st>>>(invf, h->rot_cos, h->rot_sin,
+                                                                                           dit::kMaxLen);
+#undef GET_OR_FAIL
+#undef TRY_OR_FAIL
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("svdd_dit_create: %s", cudaGetErrorString(e));
+    return fail(SVDD_ERR_CUDA);
+  }
+  *out = h;
+  return SVDD_OK;
+}
+
+extern "C" void svdd_dit_destroy(svdd_dit* h) { delete h; }
+
+extern "C" int64_t svdd_dit_mod_floats(const svdd_dit* h) {
+  return h ? (int64_t)(dit::kModPerBlock * h->n_blocks + 2) * h->H : 0;
+}
+
+static int64_t dit_chunk_seqs(int L) {
+  const int64_t s = dit::kChunkRows / L;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" size_t svdd_dit_workspace_bytes(const svdd_dit* h, int64_t n_rows, int L) {
+  if (h == nullptr) return 0;
+  const int64_t cs = dit_chunk_seqs(L);
+  const size_t R = (size_t)((n_rows < cs ? n_rows : cs) * L) + 256;
+  return DeviceArena::align(R * h->H * sizeof(float)) + 2 * DeviceArena::align(R * h->H * sizeof(__nv_bfloat16)) +
+         DeviceArena::align(R * 3 * h->H * sizeof(__nv_bfloat16)) + DeviceArena::align(R * h->F * sizeof(__nv_bfloat16));
+}
+
+template <int NV>
+static int dit_launch_ln(const float* x, const float* g, const float* b, __nv_bfloat16* out, int64_t rows,
+                         cudaStream_t st) {
+  launch_k(dit::dit_ln_kernel<NV>, dim3((unsigned)ceil_div<int64_t>(rows, 8)), dim3(256), 0, st, 1, x, g, b, out, rows);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+static int dit_ln(int H, const float* x, const float* g, const float* b, __nv_bfloat16* out, int64_t rows,
+                  cudaStream_t st) {
+  switch (H / 128) {
+    case 1: return dit_launch_ln<1>(x, g, b, out, rows, st);
+    case 2: return dit_launch_ln<2>(x, g, b, out, rows, st);
+    case 3: return dit_launch_ln<3>(x, g, b, out, rows, st);
+    case 4: return dit_launch_ln<4>(x, g, b, out, rows, st);
+    case 6: return dit_launch_ln<6>(x, g, b, out, rows, st);
+    case 8: return dit_launch_ln<8>(x, g, b, out, rows, st);
+    case 12: return dit_launch_ln<12>(x, g, b, out, rows, st);
+    case 16: return dit_launch_ln<16>(x, g, b, out, rows, st);
+  }
+  set_last_error("svdd_dit: hidden_size %d is not one of 128 x {1,2,3,4,6,8,12,16}", H);
+  return SVDD_ERR_INVALID_ARGUMENT;
+}
+template <int NV>
+static int dit_launch_final(const svdd_dit* h, const float* x, const float* g, const float* b, float* logits,
+                            int64_t rows, cudaStream_t st) {
+  launch_k(dit::dit_final_kernel<NV, kVocab>, dim3((unsigned)ceil_div<int64_t>(rows, 8)), dim3(256), 0, st, 1, x, g, b,
+           (const float*)h->wout, (const float*)h->bout, logits, rows);
+  count_launch();
+  SVDD_LAUNCH_CHECK();
+  return SVDD_OK;
+}
+
+// mod (fp32, device, svdd_dit_mod_floats() elements): per block kModPerBlock vectors of H --
+//   [0] g1 = norm1.weight * (1 + scale_msa)   [1] b1 = shift_msa   [2] gate_msa        [3] zeros
+//   [4] g2 = norm2.weight * (1 + scale_mlp)   [5] b2 = shift_mlp   [6] gate_mlp        [7] gate_mlp * mlp.2.bias
+// then the final layer's [gf = norm_final.weight * (1 + scale), bf = shift].
+extern "C" int svdd_dit_forward(svdd_dit* h, const void* tokens, int tok_dtype, const float* mod, float* logits,
+                                int64_t n_rows, int L, void* ws, size_t ws_bytes, void* stream) {
+  SVDD_CHECK_ARG(h && tokens && mod && logits, "svdd_dit_forward: null pointer");
+  SVDD_CHECK_ARG(n_rows >= 0 && L >= 1 && L <= dit::kMaxLen, "svdd_dit_forward: bad shape (L <= %d)", dit::kMaxLen);
+  SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
+  if (n_rows == 0) return SVDD_OK;
+  if (ws_bytes < svdd_dit_workspace_bytes(h, n_rows, L) || ws == nullptr) {
+    set_last_error("svdd_dit_forward: workspace too small (%zu < %zu)", ws_bytes, svdd_dit_workspace_bytes(h, n_rows, L));
+    return SVDD_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->H, F = h->F;
+  const int64_t cs = dit_chunk_seqs(L);
+  const size_t tok_bytes = tok_dtype == SVDD_TOK_I64 ? 8 : 1;
+  auto gemm = [&](const void* A, const void* W, int64_t R, int K, int N, const EpiParams& ep) -> int {
+    GemmShape g;
+    g.S = 1; g.L = (int)R; g.L_in = (int)R; g.K = K; g.N = N; g.taps = 1; g.dil = 1; g.BL = 128; g.BS = 1;
+    return launch_conv_gemm(A, W, g, EPI_GENERIC, ep, st);
+  };
+  for (int64_t s0 = 0; s0 < n_rows; s0 += cs) {
+    const int64_t ns = (n_rows - s0 < cs) ? n_rows - s0 : cs;
+    const int64_t R = ns * L;
+    Workspace W(ws, ws_bytes);
+    float* x = W.take<float>((size_t)(R + 256) * H);
+    __nv_bfloat16* hn = W.take<__nv_bfloat16>((size_t)(R + 256) * H);
+    __nv_bfloat16* ao = W.take<__nv_bfloat16>((size_t)(R + 256) * H);
+    __nv_bfloat16* qkv = W.take<__nv_bfloat16>((size_t)(R + 256) * 3 * H);
+    __nv_bfloat16* u = W.take<__nv_bfloat16>((size_t)(R + 256) * F);
+    if (!W.ok()) { set_last_error("svdd_dit_forward: workspace carve failed"); return SVDD_ERR_WORKSPACE_TOO_SMALL; }
+    const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)s0 * L * tok_bytes;
+    {
+      const unsigned grid = (unsigned)ceil_div<int64_t>(R * (H / 4), 256);
+      if (tok_dtype == SVDD_TOK_I64)
+        launch_k(dit::dit_embed_kernel<int64_t>, dim3(grid), dim3(256), 0, st, 1, (const int64_t*)tok, (const float*)h->emb, x, R, H);
+      else
+        launch_k(dit::dit_embed_kernel<uint8_t>, dim3(grid), dim3(256), 0, st, 1, (const uint8_t*)tok, (const float*)h->emb, x, R, H);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+    }
+    for (int i = 0; i < h->n_blocks; ++i) {
+      const float* m = mod + (size_t)i * dit::kModPerBlock * H;
+      SVDD_TRY(dit_ln(H, x, m, m + H, hn, R, st));
+      {
+        EpiParams ep;
+        ep.out = qkv; ep.out_dtype = DT_BF16; ep.ld_out = 3 * H;
+        SVDD_TRY(gemm(hn, h->wqkv[i], R, H, 3 * H, ep));
+      }
+      launch_k(dit::dit_attn_kernel, dim3((unsigned)ceil_div(L, dit::kQB), (unsigned)h->n_heads, (unsigned)ns), dim3(128), 0, st, 1,
+               (const __nv_bfloat16*)qkv, ao, (const float*)h->rot_cos, (const float*)h->rot_sin, L, H);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
+      {
+        EpiParams ep;                               // x += gate_msa * (ao @ Wo^T)
+        ep.scale = m + 2 * H; ep.shift = m + 3 * H;
+        ep.res = x; ep.res_dtype = DT_F32; ep.ld_res = H;
+        ep.out = x; ep.out_dtype = DT_F32; ep.ld_out = H;
+        SVDD_TRY(gemm(ao, h->wo[i], R, H, H, ep));
+      }
+      SVDD_TRY(dit_ln(H, x, m + 4 * H, m + 5 * H, hn, R, st));
+      {
+        EpiParams ep;                               // u = gelu_tanh(hn @ W1^T + b1)
+        ep.bias = h->b1[i]; ep.act = ACT_GELU_TANH;
+        ep.out = u; ep.out_dtype = DT_BF16; ep.ld_out = F;
+        SVDD_TRY(gemm(hn, h->w1[i], R, H, F, ep));
+      }
+      {
+        EpiParams ep;                               // x += gate_mlp * (u @ W2^T + b2)
+        ep.scale = m + 6 * H; ep.shift = m + 7 * H;
+        ep.res = x; ep.res_dtype = DT_F32; ep.ld_res = H;
+        ep.out = x; ep.out_dtype = DT_F32; ep.ld_out = H;
+        SVDD_TRY(gemm(u, h->w2[i], R, F, H, ep));
+      }
+    }
+    const float* mf = mod + (size_t)h->n_blocks * dit::kModPerBlock * H;
+    float* lg = logits + (size_t)s0 * L * kVocab;
+    int rc = SVDD_ERR_INVALID_ARGUMENT;
+    switch (H / 128) {
+      case 1: rc = dit_launch_final<1>(h, x, mf, mf + H, lg, R, st); break;
+      case 2: rc = dit_launch_final<2>(h, x, mf, mf + H, lg, R, st); break;
+      case 3: rc = dit_launch_final<3>(h, x, mf, mf + H, lg, R, st); break;
+      case 4: rc = dit_launch_final<4>(h, x, mf, mf + H, lg, R, st); break;
+      case 6: rc = dit_launch_final<6>(h, x, mf, mf + H, lg, R, st); break;
+      case 8: rc = dit_launch_final<8>(h, x, mf, mf + H, lg, R, st); break;
+      case 12: rc = dit_launch_final<12>(h, x, mf, mf + H, lg, R, st); break;
+      case 16: rc = dit_launch_final<16>(h, x, mf, mf + H, lg, R, st); break;
+      default: set_last_error("svdd_dit: unsupported hidden_size %d", H);
+    }
+    SVDD_TRY(rc);
+  }
+  return SVDD_OK;
+}

@@ -27,7 +27,7 @@ import itertools
 import torch
 from torch import nn
 
-from . import _lib, denoiser, noise_schedule, value_nets
+from . import _lib, denoiser, dit, noise_schedule, value_nets
 
 
 class InjectedNoise:
@@ -68,13 +68,16 @@ class Diffusion(nn.Module):
     self.mask_index = self.vocab_size
     self.vocab_size += 1
     self.parameterization = config.parameterization
-    if config.backbone != 'cnn':
-      raise NotImplementedError(
-          f"backbone '{config.backbone}': only the CNN denoiser is on the decode "
-          'path (models/__init__.py comments the others out, SURVEY.md F7)')
     if self.parameterization != 'subs':
       raise NotImplementedError("only parameterization='subs' is built")
-    self.backbone = denoiser.CNNModel(config.model, alphabet_size=self.vocab_size, num_cls=3)
+    if config.backbone == 'cnn':                                   # diffusion_gosai.py:99-101
+      self.backbone = denoiser.CNNModel(config.model, alphabet_size=self.vocab_size, num_cls=3)
+    elif config.backbone == 'dit':                                 # diffusion_gosai.py:102-104
+      self.backbone = dit.DIT(config, vocab_size=self.vocab_size)
+    else:
+      raise NotImplementedError(
+          f"backbone '{config.backbone}': the decode path is built for 'cnn' and 'dit' "
+          '(diffusion_gosai.py:105-121 comments the others out, SURVEY.md F7)')
     self.T = config.T
     self.subs_masking = config.subs_masking
     self.noise = noise_schedule.get_noise(config)

@@ -364,6 +364,45 @@ def gen_dna_trajectories():
   save('dna_trajectories.npz', **out)
 
 
+def ref_dit(n_blocks, length=200, time_conditioning=False):
+  """The reference's Diffusion with ``backbone: dit`` cannot be constructed (models/__init__.py
+  comments ``dit`` out, diffusion_gosai.py:102-104 would raise AttributeError), so the golden
+  builds the reference's own ``models.dit.DIT`` with the same seed the svdd_b200 container uses
+  (helpers.build_dit: torch.manual_seed(44) then Diffusion(cfg) -> the backbone is the first
+  module constructed) and drives its sub-modules in the order of DIT.forward's body, whose
+  ``return x`` is missing in the reference (models/dit.py:355-366)."""
+  dit = ref_import.import_reference_dit()
+  NS = __import__('types').SimpleNamespace
+  cfg = NS(model=NS(hidden_size=768, cond_dim=128, n_blocks=n_blocks, n_heads=12, dropout=0.1,
+                    scale_by_sigma=True, length=length))
+  torch.manual_seed(44)
+  m = dit.DIT(cfg, vocab_size=5).eval()
+  helpers.perturb_dit_(m, 13)
+
+  def forward(indices, sigma):
+    x = m.vocab_embed(indices)
+    c = torch.nn.functional.silu(m.sigma_map(sigma))
+    rotary_cos_sin = m.rotary_emb(x)
+    for blk in m.blocks:
+      x = blk(x, rotary_cos_sin, c, seqlens=None)
+    return m.output_layer(x, c)
+  return m, forward
+
+
+def gen_dit():
+  out = {}
+  for tag, n_blocks, L, B, sigma in (('b2_L200', 2, 200, 3, 0.0), ('b12_L200', 12, 200, 2, 0.0),
+                                     ('b2_L50_sigma', 2, 50, 3, 0.7), ('b1_L333', 1, 333, 1, 0.0)):
+    m, fwd = ref_dit(n_blocks, L)
+    x = helpers.random_tokens(B, L, 500 + L + n_blocks, 0.5)
+    x[0] = 4
+    with torch.no_grad():
+      logits = fwd(x, torch.full((B,), sigma))
+    out[f'{tag}_tokens'], out[f'{tag}_logits'], out[f'{tag}_sigma'] = x, logits, np.float32(sigma)
+    out[f'{tag}_checksum'] = helpers.state_checksum(m.state_dict())
+  save('dit_seed44.npz', **out)
+
+
 def gen_ddpm_cache():
   """_sample with predictor 'ddpm_cache' (diffusion_gosai.py:755-773, 858-865): many small steps
   so that most steps leave the batch unchanged and reuse the cached p_x0."""
@@ -391,4 +430,5 @@ if __name__ == '__main__':
   gen_enformer_full()
   gen_trajectories()
   gen_dna_trajectories()
+  gen_dit()
   gen_ddpm_cache()

@@ -176,6 +176,32 @@ def import_reference():
                                Enformer=Enformer)
 
 
+def import_reference_dit():
+  """models/dit.py of the reference, importable on CPU: omegaconf is stubbed (absent here), and
+  the two flash-attn calls (CUDA / Triton only) are replaced by oracle/dit_shim.py's restatements
+  inside the imported module.  The reference's ``models/__init__.py`` does not import ``dit``
+  (it is commented out), hence the explicit import."""
+  import_reference()
+  import importlib
+  if 'omegaconf' not in sys.modules:
+    try:
+      import omegaconf  # noqa: F401
+    except ImportError:
+      _mod('omegaconf', OmegaConf=types.SimpleNamespace(create=lambda d: d))
+  from oracle import dit_shim
+  sys.path.insert(0, REF_ROOT)
+  try:
+    dit = importlib.import_module('models.dit')
+  finally:
+    sys.path.remove(REF_ROOT)
+  rot = types.SimpleNamespace(apply_rotary_emb_qkv_=dit_shim.apply_rotary_emb_qkv_)
+  dit.flash_attn = types.SimpleNamespace(
+      layers=types.SimpleNamespace(rotary=rot),
+      flash_attn_interface=types.SimpleNamespace(
+          flash_attn_varlen_qkvpacked_func=dit_shim.flash_attn_varlen_qkvpacked_func))
+  return dit
+
+
 def make_config(length=200, hidden_dim=128, num_cnn_stacks=4, steps=128,
                 predictor='ddpm', eval_batch_size=8, time_conditioning=False):
   """The subset of the hydra config tree that ``Diffusion`` reads

@@ -22,7 +22,7 @@ from svdd_b200.synthetic import build_convgru_oracle, build_convgru_value, build
 from svdd_b200 import synthetic  # noqa: E402
 
 
-from svdd_b200.synthetic import build_enformer, svdd_step_candidates  # noqa: E402,F401
+from svdd_b200.synthetic import build_dit, build_enformer, perturb_dit_, svdd_step_candidates  # noqa: E402,F401
 
 
 def load_golden(name):

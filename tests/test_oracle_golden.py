@@ -227,3 +227,23 @@ def test_dna_trajectories_mc_and_pm():
   np.testing.assert_array_equal(a.numpy(), g['step_mc_next'])
   np.testing.assert_array_equal(b.numpy(), g['step_pm_next'])
   np.testing.assert_array_equal(c.numpy(), g['step_pm_raw_next'])
+
+
+DIT_CASES = (('b2_L200', 2, 200), ('b12_L200', 12, 200), ('b2_L50_sigma', 2, 50), ('b1_L333', 1, 333))
+
+
+def test_dit_backbone_matches_reference_modules():
+  """F4: the DiT denoiser (models/dit.py).  The goldens drive the reference's own DIT sub-modules
+  (flash-attn's two CUDA-only calls restated in oracle/dit_shim.py); the oracle's functional
+  forward over the svdd_b200 container's seeded state_dict reproduces them, incl. time
+  conditioning (sigma = 0.7) and a length that is not a multiple of the attention tiles."""
+  g = helpers.load_golden('dit_seed44.npz')
+  for tag, nb, L in DIT_CASES:
+    m = helpers.build_dit(n_blocks=nb, length=L)
+    sd = m.state_dict()
+    np.testing.assert_array_equal(
+        helpers.state_checksum({k[len('backbone.'):]: v for k, v in sd.items()}), g[f'{tag}_checksum'])
+    x = T(g[f'{tag}_tokens'])
+    with torch.no_grad():
+      o = nets.dit_logits(sd, x, torch.full((x.shape[0],), float(g[f'{tag}_sigma'])))
+    np.testing.assert_allclose(o.numpy(), g[f'{tag}_logits'], rtol=0, atol=2e-5, err_msg=tag)
