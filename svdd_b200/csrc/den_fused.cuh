@@ -69,11 +69,22 @@ struct Args {
   int a_rows;                // rows of one operand plane (multiple of 8)
   int two_seq;               // L <= 64: tile m holds sequence (2*iter + m)
   int split;                 // two_seq only: two epilogue threads per row (64 channels each)
+  // two_seq + split: COMBINED mode.  A second pair of operand planes holds BOTH sequences of the
+  // item 64 rows apart (A rows 0..L-1, B rows 64..64+L-1) so that ONE 128-row MMA per tap serves
+  // both, for every tap whose offset fits the zero gap between them (|o| <= 64 - L).  Taps with
+  // larger offsets keep one MMA per sequence on the isolated planes and accumulate into their own
+  // TMEM columns (the rows of the other sequence hold garbage there and are never read).
+  int cmb;                   // combined mode on
+  int cmb_max;               // largest |tap offset| served by the combined planes
+  int pad_c;                 // zero rows in front of a combined plane
+  int c_rows;                // rows of one combined plane (multiple of 8)
+  int iso_b;                 // isolated planes: row distance between the two sequences (legacy: 128)
+  unsigned char iso[kMaxLayers + 1];   // round r has taps on the isolated planes
   int dil[kMaxLayers];
 };
 
-__host__ __device__ inline int smem_bytes(int a_rows) {
-  return 2 * a_rows * 128 + kStages * kStageBytes + kParamBytes + kW2Bytes + kXchBytes + kBarBytes + 1024;
+__host__ __device__ inline int smem_bytes(int a_rows, int c_rows = 0) {
+  return 2 * (a_rows + c_rows) * 128 + kStages * kStageBytes + kParamBytes + kW2Bytes + kXchBytes + kBarBytes + 1024;
 }
 
 // tile m of the CTA's work item: first row in sequence coordinates
@@ -130,8 +141,10 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int plane_bytes = a.a_rows * 128;
+  const int c_plane_bytes = a.cmb ? a.c_rows * 128 : 0;
   uint8_t* s_a = smem;                                   // [2 K halves][a_rows][64 bf16], 128B swizzle
-  uint8_t* s_ring = smem + 2 * plane_bytes;              // [kStages][128 x 64 bf16]
+  uint8_t* s_c = smem + 2 * plane_bytes;                 // combined planes [2 K halves][c_rows][64 bf16] (cmb mode)
+  uint8_t* s_ring = s_c + 2 * c_plane_bytes;             // [kStages][128 x 64 bf16]
   float* s_param = reinterpret_cast<float*>(s_ring + kStages * kStageBytes);
   float* s_w2 = s_param + kParamBytes / 4;               // [5][128] + b2[5]
   float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_w2) + kW2Bytes);
@@ -165,7 +178,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     ptx::tmem_relinquish();
   }
   // zero the operand planes once: pad rows and rows >= L are never written afterwards
-  for (int i = threadIdx.x; i < 2 * plane_bytes / 16; i += kThreads)
+  for (int i = threadIdx.x; i < 2 * (plane_bytes + c_plane_bytes) / 16; i += kThreads)
     reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < kVocab * kH; i += kThreads) s_w2[i] = a.fc2_w[i];
   if (threadIdx.x < kVocab) s_w2[kVocab * kH + threadIdx.x] = a.fc2_b[threadIdx.x];
@@ -221,6 +234,46 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         ptx::tc_fence_after();
         const int taps = r < nl ? kTaps : 1;
         const int dil = r < nl ? a.dil[r] : 1;
+        if (a.cmb) {
+          // combined mode: acc0 (cols 0..127) <- taps on the combined planes, both sequences;
+          // cols 256.. <- sequence A's isolated taps, cols 128.. <- sequence B's
+          const uint32_t c_base = ptx::smem_u32(s_c);
+          uint32_t st_c = 0u, st_a = 0u, st_b = 0u;
+          for (int t = 0; t < taps; ++t) {
+            const int o = (t - taps / 2) * dil;
+            if (!(o > -L && o < L)) continue;
+            const bool comb = (o < 0 ? -o : o) <= a.cmb_max;
+            for (int kb = 0; kb < 2; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
+                if (comb) {
+                  const uint64_t da = ptx::make_kmajor_sw128_desc(c_base + kb * c_plane_bytes + (uint32_t)(a.pad_c + o) * 128u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (st_c | (uint32_t)k) != 0u);
+                } else {
+                  const uint64_t da0 = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes + (uint32_t)(a.pad_before + o) * 128u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_base + 2 * kH, da0 + 2 * k, db + 2 * k, idesc, (st_a | (uint32_t)k) != 0u);
+                  if (live1) {
+                    const uint64_t da1 = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes +
+                                                                     (uint32_t)(a.pad_before + a.iso_b - 64 + o) * 128u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      ptx::umma_bf16(tmem_base + kH, da1 + 2 * k, db + 2 * k, idesc, (st_b | (uint32_t)k) != 0u);
+                  }
+                }
+                ptx::umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              if (comb) st_c = 1u; else { st_a = 1u; st_b = 1u; }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
         uint32_t started[2] = {0u, 0u};
         for (int t = 0; t < taps; ++t) {
           const int o = (t - taps / 2) * dil;
@@ -250,6 +303,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             started[1] |= hit1 ? 1u : 0u;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+        }
         }
         if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
         __syncwarp();
@@ -473,11 +527,15 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int m = quad >> 1;
     const int etid = threadIdx.x - 64;
     const int row = (quad & 1) * 32 + lane;                      // position within the sequence
-    const int arow = a.pad_before + 128 * m + row;
-    const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + m * kH + half * 64;
-    const uint32_t t_res = t_acc + 2 * kH;
+    const bool cmb = a.cmb != 0;
+    const int arow = a.pad_before + a.iso_b * m + row;           // isolated planes (pad_before, iso_b: multiples of 8)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_acc = t_lane + (cmb ? 0 : m * kH) + half * 64;
+    const uint32_t t_iso = t_lane + (m == 0 ? 2 * kH : kH) + half * 64;       // cmb: this sequence's isolated taps
+    const uint32_t t_res = cmb ? t_lane + 3 * kH + half * 64 : t_acc + 2 * kH;   // cmb: one block, lanes 0..63 / 64..127
     uint8_t* a_rowh = s_a + (size_t)half * plane_bytes + (size_t)arow * 128;
-    const int x7 = arow & 7;
+    uint8_t* c_rowh = s_c + (size_t)half * c_plane_bytes + (size_t)(a.pad_c + 64 * m + row) * 128;   // combined planes
+    const int x7 = arow & 7;                                     // == row & 7 on both kinds of plane
     const bool wact = (row - lane) < L;
     const int ch0 = half * 64;
     const Tok* tokens = reinterpret_cast<const Tok*>(a.tokens);
@@ -487,7 +545,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     auto xch_mine = [&](int par) { return s_xch + ((size_t)par * kEpiThreads + etid) * 8; };
     auto xch_peer = [&](int par) { return s_xch + ((size_t)par * kEpiThreads + (etid ^ 128)) * 8; };
 
-    auto write_operand = [&](float* v, const float* P, bool ln, bool valid) {
+    auto write_operand = [&](float* v, const float* P, bool ln, bool valid, bool to_iso, bool to_cmb) {
       if (ln) {
         float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -521,10 +579,12 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       }
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)          // 16-byte chunk j of this K half's 128-byte row
-          ptx::sts128(a_rowh + ((j ^ x7) << 4),
-                      make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7])));
+        for (int j = 0; j < 8; ++j) {        // 16-byte chunk j of this K half's 128-byte row
+          const uint4 u = make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          if (to_iso) ptx::sts128(a_rowh + ((j ^ x7) << 4), u);
+          if (to_cmb) ptx::sts128(c_rowh + ((j ^ x7) << 4), u);
+        }
       }
     };
     auto stage_params = [&](int r, float* P) {
@@ -585,7 +645,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             }
             tmem_st_32x32(t_res + c * 32, raw);
           }
-          write_operand(v, P, true, valid);
+          write_operand(v, P, true, valid, !cmb || a.iso[0] != 0, cmb);
           tmem_st_wait();
         }
         ptx::fence_proxy_async_smem();
@@ -608,6 +668,17 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           ptx::tmem_ld_32x32(t_acc + 32, racc[1]);
           ptx::tmem_ld_32x32(t_res + 32, rres[1]);
           ptx::tmem_ld_wait();
+          if (cmb && a.iso[r]) {             // this round also ran taps on the isolated planes
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t riso[32];
+              ptx::tmem_ld_32x32(t_iso + 32 * c, riso);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                racc[c][i] = __float_as_uint(__uint_as_float(racc[c][i]) + __uint_as_float(riso[i]));
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float pb[32];
@@ -620,7 +691,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             }
             tmem_st_32x32(t_res + c * 32, rres[c]);
           }
-          write_operand(v, P, r + 1 < nl, valid);
+          write_operand(v, P, r + 1 < nl, valid, !cmb || a.iso[r + 1] != 0, cmb);
           tmem_st_wait();
         }
         ptx::fence_proxy_async_smem();

@@ -225,7 +225,36 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
       }
   a.pad_before = pad_before;
   a.a_rows = (pad_before + max_end + 7) & ~7;
-  const int smem = denf::smem_bytes(a.a_rows);
+  a.iso_b = 128;
+  int smem = denf::smem_bytes(a.a_rows);
+  // Combined mode (two sequences per CTA, split epilogue): ONE 128-row MMA per tap for both
+  // sequences on a second pair of planes where they sit 64 rows apart, for taps whose offset fits the
+  // zero gap (|o| <= 64 - L); the other taps stay on the isolated planes.  L = 50: 173 instead of 281
+  // MMA groups per item.  SVDD_DEN_CMB=0 (read per call) keeps the two-tile scheme for the A/B test.
+  const char* env_cmb = getenv("SVDD_DEN_CMB");
+  if (a.split && !(env_cmb && atoi(env_cmb) == 0)) {
+    denf::Args c = a;
+    c.cmb = 1;
+    c.cmb_max = 64 - L;
+    c.pad_c = (c.cmb_max + 7) & ~7;
+    c.c_rows = c.pad_c + 128 + c.pad_c;
+    c.iso_b = ((2 * L + 7) & ~7) < 64 ? 64 : ((2 * L + 7) & ~7);
+    int max_iso = 0;
+    for (int i = 0; i <= h->n_layers; ++i) {
+      c.iso[i] = 0;
+      if (i == h->n_layers) break;
+      for (int t = 0; t < kTaps; ++t) {
+        const int o = (t - kTaps / 2) * h->dil[i], ao = o < 0 ? -o : o;
+        if (ao < L && ao > c.cmb_max) { c.iso[i] = 1; if (ao > max_iso) max_iso = ao; }
+      }
+    }
+    c.pad_before = (max_iso + 7) & ~7;
+    // rows the VALID lanes of either sequence read; the garbage lanes of an isolated MMA may read up
+    // to 128 rows further, into the memory that follows the plane (legal, never consumed)
+    c.a_rows = max_iso > 0 ? ((c.pad_before + c.iso_b + L + max_iso + 7) & ~7) : 8;
+    const int smem_c = denf::smem_bytes(c.a_rows, c.c_rows);
+    if (smem_c <= 227 * 1024) { a = c; smem = smem_c; }
+  }
   if (smem > 227 * 1024) return SVDD_ERR_INTERNAL;
   a.tokens = tokens;
   a.embed_w = h->embed_w; a.embed_b = h->embed_b;
