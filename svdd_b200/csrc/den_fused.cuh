@@ -134,8 +134,13 @@ __device__ __forceinline__ void ld_param32(const float* p, float* v) {
                  : "r"(a + 16u * i));
 }
 
-template <typename Tok>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = epilogue warps.  8: thread = one row (or half a row, `split`).  16 (two sequences per CTA in
+// combined mode only): thread = a QUARTER of a row (32 channels), four warps per TMEM lane quadrant
+// -- the epilogue of a round is a latency chain (tensor-memory loads, LayerNorm statistics through
+// shared memory, operand stores, barrier hops), and four warps per scheduler hide it better than
+// two; <= 112 registers per thread.
+template <typename Tok, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -170,7 +175,7 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         ptx::mbar_init(&empty_bar[i], 1);
       }
       ptx::mbar_init(tfull_bar, 1);
-      ptx::mbar_init(aready_bar, kEpiWarps);
+      ptx::mbar_init(aready_bar, EW);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -178,9 +183,9 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     ptx::tmem_relinquish();
   }
   // zero the operand planes once: pad rows and rows >= L are never written afterwards
-  for (int i = threadIdx.x; i < 2 * (plane_bytes + c_plane_bytes) / 16; i += kThreads)
+  for (int i = threadIdx.x; i < 2 * (plane_bytes + c_plane_bytes) / 16; i += 64 + 32 * EW)
     reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < kVocab * kH; i += kThreads) s_w2[i] = a.fc2_w[i];
+  for (int i = threadIdx.x; i < kVocab * kH; i += 64 + 32 * EW) s_w2[i] = a.fc2_w[i];
   if (threadIdx.x < kVocab) s_w2[kVocab * kH + threadIdx.x] = a.fc2_b[threadIdx.x];
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
@@ -307,6 +312,232 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
         __syncwarp();
+      }
+    }
+  } else if constexpr (EW == 16) {
+    // ===================== quad epilogue (combined mode, 16 warps) =====================
+    // TMEM lane quadrant q = warp & 3 holds rows 32 (q & 1) .. +31 of sequence q >> 1; the four
+    // warps that can reach a quadrant split the 128 channels in slices of 32.  LayerNorm statistics
+    // of the four slices are combined through shared memory (Chan's update for four groups of 32)
+    // behind one 128-thread named barrier per round.
+    constexpr int kET = 32 * EW;
+    const int ew = warp - 2;
+    const int slice = ew >> 2;               // channels 32 * slice .. +31
+    const int quad = warp & 3;
+    const int m = quad >> 1;
+    const int etid = threadIdx.x - 64;       // slice == etid >> 7
+    const int row = (quad & 1) * 32 + lane;
+    const int arow = a.pad_before + a.iso_b * m + row;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_acc = t_lane + slice * 32;
+    const uint32_t t_iso = t_lane + (m == 0 ? 2 * kH : kH) + slice * 32;
+    const uint32_t t_res = t_lane + 3 * kH + slice * 32;
+    const int kh = slice >> 1, cj0 = (slice & 1) * 4;          // K half and first 16-byte chunk of this slice
+    uint8_t* a_rowh = s_a + (size_t)kh * plane_bytes + (size_t)arow * 128;
+    uint8_t* c_rowh = s_c + (size_t)kh * c_plane_bytes + (size_t)(a.pad_c + 64 * m + row) * 128;
+    const int x7 = arow & 7;
+    const bool wact = (row - lane) < L;
+    const int ch0 = slice * 32;
+    const Tok* tokens = reinterpret_cast<const Tok*>(a.tokens);
+    float* s_lgx = s_xch + 2 * kET * 2;                        // logits exchange [3 slices][128 rows][5]
+    uint32_t tphase = 0;
+    int xpar = 0;
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kET) : "memory"); };
+    auto grp_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); };
+
+    auto write_operand = [&](float* v, const float* P, bool ln, bool valid, bool to_iso) {
+      if (ln) {
+        float pt[32];
+        ld_param32(P + 1 * kH + ch0, pt);
+        float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] += pt[i]; s4[i & 3] += v[i]; }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        const float ml = sum * (1.0f / 32);
+        float q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float d = v[i] - ml; q4[i & 3] += d * d; }
+        const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        float* mine = s_xch + ((size_t)xpar * kET + etid) * 2;
+        *reinterpret_cast<float2*>(mine) = make_float2(sum, m2);
+        grp_sync();
+        float2 o[3];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          o[k - 1] = *reinterpret_cast<const float2*>(s_xch + ((size_t)xpar * kET + (etid ^ (k << 7))) * 2);
+        xpar ^= 1;
+        const float mean = ((sum + o[0].x) + (o[1].x + o[2].x)) * (1.0f / kH);
+        float var = (m2 + o[0].y) + (o[1].y + o[2].y);
+        {
+          const float d0 = ml - mean, d1 = o[0].x * (1.0f / 32) - mean, d2 = o[1].x * (1.0f / 32) - mean,
+                      d3 = o[2].x * (1.0f / 32) - mean;
+          var += 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+        }
+        const float rstd = rsqrtf(var * (1.0f / kH) + 1e-5f);
+        float pg[32];
+        ld_param32(P + 2 * kH + ch0, pg);
+        ld_param32(P + 3 * kH + ch0, pt);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * pg[i] + pt[i];
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          ptx::sts128(c_rowh + (((cj0 + j) ^ x7) << 4), u);
+          if (to_iso) ptx::sts128(a_rowh + (((cj0 + j) ^ x7) << 4), u);
+        }
+      }
+    };
+    auto stage_params = [&](int r, float* P) {
+      for (int i = etid; i < kH; i += kET) {
+        P[i] = r < nl ? a.conv_b[r * kH + i] : a.fc0_b[i];
+        if (r + 1 < nl) {
+          P[1 * kH + i] = a.time_bias[(r + 1) * kH + i];
+          P[2 * kH + i] = a.ln_g[(r + 1) * kH + i];
+          P[3 * kH + i] = a.ln_b[(r + 1) * kH + i];
+        }
+      }
+    };
+
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t seq = 2 * it + m;
+      const bool valid = (seq < a.n_rows) && (row < L);
+      {
+        float* P = s_param;
+        for (int i = etid; i < kH; i += kET) {
+          P[1 * kH + i] = a.time_bias[i];
+          P[2 * kH + i] = a.ln_g[i];
+          P[3 * kH + i] = a.ln_b[i];
+        }
+        epi_sync();
+        if (wact) {
+          float v[32];
+          int tk[kTaps];
+#pragma unroll
+          for (int t = 0; t < kTaps; ++t) {
+            const int li = row + t - kTaps / 2;
+            tk[t] = (valid && li >= 0 && li < L) ? load_tok(tokens, (size_t)seq * L + li) : -1;
+          }
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(a.embed_b + ch0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = __ldg(b4 + i);
+              v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+            }
+#pragma unroll
+            for (int t = 0; t < kTaps; ++t) {
+              if (tk[t] >= 0) {
+                const float4* w4 = reinterpret_cast<const float4*>(a.embed_w + (t * kVocab + tk[t]) * kH + ch0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 f = __ldg(w4 + i);
+                  v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                }
+              }
+            }
+            uint32_t raw[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = fmaxf(v[i], 0.0f);
+              raw[i] = __float_as_uint(v[i]);
+            }
+            tmem_st_32x32(t_res, raw);
+          }
+          write_operand(v, P, true, valid, a.iso[0] != 0);
+          tmem_st_wait();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(aready_bar);
+      }
+      for (int r = 0; r < nl; ++r) {
+        float* P = s_param + ((r + 1) & 1) * (4 * kH);
+        stage_params(r, P);
+        epi_sync();
+        ptx::mbar_wait(tfull_bar, tphase);
+        tphase ^= 1;
+        ptx::tc_fence_after();
+        if (wact) {
+          float v[32];
+          uint32_t racc[32], rres[32];
+          ptx::tmem_ld_32x32(t_acc, racc);
+          ptx::tmem_ld_32x32(t_res, rres);
+          ptx::tmem_ld_wait();
+          if (a.iso[r]) {
+            uint32_t riso[32];
+            ptx::tmem_ld_32x32(t_iso, riso);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[i] = __float_as_uint(__uint_as_float(racc[i]) + __uint_as_float(riso[i]));
+          }
+          {
+            float pb[32];
+            ld_param32(P + ch0, pb);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(rres[i]) + fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
+              v[i] = f;
+              rres[i] = __float_as_uint(f);
+            }
+            tmem_st_32x32(t_res, rres);
+          }
+          write_operand(v, P, r + 1 < nl, valid, a.iso[r + 1] != 0);
+          tmem_st_wait();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(aready_bar);
+      }
+      {
+        float* P = s_param + ((nl + 1) & 1) * (4 * kH);
+        stage_params(nl, P);
+        epi_sync();
+        ptx::mbar_wait(tfull_bar, tphase);
+        tphase ^= 1;
+        ptx::tc_fence_after();
+        if (wact) {
+          float lg[kVocab];
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) lg[j] = 0.0f;
+          {
+            uint32_t racc[32];
+            ptx::tmem_ld_32x32(t_acc, racc);
+            ptx::tmem_ld_wait();
+            float pb[32];
+            ld_param32(P + ch0, pb);
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(__uint_as_float(racc[i]) + pb[i], 0.0f);
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j) {
+              float w[32];
+              ld_param32(s_w2 + j * kH + ch0, w);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) lg[j] += y[i] * w[i];
+            }
+          }
+          const int qrow = quad * 32 + lane;
+          if (slice > 0) {
+            float* x = s_lgx + ((size_t)(slice - 1) * 128 + qrow) * kVocab;
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j) x[j] = lg[j];
+          }
+          grp_sync();
+          if (slice == 0 && valid) {
+            float* o = a.logits + ((size_t)seq * L + row) * kVocab;
+#pragma unroll
+            for (int j = 0; j < kVocab; ++j)
+              o[j] = ((lg[j] + s_lgx[(size_t)qrow * kVocab + j]) +
+                      (s_lgx[(size_t)(128 + qrow) * kVocab + j] + s_lgx[(size_t)(256 + qrow) * kVocab + j])) + s_w2[kVocab * kH + j];
+          }
+          grp_sync();                        // the exchange area is reused by the next item
+        }
+        ptx::tc_fence_before();
       }
     }
   } else if (!a.split) {

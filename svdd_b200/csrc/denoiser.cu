@@ -269,14 +269,24 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
   SVDD_TRY(encode_tmap_2d_bf16(&tmW0, h->fc0_w, kH, kH, 64, kH));
   const int64_t items = a.two_seq ? (n_rows + 1) / 2 : n_rows;
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+  // SVDD_DEN_EW=16 (read per call): combined mode with the 16-warp quad epilogue (thread = quarter
+  // of a row).  Measured SLOWER than the 8-warp split epilogue -- 27.9 vs 24.2 ms per 51200 x 50 pass,
+  // 0.61 vs 0.54 ms at 999 x 33: the round is a chain of fixed latencies (accumulator hand-over,
+  // named barrier, async-proxy fence, two mbarrier hops), not a shortage of warps to hide them, and
+  // the 640-thread CTA caps the kernel at 96 registers (spills).  Kept with its test.
+  const char* env_ew = getenv("SVDD_DEN_EW");
+  const bool ew16 = a.cmb && env_ew && atoi(env_ew) == 16;
+  auto launch = [&](auto kern, int threads) -> int {
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SVDD_CUDA(launch_k(kern, dim3(grid), dim3((unsigned)threads), (size_t)smem, st, 1, tmW, tmW0, a));
+    return SVDD_OK;
+  };
   if (tok_dtype == SVDD_TOK_I64) {
-    auto kern = denf::den_fused_kernel<int64_t>;
-    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SVDD_CUDA(launch_k(kern, dim3(grid), dim3(denf::kThreads), (size_t)smem, st, 1, tmW, tmW0, a));
+    if (ew16) SVDD_TRY(launch(denf::den_fused_kernel<int64_t, 16>, 64 + 32 * 16));
+    else SVDD_TRY(launch(denf::den_fused_kernel<int64_t, 8>, denf::kThreads));
   } else {
-    auto kern = denf::den_fused_kernel<uint8_t>;
-    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SVDD_CUDA(launch_k(kern, dim3(grid), dim3(denf::kThreads), (size_t)smem, st, 1, tmW, tmW0, a));
+    if (ew16) SVDD_TRY(launch(denf::den_fused_kernel<uint8_t, 16>, 64 + 32 * 16));
+    else SVDD_TRY(launch(denf::den_fused_kernel<uint8_t, 8>, denf::kThreads));
   }
   count_launch();
   return SVDD_OK;

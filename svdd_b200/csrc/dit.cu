@@ -351,6 +351,173 @@ dit_attn_kernel(const __nv_bfloat16* __restrict__ qkv /*[N*L][3*H]*/, __nv_bfloa
   }
 }
 
+
+// ---- attention, whole sequence resident (L <= 256) -----------------------------------------
+// One CTA = one (sequence, head): K (rotated) and V are staged in shared memory ONCE, then the
+// eight warps walk the 16-row query strips (strip = warp, warp + 8, ...), each warp staging and
+// rotating its own strip (no block barrier after the K / V load).  The streaming kernel above
+// reloaded and re-rotated K for every 64-query block and paid two block barriers plus a round of
+// synchronous global loads per 64 keys: 31 ms of the 85 ms forward at n = 1408, L = 200.
+constexpr int kAttnSmallMaxL = 256;
+constexpr int kAttnSmallWarps = 8;
+constexpr int kAttnSmallSmem = (2 * kAttnSmallMaxL + kAttnSmallWarps * 16) * kHd * 2;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// rotates one (row, chunk c | chunk c + 4) pair of a q / k row and stores it swizzled
+__device__ __forceinline__ void rot_store(__nv_bfloat16* tile, int r, int c, const __nv_bfloat16* src_row,
+                                          const float* __restrict__ cs_row, const float* __restrict__ sn_row, bool live) {
+  uint4 o1 = make_uint4(0, 0, 0, 0), o2 = o1;
+  if (live) {
+    const uint4 u1 = *reinterpret_cast<const uint4*>(src_row + 8 * c);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(src_row + 8 * c + 32);
+    const float4 ca = __ldg(reinterpret_cast<const float4*>(cs_row + 8 * c)), cb = __ldg(reinterpret_cast<const float4*>(cs_row + 8 * c) + 1);
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(sn_row + 8 * c)), sb = __ldg(reinterpret_cast<const float4*>(sn_row + 8 * c) + 1);
+    const float co[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    const float si[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    float x1[8], x2[8], y1[8], y2[8];
+    unpack8(u1, x1);
+    unpack8(u2, x2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y1[j] = x1[j] * co[j] - x2[j] * si[j];
+      y2[j] = x1[j] * si[j] + x2[j] * co[j];
+    }
+    o1 = pack8(y1);
+    o2 = pack8(y2);
+  }
+  *reinterpret_cast<uint4*>(tile + swz(r, c)) = o1;
+  *reinterpret_cast<uint4*>(tile + swz(r, c + 4)) = o2;
+}
+
+__global__ void __launch_bounds__(kAttnSmallWarps * 32)
+dit_attn_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                      const float* __restrict__ cs, const float* __restrict__ sn, int L, int H) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(dsm);
+  __nv_bfloat16* sV = sK + kAttnSmallMaxL * kHd;
+  __nv_bfloat16* sQ = sV + kAttnSmallMaxL * kHd;                      // [warp][16][64]
+  const int head = blockIdx.x;
+  const int64_t seq = blockIdx.y;
+  const int64_t ld = 3 * (int64_t)H;
+  const __nv_bfloat16* base = qkv + seq * L * ld + head * kHd;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Lk = (L + 63) & ~63;                                      // keys padded to whole 64-key tiles (zero rows)
+
+  for (int i = threadIdx.x; i < Lk * 4; i += blockDim.x) {
+    const int r = i >> 2, c = i & 3;
+    rot_store(sK, r, c, base + H + (int64_t)r * ld, cs + r * (kHd / 2), sn + r * (kHd / 2), r < L);
+  }
+  for (int i = threadIdx.x; i < Lk * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < L) u = *reinterpret_cast<const uint4*>(base + 2 * H + (int64_t)r * ld + 8 * c);
+    *reinterpret_cast<uint4*>(sV + swz(r, c)) = u;
+  }
+  __syncthreads();
+
+  __nv_bfloat16* myQ = sQ + warp * 16 * kHd;
+  const float sc = 1.4426950408889634f * rsqrtf((float)kHd);
+  __nv_bfloat16* ob = out + seq * L * (int64_t)H + head * kHd;
+  for (int q0 = warp * 16; q0 < L; q0 += kAttnSmallWarps * 16) {
+    __syncwarp();
+    for (int i = lane; i < 16 * 4; i += 32) {
+      const int r = i >> 2, c = i & 3, l = q0 + r;
+      rot_store(myQ, r, c, base + (int64_t)l * ld, cs + l * (kHd / 2), sn + l * (kHd / 2), l < L);
+    }
+    __syncwarp();
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldsm_x4(smem_u32(myQ + swz(lane & 15, 2 * ks + (lane >> 4))), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    for (int k0 = 0; k0 < Lk; k0 += 64) {
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(smem_u32(sK + swz(k0 + 8 * j + (lane & 7), 4 * half + (lane >> 3))), b0, b1, b2, b3);
+          mma_bf16(s[j], qa[2 * half], b0, b1);
+          mma_bf16(s[j], qa[2 * half + 1], b2, b3);
+        }
+      }
+      // m0 / m1 hold the running max of the RAW scores; the softmax scale rides in the exponent's FMA
+      float mx0 = m0, mx1 = m1;
+      if (k0 + 64 > L) {                      // last tile: keys past L are masked out
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = k0 + 8 * j + 2 * t;
+          if (key >= L) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (key + 1 >= L) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float a0 = ex2_approx((m0 - mx0) * sc), a1 = ex2_approx((m1 - mx1) * sc);
+      m0 = mx0; m1 = mx1;
+      const float ms0 = -m0 * sc, ms1 = -m1 * sc;
+      float r0 = 0.0f, r1 = 0.0f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(ex2_approx(fmaf(s[j][0], sc, ms0)), ex2_approx(fmaf(s[j][1], sc, ms0)));
+        const __nv_bfloat162 h23 = __floats2bfloat162_rn(ex2_approx(fmaf(s[j][2], sc, ms1)), ex2_approx(fmaf(s[j][3], sc, ms1)));
+        r0 += __low2float(h01) + __high2float(h01);
+        r1 += __low2float(h23) + __high2float(h23);
+        pa[j >> 1][(j & 1) * 2] = *reinterpret_cast<const uint32_t*>(&h01);
+        pa[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+      }
+      l0 = l0 * a0 + r0;
+      l1 = l1 * a1 + r1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int dn = 0; dn < 8; dn += 2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(sV + swz(k0 + 16 * ks + (lane & 15), dn + (lane >> 4))), b0, b1, b2, b3);
+          mma_bf16(o[dn], pa[ks], b0, b1);
+          mma_bf16(o[dn + 1], pa[ks], b2, b3);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int row0 = q0 + g, row1 = row0 + 8;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      if (row0 < L)
+        *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * H + 8 * dn + 2 * t) = gemm_detail::pack_bf16x2(o[dn][0] * i0, o[dn][1] * i0);
+      if (row1 < L)
+        *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * H + 8 * dn + 2 * t) = gemm_detail::pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
+    }
+  }
+}
+
 }  // namespace dit
 }  // namespace svdd
 
@@ -461,6 +628,13 @@ extern "C" int64_t svdd_dit_mod_floats(const svdd_dit* h) {
   return h ? (int64_t)(dit::kModPerBlock * h->n_blocks + 2) * h->H : 0;
 }
 
+// SVDD_DIT_ATTN_STREAM=1 (read per call) forces the streaming attention kernel also for L <= 256:
+// the A/B and the cross-check in tests/test_gpu_dit.py
+static bool dit_attn_streaming() {
+  const char* e = getenv("SVDD_DIT_ATTN_STREAM");
+  return e != nullptr && atoi(e) != 0;
+}
+
 static int64_t dit_chunk_seqs(int L) {
   const int64_t s = dit::kChunkRows / L;
   return s < 1 ? 1 : s;
@@ -558,8 +732,18 @@ extern "C" int svdd_dit_forward(svdd_dit* h, const void* tokens, int tok_dtype, 
         ep.out = qkv; ep.out_dtype = DT_BF16; ep.ld_out = 3 * H;
         SVDD_TRY(gemm(hn, h->wqkv[i], R, H, 3 * H, ep));
       }
-      launch_k(dit::dit_attn_kernel, dim3((unsigned)ceil_div(L, dit::kQB), (unsigned)h->n_heads, (unsigned)ns), dim3(128), 0, st, 1,
-               (const __nv_bfloat16*)qkv, ao, (const float*)h->rot_cos, (const float*)h->rot_sin, L, H);
+      if (L <= dit::kAttnSmallMaxL && !dit_attn_streaming()) {
+        static bool configured = false;
+        if (!configured) {
+          SVDD_CUDA(cudaFuncSetAttribute(dit::dit_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dit::kAttnSmallSmem));
+          configured = true;
+        }
+        launch_k(dit::dit_attn_small_kernel, dim3((unsigned)h->n_heads, (unsigned)ns), dim3(dit::kAttnSmallWarps * 32),
+                 (size_t)dit::kAttnSmallSmem, st, 1, (const __nv_bfloat16*)qkv, ao, (const float*)h->rot_cos, (const float*)h->rot_sin, L, H);
+      } else {
+        launch_k(dit::dit_attn_kernel, dim3((unsigned)ceil_div(L, dit::kQB), (unsigned)h->n_heads, (unsigned)ns), dim3(128), 0, st, 1,
+                 (const __nv_bfloat16*)qkv, ao, (const float*)h->rot_cos, (const float*)h->rot_sin, L, H);
+      }
       count_launch();
       SVDD_LAUNCH_CHECK();
       {

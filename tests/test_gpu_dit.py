@@ -132,3 +132,20 @@ def test_dit_time_conditioning_and_checkpoint_keys(cuda, tmp_path):
   xn, _, q, _ = m._ddpm_update_finetune(x, t, (1 - 1e-5) / 128)
   keep = (x != 4)
   assert torch.equal(xn[keep], x[keep]) and q.shape == (3, 50, 5)
+
+
+@pytest.mark.parametrize('L,n', [(200, 9), (50, 33), (256, 2), (77, 5), (16, 3)])
+def test_dit_attention_resident_kernel_matches_streaming_kernel(cuda, L, n, monkeypatch):
+  """L <= 256: the whole-sequence-resident attention kernel (K / V rotated and staged once per
+  (sequence, head)) against the streaming kernel it replaces (SVDD_DIT_ATTN_STREAM=1, read per
+  call): same rotary, same bf16 roundings, same key order within the online softmax."""
+  m = helpers.build_dit(n_blocks=2, length=L).to(cuda)
+  den = m.backbone.packed()
+  x = helpers.random_tokens(n, L, 17, 0.5).to(cuda)
+  monkeypatch.setenv('SVDD_DIT_ATTN_STREAM', '1')
+  a = den.forward(x, 0.0).clone()
+  monkeypatch.setenv('SVDD_DIT_ATTN_STREAM', '0')
+  b = den.forward(x, 0.0)
+  err = float((a - b).abs().max()) / float(a.abs().max())
+  print(f'\n[dit attention resident vs streaming L={L} n={n}] rel.err {err:.3e}')
+  assert err < 2e-3

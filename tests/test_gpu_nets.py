@@ -118,6 +118,33 @@ def test_denoiser_split_epilogue_matches_one_thread_per_row(cuda, L, n, monkeypa
   assert err < 6e-3
 
 
+@pytest.mark.parametrize('L,n', [(50, 333), (33, 40), (64, 3), (20, 9)])
+def test_denoiser_combined_planes_match_two_tile_scheme(cuda, L, n, monkeypatch):
+  """Short sequences: combined operand planes (ONE 128-row MMA per tap serves both sequences of a
+  CTA for taps that fit the zero gap between them, the rest on isolated planes with their own
+  accumulators) against the two-tile scheme (SVDD_DEN_CMB=0, read per call), and the 16-warp quad
+  epilogue (SVDD_DEN_EW=16) against the default 8-warp split epilogue.  Same bf16 rounding
+  points; the sums differ in accumulation order only."""
+  m = helpers.build_denoiser(44, L).to(cuda)
+  x = helpers.random_tokens(n, L, 13, 0.5).to(cuda).to(torch.uint8)
+  den = m.packed()
+  monkeypatch.setenv('SVDD_DEN_CMB', '0')
+  two = den.forward(x, 0.0).clone()
+  monkeypatch.setenv('SVDD_DEN_CMB', '1')
+  cmb = den.forward(x, 0.0).clone()
+  assert torch.equal(cmb, den.forward(x, 0.0)), 'combined mode is not deterministic'
+  monkeypatch.setenv('SVDD_DEN_EW', '16')
+  q16 = den.forward(x, 0.0).clone()
+  monkeypatch.delenv('SVDD_DEN_EW')
+  scale = float(two.abs().max())
+  e1, e2 = float((cmb - two).abs().max()) / scale, float((q16 - two).abs().max()) / scale
+  print(f'\n[denoiser combined vs two-tile L={L} n={n}] rel.err {e1:.3e}; 16-warp epilogue {e2:.3e}')
+  assert e1 < 6e-3 and e2 < 6e-3
+  # odd batch: the last CTA item holds one sequence only
+  one = den.forward(x[:1].contiguous(), 0.0)
+  assert torch.equal(one[0], cmb[0])
+
+
 def test_convgru_value(cuda):
   g = helpers.load_golden('value_nets.npz')
   tok = T(g['convgru_tokens'])
