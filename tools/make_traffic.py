@@ -1,0 +1,56 @@
+"""profiles/<tag>_launches_c2_step.csv (ncu launch list with dram__bytes_read/write) ->
+profiles/<tag>_traffic.json, stamped with the fingerprint of the kernel sources (bench.csrc_sha):
+bench.py quotes `roofline.traffic` from it only while the sources are unchanged.
+    python tools/make_traffic.py r02"""
+import collections
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r02'
+path = os.path.join(ROOT, 'profiles', f'{tag}_launches_c2_step.csv')
+data = collections.OrderedDict()
+for row in csv.DictReader(l for l in open(path) if l.startswith('"')):
+  k = (int(row['ID']), row['Kernel Name'])
+  data.setdefault(k, {})[row['Metric Name']] = float(row['Metric Value'].replace(',', ''))
+unit = {}
+for row in csv.DictReader(l for l in open(path) if l.startswith('"')):
+  unit[row['Metric Name']] = row['Metric Unit']
+scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+
+
+def dram(m):
+  # ncu prints every launch of a metric in the same unit within one csv
+  return sum(m.get(k, 0.0) * scale.get(unit.get(k, 'byte'), 1.0) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+
+
+fam = [(k, m) for k, m in data.items() if any(s in k[1] for s in ('gemm2_kernel', 'tower_kernel', 'conv_gemm_kernel', 'den_fused_kernel'))]
+# one reverse step = the first denoiser launch + the value net; the second den_fused launch is the noise-removal pass
+den = [x for x in fam if 'den_fused' in x[0][1]]
+step = [x for x in fam if 'den_fused' not in x[0][1]] + den[:1]
+tower = [x for x in fam if 'tower_kernel' in x[0][1]][0]
+out = {
+    'source': f'profiles/{tag}_launches_c2_step.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum '
+              '--clock-control none, one eager c2 reverse step, cold caches)',
+    'csrc_sha': bench.csrc_sha(),
+    'gemm_family_dram_bytes_per_step': int(sum(dram(m) for _, m in step)),
+    'gemm_family_launches': len(step),
+    'dominant_launch': {
+        'kernel': 'tower_kernel<2, 256>: the value net\'s 11 transformer blocks on 2560 rows in one persistent launch',
+        'dram_bytes': int(dram(tower[1])),
+        'algorithmic_bytes': 385351680,
+        'algorithmic_bytes_note': 'bf16 weights of the 44 GEMMs read once (346 MB) + the fp32 residual stream in and out + the bf16 '
+                                  'operand of the pointwise conv; qkv / attention output / FFN hidden are produced and consumed inside '
+                                  'the kernel but leave L2 as write-backs',
+        'ncu_us': tower[1].get('gpu__time_duration.sum', 0.0) / 1e3,
+        'tensor_pipe_pct': tower[1].get('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active'),
+    },
+}
+dst = os.path.join(ROOT, 'profiles', f'{tag}_traffic.json')
+json.dump(out, open(dst, 'w'), indent=2)
+print(open(dst).read())
