@@ -449,6 +449,16 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
         if (mode == EPI_PAIR) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
         return launch2_impl<256, EPI_GENERIC, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
       }
+      // SVDD_POOL16=1 (read per call): EPI_POOL2 with a staged bf16 output only (every stage but the last)
+      // on 16 epilogue warps, the pooled operands y0 / yd read directly from global memory a chunk ahead
+      // instead of through TMA slabs.  Measured SLOWER on every stage of the c2 pass (stage 0: 281 vs
+      // 199 us, stage 3: 66 vs 54 us): one 32-byte row segment per thread and load is 32 separate
+      // sectors per warp instruction, and the 8-warp variant's slab traffic was never the limit (ncu:
+      // ~6 % of its stall samples wait for a slab).  Bit-identical results; kept with its test.
+      const char* e16 = getenv("SVDD_POOL16");
+      const int pool16 = e16 ? atoi(e16) : 0;
+      if (pool16 && mode == EPI_POOL2 && bn2 == 256 && cg == 2 && !g.halo && ep2.out == nullptr && ep2.out2 != nullptr)
+        return launch2_impl<256, EPI_POOL2, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }
     if (g.halo) {
       if (bn2 == 256) return launch2_impl<256, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);

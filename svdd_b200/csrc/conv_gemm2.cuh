@@ -574,7 +574,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (EW == 16 && warp < 2 + EW) {
     // ===================== epilogue math, 16 warps: thread = (row, column quarter) =====================
     if constexpr (EW == 16) {
-      static_assert(EW != 16 || (BN == 256 && !HALO && (MODE == EPI_GENERIC || MODE == EPI_PAIR)), "EW = 16 variants");
+      static_assert(EW != 16 || (BN == 256 && !HALO && (MODE == EPI_GENERIC || MODE == EPI_PAIR || MODE == EPI_POOL2)), "EW = 16 variants");
       const int ew = warp - 2;
       const int quad = warp & 3;           // TMEM lane quadrant this warp may read
       const int grp = ew >> 2;             // column quarter
@@ -598,6 +598,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + grp * 64;
         uint32_t raw[2][16];
+        // EPI_POOL2: the two pooled operands (y0, yd: bf16 rows of `res` / `res2`) are read DIRECTLY
+        // from global memory, one 16-column chunk ahead of its use and before the accumulator wait
+        // -- the 8-warp variant stages them through TMA slabs and, with both slab buffers of a column
+        // half taken by the inputs, serialises load -> math -> store per 64-column step
+        uint4 py0[2][2], pyd[2][2];
+        const __nv_bfloat16* y0p = nullptr;
+        const __nv_bfloat16* ydp = nullptr;
+        if constexpr (MODE == EPI_POOL2) {
+          const int64_t r0 = (int64_t)s * (ep.res_pitch > 0 ? ep.res_pitch : g.L) + l;
+          const int64_t r1 = (int64_t)s * (ep.res2_pitch > 0 ? ep.res2_pitch : g.L) + l;
+          y0p = reinterpret_cast<const __nv_bfloat16*>(ep.res) + r0 * ep.ld_res + n0 + grp * 64;
+          ydp = reinterpret_cast<const __nv_bfloat16*>(ep.res2) + r1 * ep.ld_res2 + n0 + grp * 64;
+          const bool ok = valid && n0 + grp * 64 < n_end;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            py0[0][u] = ok ? __ldg(reinterpret_cast<const uint4*>(y0p) + u) : make_uint4(0, 0, 0, 0);
+            pyd[0][u] = ok ? __ldg(reinterpret_cast<const uint4*>(ydp) + u) : make_uint4(0, 0, 0, 0);
+          }
+        }
         ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
         ptx::tc_fence_after();
         tmem_ld_32x16(taddr, raw[0]);
@@ -606,6 +625,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int c0 = grp * 64 + c * 16;  // column within the tile
           if (c == 0) ptx::mbar_wait(&rin_bar[grp], job & 1);
           float v[16], pv[16];
+          if constexpr (MODE == EPI_POOL2) {
+            if (c + 1 < 4) {
+              const bool ok = valid && n0 + c0 + 16 < n_end;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                py0[(c + 1) & 1][u] = ok ? __ldg(reinterpret_cast<const uint4*>(y0p + (c + 1) * 16) + u) : make_uint4(0, 0, 0, 0);
+                pyd[(c + 1) & 1][u] = ok ? __ldg(reinterpret_cast<const uint4*>(ydp + (c + 1) * 16) + u) : make_uint4(0, 0, 0, 0);
+              }
+            }
+          }
           ptx::tmem_ld_wait();
           if (c + 1 < 4) tmem_ld_32x16(taddr + (c + 1) * 16, raw[(c + 1) & 1]);
 #pragma unroll
@@ -615,6 +644,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
           }
+          if constexpr (MODE == EPI_POOL2) {
+            // v = Wp.(y1 - y0): pooled = y0 + sigmoid(v) * yd; out2 = act2(pooled * scale2 + shift2)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t w0[4] = {py0[c & 1][u].x, py0[c & 1][u].y, py0[c & 1][u].z, py0[c & 1][u].w};
+              const uint32_t wd[4] = {pyd[c & 1][u].x, pyd[c & 1][u].y, pyd[c & 1][u].z, pyd[c & 1][u].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w0[k]);
+                const __nv_bfloat162 hd = *reinterpret_cast<const __nv_bfloat162*>(&wd[k]);
+                const float y0v[2] = {__low2float(h0), __high2float(h0)};
+                const float ydv[2] = {__low2float(hd), __high2float(hd)};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int i = 8 * u + 2 * k + e;
+                  float th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v[i]));
+                  v[i] = fmaf(fmaf(0.5f, th, 0.5f), ydv[e], y0v[e]);
+                }
+              }
+            }
+            if (ep.scale2 != nullptr) {
+              float ps[16];
+              load_param16(P + P_SCALE2 * BN + c0, ps);
+              load_param16(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+            }
+            act16(v, ep.act2);
+            slab_write16(buf, x7, c, v);
+          } else {
           if (ep.scale != nullptr) {
             float ps[16];
             load_param16(P + P_SCALE * BN + c0, ps);
@@ -657,6 +717,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             slab_write16(buf, x7, c, v);
           }
+          }   // MODE != EPI_POOL2
           if (c == 3) {
             ptx::fence_proxy_async_smem();
             __syncwarp();

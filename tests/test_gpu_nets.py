@@ -386,3 +386,21 @@ def test_value_rank_agreement(cuda):
   spread = float((ref.max(0).values - ref.min(0).values).mean())
   print(f'\n[rank] argmax agreement={agree:.3f} worst regret={regret:.2e} mean spread={spread:.2e}')
   assert agree >= 0.8 and regret <= 0.25 * spread
+
+
+@pytest.mark.parametrize('full,n_cand', [(False, 70), (True, 130)])
+def test_enformer_pool16_matches_slab_variant(cuda, full, n_cand, monkeypatch):
+  """Difference pooling (EPI_POOL2) with 16 epilogue warps and the pooled operands read directly
+  from global memory against the 8-warp variant that stages them through TMA slabs
+  (SVDD_POOL16=0, read per call): the same arithmetic on the same bf16 values, so the scores are
+  bit-identical.  The small net has ragged 256-wide column tiles (N = 384), the full one is the
+  bench network."""
+  emb, head = helpers.build_enformer(full=full)
+  emb, head = emb.to(cuda), head.to(cuda)
+  tok = helpers.random_tokens(n_cand, 200, 71, 0.5).to(cuda)
+  monkeypatch.setenv('SVDD_POOL16', '0')
+  ref = value_nets.score_tokens(emb, head, tok).cpu()
+  monkeypatch.setenv('SVDD_POOL16', '1')
+  got = value_nets.score_tokens(emb, head, tok).cpu()
+  print(f'\n[pool16 full={full}] max|d| = {float((got - ref).abs().max()):.3e}')
+  assert torch.equal(got, ref)
