@@ -460,12 +460,12 @@ class _ScoreHandle(_Handle):
     return scores
 
 
-def _named_with_head(sd_embedding, sd_head):
+def _named_with_head(sd_embedding, sd_head, task=0):
   """Trunk tensors under their own names + the head's under 'head.'.  A multi-task head
-  (the DNA oracle has 3) contributes task 0 only: the path reads ``reward_model(x)[:, 0]``
-  (diffusion_gosai.py:1430, Enformer.py:447)."""
+  (the DNA oracle has 3) contributes ONE task, by default task 0: the path reads
+  ``reward_model(x)[:, 0]`` (diffusion_gosai.py:1430, Enformer.py:447)."""
   named = [(k, v) for k, v in sd_embedding.items() if v.dtype.is_floating_point]
-  named += [('head.' + k, v[:1]) for k, v in sd_head.items() if v.dtype.is_floating_point]
+  named += [('head.' + k, v[task:task + 1]) for k, v in sd_head.items() if v.dtype.is_floating_point]
   if not named or named[0][1].device.type != 'cuda':
     raise SvddError('move the value network to a CUDA device before scoring')
   return named
@@ -474,14 +474,14 @@ def _named_with_head(sd_embedding, sd_head):
 class ConvGRUHandle(_ScoreHandle):
   _net = 'convgru'
 
-  def __init__(self, sd_embedding, sd_head):
+  def __init__(self, sd_embedding, sd_head, task=0):
     super().__init__()
-    self._create(_named_with_head(sd_embedding, sd_head))
+    self._create(_named_with_head(sd_embedding, sd_head, task))
 
 
 class EnformerHandle(_ScoreHandle):
   _net = 'enformer'
 
-  def __init__(self, sd_embedding, sd_head, n_heads=8):
+  def __init__(self, sd_embedding, sd_head, n_heads=8, task=0):
     super().__init__()
-    self._create(_named_with_head(sd_embedding, sd_head), int(n_heads))
+    self._create(_named_with_head(sd_embedding, sd_head, task), int(n_heads))

@@ -46,31 +46,6 @@ def exponential_linspace_int(start, end, num, divisible_by=1):
           for i in range(num)]
 
 
-def relative_position_table(n, feats):
-  """[2n-1, feats] Enformer relative-position basis for a length-n sequence
-  (enformer_pytorch ``get_positional_embed``, use_tf_gamma=False): exponential,
-  central-mask and gamma families, each mirrored with sign(distance).  Constant
-  for fixed n, so it is folded into the packed weights."""
-  if feats % 6:
-    raise ValueError('num_rel_pos_features must be divisible by 6')
-  k = feats // 6
-  d = torch.arange(-(n - 1), n, dtype=torch.float32)
-  ad = d.abs()[:, None]
-  half_life = 2.0 ** torch.linspace(3.0, math.log(n) / math.log(2.0), k)
-  f_exp = torch.exp(-math.log(2.0) / half_life[None] * ad)
-  widths = 2.0 ** torch.arange(1, k + 1, dtype=torch.float32) - 1
-  f_mask = (widths[None] > ad).float()
-  stddev = n / (2 * k)
-  mean = torch.linspace(n / k, n, k)[None]
-  conc, rate = (mean / stddev) ** 2, mean / stddev ** 2
-  logp = torch.xlogy(conc - 1.0, ad) - rate * ad - (
-      torch.lgamma(conc) - conc * torch.log(rate))
-  f_gam = torch.exp(logp) + 1e-8
-  f_gam = f_gam / f_gam.amax(dim=-1, keepdim=True)
-  base = torch.cat([f_exp, f_mask, f_gam], dim=-1)
-  return torch.cat([base, torch.sign(d)[:, None] * base], dim=-1)
-
-
 class ConvHead(nn.Module):
   """1x1 conv to n_tasks + average over length (Enformer.py:2131-2173) for the
   decode path's settings (norm=False, act_func=None, pool_func='avg')."""
@@ -86,10 +61,41 @@ class ConvHead(nn.Module):
         conv=_holder(layer=nn.Conv1d(in_channels, n_tasks, kernel_size=1)))
 
   def forward(self, x):
-    raise RuntimeError(
-        'ConvHead is fused into the trunk kernels: call '
-        'svdd_b200.value_nets.score_tokens(embedding, head, tokens) or pass '
-        '(embedding, head) to Diffusion.controlled_sample')
+    """``head(embedding(onehot))`` as the reference spells it (diffusion_gosai.py:1208-1209,
+    Enformer.py:443): ``x`` is what the trunk's ``forward`` returned -- a deferred handle on the
+    token rows, because trunk and head run as ONE fused scoring pass.  Returns fp32
+    [N, n_tasks, 1] like the reference's ConvHead (:2166-2173); with n_tasks > 1 every task is a
+    scoring pass of its own (the engine's own path scores task 0 once, diffusion_gosai.py:1430)."""
+    if not isinstance(x, _TrunkOutput):
+      raise RuntimeError(
+          'ConvHead is fused into the trunk kernels: it consumes the output of '
+          'EnformerTrunk / ConvGRUTrunk.forward (or call score_tokens(embedding, head, tokens))')
+    cols = [packed_scorer(x.trunk, self, task=t).score(x.tokens) for t in range(self.n_tasks)]
+    return torch.stack(cols, dim=1).unsqueeze(-1)
+
+
+class _TrunkOutput:
+  """What ``EnformerTrunk.forward`` / ``ConvGRUTrunk.forward`` return: the trunk and the token rows
+  recovered from the one-hot input.  The feature tensor itself never exists outside the kernels."""
+
+  def __init__(self, trunk, tokens):
+    self.trunk, self.tokens = trunk, tokens
+
+
+def _onehot_to_tokens(x, channels_last):
+  """fp one-hot [N,L,4] (or [N,4,L]) with all-zero rows for masked positions
+  (transform_samples, diffusion_gosai.py:1462-1470) -> int64 tokens [N,L] with 4 = mask."""
+  if not channels_last:
+    x = x.transpose(1, 2)
+  if x.dim() != 3 or x.shape[-1] != 4:
+    raise ValueError(f'expected a one-hot input with 4 channels, got {tuple(x.shape)}')
+  if not x.is_cuda:
+    raise _lib.SvddError('svdd_b200 kernels need CUDA tensors (there is no CPU path)')
+  hot = x != 0
+  if bool(((x != 0) & (x != 1)).any()) or bool((hot.sum(-1) > 1).any()):
+    raise ValueError('the scoring kernels consume token rows: the input must be one-hot '
+                     '(soft inputs are not on the decode path)')
+  return torch.where(hot.any(-1), x.argmax(-1), torch.full(x.shape[:2], 4, device=x.device))
 
 
 class ConvGRUTrunk(nn.Module):
@@ -136,7 +142,9 @@ class ConvGRUTrunk(nn.Module):
     self.gru_tower = _holder(gru=gru, ffn=ffn)
 
   def forward(self, x):
-    raise RuntimeError('use svdd_b200.value_nets.score_tokens(embedding, head, tokens)')
+    """x: one-hot [N, L, 4] or [N, 4, L] (transposed when dim 1 is not the channel count,
+    Enformer.py:1422-1423).  Returns the deferred trunk output ``ConvHead.forward`` consumes."""
+    return _TrunkOutput(self, _onehot_to_tokens(x, channels_last=(x.shape[1] != 4)))
 
 
 class _AttentionParams(nn.Module):
@@ -217,7 +225,9 @@ class EnformerTrunk(nn.Module):
     self.pointwise_conv = _nacdr(channels, 2 * channels, 1, pool=False)
 
   def forward(self, x):
-    raise RuntimeError('use svdd_b200.value_nets.score_tokens(embedding, head, tokens)')
+    """x: one-hot [N, L, 4] (this trunk transposes unconditionally, Enformer.py:1328).  Returns the
+    deferred trunk output ``ConvHead.forward`` consumes."""
+    return _TrunkOutput(self, _onehot_to_tokens(x, channels_last=True))
 
 
 class OriBaseModel(nn.Module):
@@ -229,31 +239,42 @@ class OriBaseModel(nn.Module):
     super().__init__()
     self.embedding, self.head = embedding, head
 
+  def forward(self, x):
+    """x: one-hot [N, 4, L] -- the gReLU reward model's layout, which is why the path calls
+    ``reward_model(onehot.float().transpose(1, 2))`` (diffusion_gosai.py:1430).  -> [N, n_tasks, 1]."""
+    if isinstance(self.embedding, ConvGRUTrunk):
+      return self.head(self.embedding(x))
+    return self.head(_TrunkOutput(self.embedding, _onehot_to_tokens(x, channels_last=False)))
+
 
 # -- packing + scoring ---------------------------------------------------------
 
 _PACK_CACHE_ATTR = '_svdd_packed'
 
 
-def packed_scorer(embedding, head):
+def packed_scorer(embedding, head, task=0):
   """Returns (and caches on ``embedding``) the packed device weights of an
-  (embedding, head) pair.  Accepts the containers above or any nn.Module with
-  the reference's state_dict layout (duck-typed on key names)."""
+  (embedding, head) pair for one task of the head.  Accepts the containers above or any
+  nn.Module with the reference's state_dict layout (duck-typed on key names)."""
   sd = embedding.state_dict()
   key = tuple((v.data_ptr(), v._version) for v in sd.values()) + tuple(
       (v.data_ptr(), v._version) for v in head.state_dict().values())
-  cached = getattr(embedding, _PACK_CACHE_ATTR, None)
-  if cached is not None and cached[0] == key:
-    return cached[1]
+  cache = getattr(embedding, _PACK_CACHE_ATTR, None)
+  if cache is None or cache[0] != key:
+    cache = (key, {})
+    object.__setattr__(embedding, _PACK_CACHE_ATTR, cache)
+  handle = cache[1].get(task)
+  if handle is not None:
+    return handle
   if any(k.startswith('gru_tower.') for k in sd):
-    handle = _lib.ConvGRUHandle(sd, head.state_dict())
+    handle = _lib.ConvGRUHandle(sd, head.state_dict(), task=task)
   elif any(k.startswith('transformer_tower.') or k.startswith('conv_tower.blocks.0.0.')
            for k in sd):
     n_heads = getattr(embedding, 'n_heads', 8)
-    handle = _lib.EnformerHandle(sd, head.state_dict(), n_heads)
+    handle = _lib.EnformerHandle(sd, head.state_dict(), n_heads, task=task)
   else:
     raise TypeError('unrecognised value-network parameter layout')
-  object.__setattr__(embedding, _PACK_CACHE_ATTR, (key, handle))
+  cache[1][task] = handle
   return handle
 
 

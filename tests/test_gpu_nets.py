@@ -404,3 +404,37 @@ def test_enformer_pool16_matches_slab_variant(cuda, full, n_cand, monkeypatch):
   got = value_nets.score_tokens(emb, head, tok).cpu()
   print(f'\n[pool16 full={full}] max|d| = {float((got - ref).abs().max()):.3e}')
   assert torch.equal(got, ref)
+
+
+def test_module_call_surface_head_of_embedding(cuda):
+  """Drop-in surface: the reference spells scoring as ``head(embedding(onehot))``
+  (diffusion_gosai.py:1208-1209) and ``reward_model(onehot.transpose(1, 2))[:, 0]`` (:1430).  The
+  parameter containers serve both spellings (trunk + head run as one fused pass behind a deferred
+  trunk output) and return the reference's shapes; a 3-task head returns all three tasks."""
+  from svdd_b200 import synthetic
+  g = helpers.load_golden('enformer_full.npz')
+  _, cand = helpers.svdd_step_candidates(32, 10, 200, seed=2024)
+  tok = cand[0].to(cuda)
+  onehot = svdd.transform_samples(cand[0]).float().to(cuda)              # [N, L, 4], masked rows all zero
+  emb, head = helpers.build_enformer(full=True)
+  emb, head = emb.to(cuda), head.to(cuda)
+  direct = value_nets.score_tokens(emb, head, tok)
+  out = head(emb(onehot))
+  assert out.shape == (32, 1, 1) and torch.equal(out.reshape(-1), direct)
+  rm = synthetic.build_dna_reward_model().to(cuda)
+  out3 = rm(onehot.transpose(1, 2))
+  assert out3.shape == (32, 3, 1)
+  ref3 = T(g['values3'])[0]                                              # [32, 3] from the reference modules
+  err = float((out3.squeeze(-1).cpu() - ref3).abs().max())
+  print(f'\n[module call] 3-task oracle via OriBaseModel.forward: max|d| vs reference {err:.3e}')
+  assert err <= EF_REF
+  assert torch.equal(out3[:, 0, 0], value_nets.score_tokens(rm.embedding, rm.head, tok))
+  # RNA: ConvGRU value net, both input layouts
+  e2, h2 = helpers.build_convgru_value()
+  e2, h2 = e2.to(cuda), h2.to(cuda)
+  t2 = helpers.random_tokens(9, 50, 4, 0.4).to(cuda)
+  oh2 = svdd.transform_samples(t2.cpu()).float().to(cuda)
+  want = value_nets.score_tokens(e2, h2, t2)
+  assert torch.equal(h2(e2(oh2)).reshape(-1), want) and torch.equal(h2(e2(oh2.transpose(1, 2))).reshape(-1), want)
+  with pytest.raises(ValueError):
+    head(emb(onehot * 0.5))                                              # soft inputs are not on the path
