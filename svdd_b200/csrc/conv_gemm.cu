@@ -247,6 +247,13 @@ int pick_bn2(const GemmShape& g, int cg, int mode = EPI_GENERIC) {
 
 }  // namespace
 
+int encode_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  const cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  const cuuint64_t str[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  return encode_bf16_map(map, base, 3, dims, str, box);
+}
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                         uint32_t box_inner, uint32_t box_rows) {
   const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};

@@ -681,6 +681,9 @@ int conv_gemm_n_tiles(const GemmShape& shape, int mode);
 // 128B-swizzled 2-D tensor map over a row-major bf16 matrix [rows, inner] (inner contiguous).
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                         uint32_t box_inner, uint32_t box_rows);
+// 128B-swizzled 3-D tensor map over bf16 [d2][d1][d0] (d0 contiguous; strides in bytes)
+int encode_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
 // the same over an fp32 matrix (box_inner * 4 bytes <= 128)
 int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                        uint32_t box_inner, uint32_t box_rows);

@@ -16,6 +16,7 @@
 #include <new>
 
 #include "conv_gemm.cuh"
+#include "gru_umma.cuh"
 #include "weights.cuh"
 
 namespace svdd {
@@ -27,7 +28,12 @@ constexpr int kStemTapsMax = 15;
 constexpr int kMaxBlocks = 16;
 constexpr int64_t kChunkRows = 16384;
 
-// ---- stem: one warp per position, lane -> 2 channels -------------------------------
+// ---- stem: one warp per 8 consecutive positions, lane -> 2 channels -----------------------
+// The one-hot conv is a gather-add of weight rows.  The warp loads the 8 + taps - 1 tokens its
+// positions see once (one per lane) and walks the taps with the 8 positions' accumulators as
+// independent chains (the first version did one position at a time, a dependent chain of `taps`
+// shuffle + shared-load + add per position: 164 us per 12 800 x 50 rows against 14 us of HBM time).
+constexpr int kEmbedPos = 8;
 template <typename Tok>
 __global__ void __launch_bounds__(256)
 cg_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[taps][4][64]*/,
@@ -41,29 +47,44 @@ cg_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[t
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 2;
   const float2 bias = *reinterpret_cast<const float2*>(b + c);
-  const int64_t pos_base = ((int64_t)blockIdx.x * 8 + warp) * 8;
-  for (int i = 0; i < 8; ++i) {
-    const int64_t pos = pos_base + i;
-    if (pos >= NL) break;
-    const int l = (int)(pos % L);
-    int tokv = -1;
-    if (lane < taps) {
-      const int li = l + lane - taps / 2;
-      if (li >= 0 && li < L) {
-        const int t = load_tok(tokens, pos + lane - taps / 2);
-        tokv = (t < 4) ? t : -1;
-      }
+  const int64_t pos_base = ((int64_t)blockIdx.x * 8 + warp) * kEmbedPos;
+  if (pos_base >= NL) return;
+  const int half = taps / 2;
+  // lane j holds the token at global position pos_base - half + j (j < kEmbedPos + taps - 1 <= 22);
+  // -1 outside the tensor and for the mask token (all-zero one-hot row)
+  int tokv = -1;
+  {
+    const int64_t gp = pos_base - half + lane;
+    if (lane < kEmbedPos + taps - 1 && gp >= 0 && gp < NL) {
+      const int t = load_tok(tokens, (size_t)gp);
+      tokv = (t < 4) ? t : -1;
     }
-    float2 acc = bias;
-    for (int t = 0; t < taps; ++t) {
-      const int tk = __shfl_sync(0xffffffffu, tokv, t);
-      if (tk >= 0) {
+  }
+  const int l0 = (int)(pos_base % L);
+  float2 acc[kEmbedPos];
+#pragma unroll
+  for (int i = 0; i < kEmbedPos; ++i) acc[i] = bias;
+  for (int t = 0; t < taps; ++t) {
+#pragma unroll
+    for (int i = 0; i < kEmbedPos; ++i) {
+      const int tk = __shfl_sync(0xffffffffu, tokv, i + t);
+      // position i of the warp sits at l = (l0 + i) mod L of its sequence; tap t reads l + t - half,
+      // which must stay inside that sequence (zero padding at its ends)
+      int li = l0 + i;
+      if (li >= L) li -= L;                      // kEmbedPos <= L is checked by the launcher
+      const int lt = li + t - half;
+      if (tk >= 0 && lt >= 0 && lt < L) {
         const float2 ww = *reinterpret_cast<const float2*>(&s_w[(t * 4 + tk) * kC + c]);
-        acc.x += ww.x; acc.y += ww.y;
+        acc[i].x += ww.x; acc[i].y += ww.y;
       }
     }
-    *reinterpret_cast<__nv_bfloat162*>(out + pos * kC + c) =
-        __floats2bfloat162_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+  }
+#pragma unroll
+  for (int i = 0; i < kEmbedPos; ++i) {
+    const int64_t pos = pos_base + i;
+    if (pos < NL)
+      *reinterpret_cast<__nv_bfloat162*>(out + pos * kC + c) =
+          __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
   }
 }
 
@@ -369,6 +390,16 @@ __global__ void cg_fold_gate_bias_kernel(const float* __restrict__ bih_f, const 
   if (j >= 2 * kC) bhn[dir * kC + j - 2 * kC] = bhh[j];
 }
 
+// W_hh fp32 [n] -> bf16 hi / lo planes (hi = rn(w), lo = rn(w - hi)) for the tcgen05 recurrence
+__global__ void cg_split_hi_lo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const __nv_bfloat16 h = __float2bfloat16_rn(w[i]);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(h));
+}
+
 }  // namespace
 }  // namespace svdd
 
@@ -387,6 +418,8 @@ struct svdd_convgru {
   __nv_bfloat16* wih = nullptr;          // [384][64]
   float* gate_b = nullptr;               // [384]
   float* whh = nullptr;                  // [2][192][64]
+  __nv_bfloat16* whh_hi = nullptr;       // [2][192][64]  bf16 hi / lo split of W_hh (tcgen05 recurrence)
+  __nv_bfloat16* whh_lo = nullptr;
   float* bhn = nullptr;                  // [2][64]
   float* ln_g = nullptr;
   float* ln_b = nullptr;
@@ -435,6 +468,8 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
   A.reserve(sizeof(__nv_bfloat16) * 2 * kG3 * kC);
   A.reserve(sizeof(float) * 2 * kG3);
   A.reserve(sizeof(float) * 2 * kG3 * kC);
+  A.reserve(sizeof(__nv_bfloat16) * 2 * kG3 * kC);
+  A.reserve(sizeof(__nv_bfloat16) * 2 * kG3 * kC);
   A.reserve(sizeof(float) * 2 * kC);
   A.reserve(sizeof(float) * kC);
   A.reserve(sizeof(float) * kC);
@@ -454,6 +489,8 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
   h->wih = A.take<__nv_bfloat16>(2 * kG3 * kC);
   h->gate_b = A.take<float>(2 * kG3);
   h->whh = A.take<float>(2 * kG3 * kC);
+  h->whh_hi = A.take<__nv_bfloat16>(2 * kG3 * kC);
+  h->whh_lo = A.take<__nv_bfloat16>(2 * kG3 * kC);
   h->bhn = A.take<float>(2 * kC);
   h->ln_g = A.take<float>(kC);
   h->ln_b = A.take<float>(kC);
@@ -501,6 +538,7 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
   TRY_OR_FAIL(copy_f32(whh_f, h->whh, kG3 * kC, st));
   TRY_OR_FAIL(copy_f32(whh_b, h->whh + kG3 * kC, kG3 * kC, st));
   cg_fold_gate_bias_kernel<<<1, 2 * kG3, 0, st>>>(bih_f, bhh_f, bih_b, bhh_b, h->gate_b, h->bhn);
+  cg_split_hi_lo_kernel<<<ceil_div(2 * kG3 * kC, 256), 256, 0, st>>>(h->whh, h->whh_hi, h->whh_lo, 2 * kG3 * kC);
   const std::string fp = "gru_tower.ffn.";
   GET_OR_FAIL(lg, fp + "dense1.norm.layer.weight", kC);
   GET_OR_FAIL(lb, fp + "dense1.norm.layer.bias", kC);
@@ -540,11 +578,43 @@ bool gru_scalar() {
   static const bool v = [] { const char* e = getenv("SVDD_GRU_SCALAR"); return e && e[0] == '1'; }();
   return v;
 }
-size_t cg_carve(Workspace& W, int64_t rows, int L, CgWs* o) {
+// The tcgen05 recurrence (256 sequences per CTA, the step a serial chain of ~3 us) wins once there
+// are enough sequences to fill the SMs with such CTAs: measured 4.29 vs 6.56 ms at 51 200 rows,
+// 0.92 vs 1.22 ms at 8 192, equal at 4 096, 0.61 vs 0.45 ms at 2 048 (the mma.sync kernel spreads 16
+// sequences per block over many more blocks).  SVDD_GRU_UMMA (read per call): 0 = never, 1 = always
+// (the tests), unset = from kGruUmmaMinRows rows.
+constexpr int64_t kGruUmmaMinRows = 6144;
+constexpr int64_t kChunkRowsUmma = 65536;   // no gi tensor on this path: 904 instead of 2440 bytes per position
+bool gru_umma(int64_t rows) {
+  if (gru_scalar()) return false;
+  const char* e = getenv("SVDD_GRU_UMMA");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  return rows >= kGruUmmaMinRows;
+}
+int launch_gru_umma(const svdd_convgru* h, const __nv_bfloat16* x, float* y, int64_t rows, int L, cudaStream_t st) {
+  CUtensorMap tX, tWx, tWhi, tWlo;
+  SVDD_TRY(encode_tmap_3d_bf16(&tX, x, kC, (uint64_t)L, (uint64_t)rows, (uint64_t)kC * 2, (uint64_t)L * kC * 2, kC, 1,
+                               gruu::kRowsG));
+  SVDD_TRY(encode_tmap_2d_bf16(&tWx, h->wih, kC, 2 * kG3, kC, kG3));
+  SVDD_TRY(encode_tmap_2d_bf16(&tWhi, h->whh_hi, kC, 2 * kG3, kC, kG3));
+  SVDD_TRY(encode_tmap_2d_bf16(&tWlo, h->whh_lo, kC, 2 * kG3, kC, kG3));
+  static bool configured = false;
+  if (!configured) {
+    SVDD_CUDA(cudaFuncSetAttribute(gruu::cg_gru_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gruu::kSmemBytes));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)ceil_div<int64_t>(rows, gruu::kGroups * gruu::kRowsG);
+  SVDD_CUDA(launch_k(gruu::cg_gru_umma_kernel, dim3(grid, 2), dim3(gruu::kThreads), (size_t)gruu::kSmemBytes, st, 1, tX, tWx,
+                     tWhi, tWlo, (const float*)h->gate_b, (const float*)h->bhn, y, rows, L));
+  count_launch();
+  return SVDD_OK;
+}
+size_t cg_carve(Workspace& W, int64_t rows, int L, CgWs* o, bool with_gi = true) {
   const size_t nl = (size_t)rows * L + 1;
   o->x[0] = W.take<__nv_bfloat16>(nl * kC);
   o->x[1] = W.take<__nv_bfloat16>(nl * kC);
-  o->gi = W.take<float>(nl * 2 * kG3);
+  o->gi = with_gi ? W.take<float>(nl * 2 * kG3) : nullptr;
   o->y = W.take<float>(2 * nl * kC);
   o->z = W.take<__nv_bfloat16>(nl * kC);
   o->partials = W.take<float>(nl * 2);
@@ -554,15 +624,18 @@ size_t cg_carve(Workspace& W, int64_t rows, int L, CgWs* o) {
 
 extern "C" size_t svdd_convgru_workspace_bytes(const svdd_convgru* h, int64_t n_rows, int L) {
   (void)h;
-  Workspace W(nullptr, 0);
+  // enough for either recurrence path: chunks of kChunkRows with the gi tensor, or of kChunkRowsUmma without
+  Workspace W(nullptr, 0), W2(nullptr, 0);
   CgWs o;
-  return cg_carve(W, n_rows < kChunkRows ? n_rows : kChunkRows, L, &o);
+  const size_t a = cg_carve(W, n_rows < kChunkRows ? n_rows : kChunkRows, L, &o);
+  const size_t b = cg_carve(W2, n_rows < kChunkRowsUmma ? n_rows : kChunkRowsUmma, L, &o, false);
+  return a > b ? a : b;
 }
 
 extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_dtype, float* scores,
                                   int64_t n_rows, int L, void* ws, size_t ws_bytes, void* stream) {
   SVDD_CHECK_ARG(h && tokens && scores, "svdd_convgru_score: null pointer");
-  SVDD_CHECK_ARG(n_rows >= 0 && L >= 1, "svdd_convgru_score: bad shape");
+  SVDD_CHECK_ARG(n_rows >= 0 && L >= kEmbedPos, "svdd_convgru_score: bad shape (L >= %d)", kEmbedPos);
   SVDD_CHECK_ARG(tok_dtype == SVDD_TOK_I64 || tok_dtype == SVDD_TOK_U8, "bad tok_dtype %d", tok_dtype);
   if (n_rows == 0) return SVDD_OK;
   if (ws == nullptr || ws_bytes < svdd_convgru_workspace_bytes(h, n_rows, L)) {
@@ -571,12 +644,14 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tok_bytes = tok_dtype == SVDD_TOK_I64 ? 8 : 1;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += kChunkRows) {
-    const int64_t rows = (n_rows - r0 < kChunkRows) ? n_rows - r0 : kChunkRows;
+  const bool umma = gru_umma(n_rows);
+  const int64_t chunk = umma ? kChunkRowsUmma : kChunkRows;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int64_t rows = (n_rows - r0 < chunk) ? n_rows - r0 : chunk;
     const int64_t NL = rows * L;
     Workspace W(ws, ws_bytes);
     CgWs b;
-    cg_carve(W, rows, L, &b);
+    cg_carve(W, rows, L, &b, !umma);
     const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)r0 * L * tok_bytes;
     const unsigned eg = (unsigned)ceil_div<int64_t>(NL, 64);
     if (tok_dtype == SVDD_TOK_I64)
@@ -599,20 +674,25 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
       SVDD_TRY(launch_conv_gemm(b.x[cur], h->conv_w[i], g, EPI_GENERIC, ep, st));
       cur ^= 1;
     }
-    {  // GRU input projections, both directions at once: [NL,64] x [64,384]
-      GemmShape g;
-      g.S = 1; g.L = (int)NL; g.L_in = (int)NL; g.K = kC; g.N = 2 * kG3; g.BL = 128; g.BS = 1;
-      EpiParams ep;
-      ep.bias = h->gate_b;
-      ep.out = b.gi; ep.out_dtype = DT_F32; ep.ld_out = 2 * kG3;
-      SVDD_TRY(launch_conv_gemm(b.x[cur], h->wih, g, EPI_GENERIC, ep, st));
+    if (umma) {
+      // tcgen05 recurrence with the input projection fused in (csrc/gru_umma.cuh): no gi tensor
+      SVDD_TRY(launch_gru_umma(h, b.x[cur], b.y, rows, L, st));
+    } else {
+      {  // GRU input projections, both directions at once: [NL,64] x [64,384]
+        GemmShape g;
+        g.S = 1; g.L = (int)NL; g.L_in = (int)NL; g.K = kC; g.N = 2 * kG3; g.BL = 128; g.BS = 1;
+        EpiParams ep;
+        ep.bias = h->gate_b;
+        ep.out = b.gi; ep.out_dtype = DT_F32; ep.ld_out = 2 * kG3;
+        SVDD_TRY(launch_conv_gemm(b.x[cur], h->wih, g, EPI_GENERIC, ep, st));
+      }
+      if (gru_scalar())   // SVDD_GRU_SCALAR=1: the FMA-pipe kernel (A/B and cross-check of the tensor-core ones)
+        launch_k(cg_gru_kernel, dim3((unsigned)ceil_div<int64_t>(rows, kSeq), 2), dim3(kG3), 0, st, 1, b.gi, h->whh, h->bhn, b.y, rows, L);
+      else
+        launch_k(cg_gru_mma_kernel, dim3((unsigned)ceil_div<int64_t>(rows, kSeqT), 2), dim3(128), 0, st, 1, b.gi, h->whh, h->bhn, b.y, rows, L);
+      count_launch();
+      SVDD_LAUNCH_CHECK();
     }
-    if (gru_scalar())   // SVDD_GRU_SCALAR=1: the FMA-pipe kernel (A/B and cross-check of the tensor-core one)
-      launch_k(cg_gru_kernel, dim3((unsigned)ceil_div<int64_t>(rows, kSeq), 2), dim3(kG3), 0, st, 1, b.gi, h->whh, h->bhn, b.y, rows, L);
-    else
-      launch_k(cg_gru_mma_kernel, dim3((unsigned)ceil_div<int64_t>(rows, kSeqT), 2), dim3(128), 0, st, 1, b.gi, h->whh, h->bhn, b.y, rows, L);
-    count_launch();
-    SVDD_LAUNCH_CHECK();
     launch_k(cg_ln_kernel, dim3((unsigned)ceil_div<int64_t>(NL, 8)), dim3(256), 0, st, 1, b.y, h->ln_g, h->ln_b, b.z, NL);
     count_launch();
     SVDD_LAUNCH_CHECK();

@@ -438,3 +438,25 @@ def test_module_call_surface_head_of_embedding(cuda):
   assert torch.equal(h2(e2(oh2)).reshape(-1), want) and torch.equal(h2(e2(oh2.transpose(1, 2))).reshape(-1), want)
   with pytest.raises(ValueError):
     head(emb(onehot * 0.5))                                              # soft inputs are not on the path
+
+
+@pytest.mark.parametrize('n,L', [(77, 50), (1000, 50), (129, 50), (300, 33), (5, 64), (256, 50)])
+def test_convgru_umma_recurrence_matches_mma_sync_path(cuda, n, L, monkeypatch):
+  """The tcgen05 GRU recurrence with the input projection fused in (csrc/gru_umma.cuh: 256
+  sequences per CTA in two groups that alternate between tensor core and gate arithmetic)
+  against the mma.sync recurrence fed by the separate projection GEMM (SVDD_GRU_UMMA=0, read per
+  call).  Same bf16 operands and hi / lo split; the sums differ in association only.  Row counts
+  cover a partial first group, a dead second group and several CTAs."""
+  for build in (helpers.build_convgru_value, helpers.build_convgru_oracle):
+    emb, head = build()
+    emb, head = emb.to(cuda), head.to(cuda)
+    tok = helpers.random_tokens(n, L, 29 + n, 0.4).to(cuda)
+    monkeypatch.setenv('SVDD_GRU_UMMA', '0')
+    ref = value_nets.score_tokens(emb, head, tok).cpu()
+    monkeypatch.setenv('SVDD_GRU_UMMA', '1')
+    got = value_nets.score_tokens(emb, head, tok).cpu()
+    again = value_nets.score_tokens(emb, head, tok).cpu()
+    err = float((got - ref).abs().max())
+    print(f'\n[convgru umma vs mma.sync n={n} L={L}] max |d| = {err:.3e} (scale {float(ref.abs().max()):.3g})')
+    assert torch.equal(got, again) and torch.isfinite(got).all()
+    assert err <= 2e-5 * max(1.0, float(ref.abs().max()))
