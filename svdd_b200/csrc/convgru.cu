@@ -47,9 +47,10 @@ cg_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[t
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 2;
   const float2 bias = *reinterpret_cast<const float2*>(b + c);
-  const int64_t pos_base = ((int64_t)blockIdx.x * 8 + warp) * kEmbedPos;
-  if (pos_base >= NL) return;
   const int half = taps / 2;
+  // grid-stride over groups of 8 positions: the 15 KB weight table is staged once per (persistent) block
+  for (int64_t grp = (int64_t)blockIdx.x * 8 + warp; grp * kEmbedPos < NL; grp += (int64_t)gridDim.x * 8) {
+  const int64_t pos_base = grp * kEmbedPos;
   // lane j holds the token at global position pos_base - half + j (j < kEmbedPos + taps - 1 <= 22);
   // -1 outside the tensor and for the mask token (all-zero one-hot row)
   int tokv = -1;
@@ -85,6 +86,7 @@ cg_embed_kernel(const Tok* __restrict__ tokens, const float* __restrict__ w /*[t
     if (pos < NL)
       *reinterpret_cast<__nv_bfloat162*>(out + pos * kC + c) =
           __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
+  }
   }
 }
 
@@ -653,7 +655,8 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
     CgWs b;
     cg_carve(W, rows, L, &b, !umma);
     const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)r0 * L * tok_bytes;
-    const unsigned eg = (unsigned)ceil_div<int64_t>(NL, 64);
+    const int64_t eg_all = ceil_div<int64_t>(NL, 64);
+    const unsigned eg = (unsigned)(eg_all < 8 * (int64_t)num_sms() ? eg_all : 8 * (int64_t)num_sms());
     if (tok_dtype == SVDD_TOK_I64)
       launch_k(cg_embed_kernel<int64_t>, dim3(eg), dim3(256), 0, st, 1, (const int64_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
     else
