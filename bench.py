@@ -285,6 +285,32 @@ def other_config_legs(device, rank, world, dna_model, emb, head, barrier):
   cfg = config.load_config('rna')
   torch.manual_seed(44)
   rna = diffusion_gosai.Diffusion(cfg).to(device).eval()
+  # c1: the reference's own CPU-runnable case (RNA SVDD-MC, L = 50, batch 10, M = 10): latency-bound
+  # (100 candidates per step), so it is timed as the product runs it -- the whole 128-step decode as
+  # one CUDA graph; every rank decodes its own 10 sequences
+  ve, vh = synthetic.build_convgru_value()
+  ve, vh = ve.to(device), vh.to(device)
+  run1 = lambda: rna.controlled_sample(ve, vh, eval_sp_size=10, sample_M=10, row_offset=rank * 10)
+  run1(); run1()
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(3):
+    x = run1()
+  e1.record()
+  barrier()
+  ms = torch.tensor([e0.elapsed_time(e1) / 3], device=device)
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  f1 = 10 * f_den(50) + 100 * F_VAL_GRU
+  legs['c1'] = {'workload': "RNA 5'UTR MRL SVDD-MC (decode.py --task rna --sample_M 10), L=50, batch 10 per GPU, M=10, full "
+                            '128-step decode as one CUDA graph', 'B_per_gpu': 10, 'global_batch': 10 * world, 'n_gpus': world,
+                'timed_reverse_steps': NUM_STEPS, 'ms_per_denoise_step': float(ms) / NUM_STEPS,
+                'decoded_seqs_per_sec_at_128_steps': 10 * world / (float(ms) * 1e-3),
+                'roofline': {'bound': 'latency (100 candidates per step)', 'achieved': f1 / (float(ms) / NUM_STEPS * 1e-3) / 1e12,
+                             'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
+                             'frac': f1 / (float(ms) / NUM_STEPS * 1e-3) / 1e12 / pk['tf_sust'], 'flops_per_step_per_gpu': f1}}
+  del ve, vh
   oe, oh = synthetic.build_convgru_oracle()
   rm5 = value_nets.OriBaseModel(oe.to(device), oh.to(device))
   B5 = 8192 // world

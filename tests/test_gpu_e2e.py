@@ -645,3 +645,22 @@ def test_cli_loads_reference_layout_value_checkpoint(cuda, tmp_path):
   r = subprocess.run(cmd, cwd=helpers.ROOT, capture_output=True, text=True, timeout=600)
   assert r.returncode == 0, r.stdout + r.stderr
   assert np.load(tmp_path / 'rna-MRL.npz')['decoding'].shape == (8,)
+
+
+def test_shard_equivalence_dna_headline_networks(cuda):
+  """The same property on the headline configuration's networks (fused L = 200 denoiser, full
+  Enformer value net, M = 10): a batch of 8 decoded whole == two shards of 4 with their row
+  offsets, eager and through the graph.  Requires per-row results of every kernel to be
+  independent of the batch composition (tile placement, chunking)."""
+  m = _dna_model(cuda)
+  emb, head = helpers.build_enformer(full=True)
+  emb, head = emb.to(cuda), head.to(cuda)
+  for graph in (False, True):
+    m.use_cuda_graph = graph
+
+    def run(rows, off):
+      m.manual_seed(31)
+      return m.controlled_sample(emb, head, num_steps=3, eval_sp_size=rows, sample_M=10, row_offset=off)
+    whole = run(8, 0)
+    assert torch.equal(whole, torch.cat([run(4, 0), run(4, 4)], 0)), f'graph={graph}'
+    assert torch.equal(whole, torch.cat([run(5, 0), run(3, 5)], 0)), f'graph={graph}'

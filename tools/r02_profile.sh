@@ -18,11 +18,11 @@ timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measur
     --csv --log-file $OUT/${TAG}_launches_c2_step.csv python tools/profile_step.py --steps 1 > $OUT/${TAG}_launches.log 2>&1
 timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measured/" \
     --csv --log-file $OUT/${TAG}_launches_c5_step.csv python tools/profile_step_rna.py --steps 1 > $OUT/${TAG}_launches_c5.log 2>&1
-for spec in "tower:tower_kernel:profile_step.py" "den_l50:den_fused_kernel:profile_step_rna.py" "dit_attn:dit_attn_small_kernel:time_dit.py 64 200"; do
-  name=${spec%%:*}; rest=${spec#*:}; re=${rest%%:*}; script=${rest#*:}
+for spec in "tower:tower_kernel:profile_step.py:0" "den_l50:den_fused_kernel:profile_step_rna.py:1" "gru_umma:cg_gru_umma_kernel:profile_step_rna.py --B 1024:0" "dit_attn:dit_attn_small_kernel:time_dit.py 64 200:1"; do
+  name=${spec%%:*}; rest=${spec#*:}; re=${rest%%:*}; rest=${rest#*:}; script=${rest%%:*}; skip=${rest#*:}
   inc="--nvtx --nvtx-include measured/"
   if [ "$name" = "dit_attn" ]; then inc=""; export SVDD_TIME_DIT_NO_PROFILE=1; fi
-  timeout 900 ncu --set full --clock-control none --import-source on $inc -k regex:"$re" -s 1 -c 1 \
+  timeout 900 ncu --set full --clock-control none --import-source on $inc -k regex:"$re" -s $skip -c 1 \
       -o $OUT/${TAG}_${name}_full -f python tools/$script > $OUT/${TAG}_${name}_full.log 2>&1
   ncu -i $OUT/${TAG}_${name}_full.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_${name}_raw.csv 2>/dev/null
   rm -f $OUT/${TAG}_${name}_full.ncu-rep
