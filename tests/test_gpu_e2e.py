@@ -664,3 +664,21 @@ def test_shard_equivalence_dna_headline_networks(cuda):
     whole = run(8, 0)
     assert torch.equal(whole, torch.cat([run(4, 0), run(4, 4)], 0)), f'graph={graph}'
     assert torch.equal(whole, torch.cat([run(5, 0), run(3, 5)], 0)), f'graph={graph}'
+
+
+@pytest.mark.parametrize('script,extra,name', [('decode.py', [], 'dna-HepG2.npz'),
+                                               ('decode_tweedie.py', ['--tweedie', 'True'], 'dna-HepG2_tw.npz')])
+def test_cli_dna_decode_and_tweedie(cuda, tmp_path, script, extra, name):
+  """BASELINE configs 2 / 3 through the reference's CLI surface: decode.py --task dna (SVDD-MC,
+  Enformer value net built as decode.py:78-80 does) and decode_tweedie.py --tweedie True (SVDD-PM,
+  3-task Enformer reward oracle), random-init weights, small batch: ./log/dna-HepG2[_tw].npz with
+  float32 (N,) arrays `decoding` and `baseline`."""
+  import subprocess, sys
+  cmd = [sys.executable, script, '--task', 'dna', '--sample_M', '3', '--batch_size', '8', '--val_batch_num', '1',
+         '--reward_name', 'HepG2', '--random_init', '--out_dir', str(tmp_path)] + extra
+  r = subprocess.run(cmd, cwd=helpers.ROOT, capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+  d = np.load(tmp_path / name)
+  assert sorted(d.files) == ['baseline', 'decoding']
+  assert d['decoding'].shape == (8,) and d['decoding'].dtype == np.float32
+  assert d['baseline'].shape == (8,) and np.isfinite(d['decoding']).all() and np.isfinite(d['baseline']).all()
