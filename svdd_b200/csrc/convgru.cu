@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <new>
 
+#include "cg_fused.cuh"
 #include "conv_gemm.cuh"
 #include "gru_umma.cuh"
 #include "weights.cuh"
@@ -392,6 +393,22 @@ __global__ void cg_fold_gate_bias_kernel(const float* __restrict__ bih_f, const 
   if (j >= 2 * kC) bhn[dir * kC + j - 2 * kC] = bhh[j];
 }
 
+// packed stem weight [taps][4][64] fp32 -> bf16 hi / lo tiles [64 out][64 K], K = 4 * tap + token (K >= 4 * taps: zero)
+__global__ void cg_pack_stem_hilo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int taps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kC * kC) return;
+  const int c = i / kC, k = i % kC;
+  const float v = k < 4 * taps ? w[(size_t)k * kC + c] : 0.0f;      // w[(tap * 4 + tok) * 64 + c]
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void cg_fill_kernel(float* __restrict__ p, float v, int n) {
+  if ((int)threadIdx.x < n) p[threadIdx.x] = v;
+}
+
 // W_hh fp32 [n] -> bf16 hi / lo planes (hi = rn(w), lo = rn(w - hi)) for the tcgen05 recurrence
 __global__ void cg_split_hi_lo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, int n) {
@@ -417,6 +434,8 @@ struct svdd_convgru {
   __nv_bfloat16* conv_w[kMaxBlocks] = {};
   float* conv_scale[kMaxBlocks] = {};
   float* conv_shift[kMaxBlocks] = {};   // (or plain bias when there is no BN)
+  __nv_bfloat16* conv_w_all = nullptr;   // [1 + n_blocks][taps][64][64]: layer 0 = stem as (W hi, W lo) over the 60 one-hot features, then the conv weights, contiguous
+  float* conv_ss_all = nullptr;          // [1 + n_blocks][2][64]: scale (1 for the stem / without BN), shift
   __nv_bfloat16* wih = nullptr;          // [384][64]
   float* gate_b = nullptr;               // [384]
   float* whh = nullptr;                  // [2][192][64]
@@ -467,6 +486,8 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
     A.reserve(sizeof(float) * kC);
     A.reserve(sizeof(float) * kC);
   }
+  A.reserve(sizeof(__nv_bfloat16) * (size_t)(nb + 1) * h->taps * kC * kC);
+  A.reserve(sizeof(float) * (size_t)(nb + 1) * 2 * kC);
   A.reserve(sizeof(__nv_bfloat16) * 2 * kG3 * kC);
   A.reserve(sizeof(float) * 2 * kG3);
   A.reserve(sizeof(float) * 2 * kG3 * kC);
@@ -488,6 +509,8 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
     h->conv_scale[i] = A.take<float>(kC);
     h->conv_shift[i] = A.take<float>(kC);
   }
+  h->conv_w_all = A.take<__nv_bfloat16>((size_t)(nb + 1) * h->taps * kC * kC);
+  h->conv_ss_all = A.take<float>((size_t)(nb + 1) * 2 * kC);
   h->wih = A.take<__nv_bfloat16>(2 * kG3 * kC);
   h->gate_b = A.take<float>(2 * kG3);
   h->whh = A.take<float>(2 * kG3 * kC);
@@ -525,6 +548,28 @@ extern "C" int svdd_convgru_create(const svdd_tensor* tensors, int n_tensors, vo
     } else {
       TRY_OR_FAIL(copy_f32(cb, h->conv_shift[i], kC, st));
     }
+  }
+  if (h->taps >= 2 && h->stem_taps * 4 <= kC) {
+    // layer 0 of the fused conv-stack kernel: the stem over one-hot im2col features, bf16 hi / lo tiles
+    if (cudaMemsetAsync(h->conv_w_all, 0, sizeof(__nv_bfloat16) * h->taps * kC * kC, st) != cudaSuccess) return fail(SVDD_ERR_CUDA);
+    cg_pack_stem_hilo_kernel<<<ceil_div(kC * kC, 256), 256, 0, st>>>(h->stem_w, h->conv_w_all, h->conv_w_all + kC * kC, h->stem_taps);
+    cg_fill_kernel<<<1, kC, 0, st>>>(h->conv_ss_all, 1.0f, kC);
+    if (cudaMemcpyAsync(h->conv_ss_all + kC, h->stem_b, sizeof(float) * kC, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(SVDD_ERR_CUDA);
+  }
+  for (int i = 0; i < nb; ++i) {
+    __nv_bfloat16* wdst = h->conv_w_all + (size_t)(i + 1) * h->taps * kC * kC;
+    float* sdst = h->conv_ss_all + (size_t)(i + 1) * 2 * kC;
+    if (cudaMemcpyAsync(wdst, h->conv_w[i], sizeof(__nv_bfloat16) * h->taps * kC * kC, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(SVDD_ERR_CUDA);
+    if (h->has_bn) {
+      if (cudaMemcpyAsync(sdst, h->conv_scale[i], sizeof(float) * kC, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail(SVDD_ERR_CUDA);
+    } else {
+      cg_fill_kernel<<<1, kC, 0, st>>>(sdst, 1.0f, kC);
+    }
+    if (cudaMemcpyAsync(sdst + kC, h->conv_shift[i], sizeof(float) * kC, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(SVDD_ERR_CUDA);
   }
   const std::string gp = "gru_tower.gru.";
   GET_OR_FAIL(wih_f, gp + "weight_ih_l0", (int64_t)kG3 * kC);
@@ -594,6 +639,34 @@ bool gru_umma(int64_t rows) {
   if (e && e[0] == '1') return true;
   return rows >= kGruUmmaMinRows;
 }
+// SVDD_CG_FUSED=0 (read per call): stem + conv blocks as separate launches (one-hot stem kernel + one
+// first-generation implicit GEMM per block) instead of the persistent conv-stack kernel
+bool cg_fused_usable(const svdd_convgru* h, int L) {
+  const char* e = getenv("SVDD_CG_FUSED");
+  if (e && e[0] == '0') return false;
+  return h->n_blocks >= 1 && h->n_blocks <= cgf::kMaxLayers && h->taps % 2 == 1 && h->taps >= 2 && h->taps <= cgf::kMaxTaps &&
+         h->stem_taps * 4 <= kC && h->stem_taps <= 16 && L + h->taps / 2 <= 64 && h->taps / 2 <= cgf::kPad;
+}
+int launch_convstack(const svdd_convgru* h, const void* tok, int tok_dtype, __nv_bfloat16* out, int64_t rows, int L,
+                     cudaStream_t st) {
+  CUtensorMap tW;
+  SVDD_TRY(encode_tmap_2d_bf16(&tW, h->conv_w_all, kC, (uint64_t)(h->n_blocks + 1) * h->taps * kC, kC, kC));
+  cgf::Args a = {};
+  a.tokens = tok; a.ss = h->conv_ss_all; a.out = out;
+  a.rows = rows; a.L = L; a.n_layers = h->n_blocks; a.taps = h->taps; a.stem_taps = h->stem_taps;
+  a.residual = h->residual ? 1 : 0;
+  const int64_t items = ceil_div<int64_t>(rows, cgf::kSeqPerItem);
+  const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+  auto launch = [&](auto kern) -> int {
+    SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cgf::kSmemBytes));
+    SVDD_CUDA(launch_k(kern, dim3(grid), dim3(cgf::kThreads), (size_t)cgf::kSmemBytes, st, 1, tW, a));
+    return SVDD_OK;
+  };
+  if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch(cgf::cg_convstack_kernel<int64_t>));
+  else SVDD_TRY(launch(cgf::cg_convstack_kernel<uint8_t>));
+  count_launch();
+  return SVDD_OK;
+}
 int launch_gru_umma(const svdd_convgru* h, const __nv_bfloat16* x, float* y, int64_t rows, int L, cudaStream_t st) {
   CUtensorMap tX, tWx, tWhi, tWlo;
   SVDD_TRY(encode_tmap_3d_bf16(&tX, x, kC, (uint64_t)L, (uint64_t)rows, (uint64_t)kC * 2, (uint64_t)L * kC * 2, kC, 1,
@@ -655,6 +728,10 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
     CgWs b;
     cg_carve(W, rows, L, &b, !umma);
     const void* tok = reinterpret_cast<const uint8_t*>(tokens) + (size_t)r0 * L * tok_bytes;
+    int cur = 0;
+    if (cg_fused_usable(h, L)) {
+      SVDD_TRY(launch_convstack(h, tok, tok_dtype, b.x[0], rows, L, st));
+    } else {
     const int64_t eg_all = ceil_div<int64_t>(NL, 64);
     const unsigned eg = (unsigned)(eg_all < 8 * (int64_t)num_sms() ? eg_all : 8 * (int64_t)num_sms());
     if (tok_dtype == SVDD_TOK_I64)
@@ -663,7 +740,6 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
       launch_k(cg_embed_kernel<uint8_t>, dim3(eg), dim3(256), 0, st, 1, (const uint8_t*)tok, h->stem_w, h->stem_b, b.x[0], NL, L, h->stem_taps);
     count_launch();
     SVDD_LAUNCH_CHECK();
-    int cur = 0;
     for (int i = 0; i < h->n_blocks; ++i) {
       GemmShape g;
       g.S = (int)rows; g.L = L; g.L_in = L; g.K = kC; g.N = kC; g.taps = h->taps; g.dil = 1;
@@ -676,6 +752,7 @@ extern "C" int svdd_convgru_score(svdd_convgru* h, const void* tokens, int tok_d
       ep.out = b.x[cur ^ 1]; ep.out_dtype = DT_BF16; ep.ld_out = kC;
       SVDD_TRY(launch_conv_gemm(b.x[cur], h->conv_w[i], g, EPI_GENERIC, ep, st));
       cur ^= 1;
+    }
     }
     if (umma) {
       // tcgen05 recurrence with the input projection fused in (csrc/gru_umma.cuh): no gi tensor

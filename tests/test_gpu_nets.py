@@ -460,3 +460,29 @@ def test_convgru_umma_recurrence_matches_mma_sync_path(cuda, n, L, monkeypatch):
     print(f'\n[convgru umma vs mma.sync n={n} L={L}] max |d| = {err:.3e} (scale {float(ref.abs().max()):.3g})')
     assert torch.equal(got, again) and torch.isfinite(got).all()
     assert err <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('n,L', [(77, 50), (1000, 50), (8, 50), (9, 33), (301, 62), (16, 20)])
+def test_convgru_fused_conv_stack_matches_per_layer_launches(cuda, n, L, monkeypatch):
+  """The persistent conv-stack kernel (csrc/cg_fused.cuh: stem + conv blocks of 8 sequences at a time
+  resident in shared memory / TMEM, two sequences per 128-row tile) against the launch-per-layer path
+  (SVDD_CG_FUSED=0, read per call), for the value net (BatchNorm + residual) and the oracle variant
+  (bias only).  Same bf16 rounding points (every layer's output is rounded to bf16 in both), same
+  fp32 accumulation over (tap, channel) -- the scores agree to accumulation-order noise.  Row counts
+  cover partial items, a single item and several items per CTA; L = 62 is the longest sequence
+  the two-per-tile layout admits for k5 convs."""
+  for build in (helpers.build_convgru_value, helpers.build_convgru_oracle):
+    emb, head = build()
+    emb, head = emb.to(cuda), head.to(cuda)
+    tok = helpers.random_tokens(n, L, 41 + n, 0.4).to(cuda)
+    monkeypatch.setenv('SVDD_CG_FUSED', '0')
+    ref = value_nets.score_tokens(emb, head, tok).cpu()
+    monkeypatch.setenv('SVDD_CG_FUSED', '1')
+    before = _lib.launch_count()
+    got = value_nets.score_tokens(emb, head, tok).cpu()
+    launches = _lib.launch_count() - before
+    again = value_nets.score_tokens(emb, head, tok.to(torch.uint8)).cpu()
+    err = float((got - ref).abs().max())
+    print(f'\n[convgru fused conv stack n={n} L={L}] launches={launches} max |d| = {err:.3e} (scale {float(ref.abs().max()):.3g})')
+    assert torch.equal(got, again) and torch.isfinite(got).all()
+    assert err <= 2e-4 * max(1.0, float(ref.abs().max()))

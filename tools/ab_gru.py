@@ -15,7 +15,7 @@ emb, head = emb.to(dev), head.to(dev)
 tok = synthetic.random_tokens(n, 50, 3, 0.3).to(dev).to(torch.uint8)
 res = {}
 for mode in ('0', '1', '0', '1'):
-  os.environ['SVDD_GRU_UMMA'] = mode
+  os.environ[os.environ.get('AB_VAR', 'SVDD_GRU_UMMA')] = mode
   out = value_nets.score_tokens(emb, head, tok)
   torch.cuda.synchronize()
   ts = []
@@ -25,5 +25,5 @@ for mode in ('0', '1', '0', '1'):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
   res[mode] = out.clone()
-  print(f'SVDD_GRU_UMMA={mode}: ConvGRU score of {n} x 50: min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
+  print(f'{os.environ.get("AB_VAR", "SVDD_GRU_UMMA")}={mode}: ConvGRU score of {n} x 50: min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
 print('max |d|', float((res['0'] - res['1']).abs().max()))
