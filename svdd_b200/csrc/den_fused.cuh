@@ -74,6 +74,14 @@ struct Args {
   // both, for every tap whose offset fits the zero gap between them (|o| <= 64 - L).  Taps with
   // larger offsets keep one MMA per sequence on the isolated planes and accumulate into their own
   // TMEM columns (the rows of the other sequence hold garbage there and are never read).
+  // two_seq + split: INTERLEAVED mode (supersedes the combined mode below).  The two sequences of an
+  // item share ONE pair of operand planes with their positions interleaved: plane row 2p = sequence A,
+  // position p; row 2p + 1 = sequence B, position p.  A tap offset o is then a row offset of 2 o, which
+  // keeps A's rows reading A's rows and B's reading B's for EVERY offset (parity is preserved), and the
+  // zero rows either side of the 2 L real rows are the conv padding of both.  One 128-row MMA per tap
+  // serves both sequences for all taps: no isolated planes, no extra accumulators (TMEM: accumulator
+  // + residual = 256 columns), L = 50: 141 MMA groups per item (combined mode 173, two tiles 281).
+  int ilv;
   int cmb;                   // combined mode on
   int cmb_max;               // largest |tap offset| served by the combined planes
   int pad_c;                 // zero rows in front of a combined plane
@@ -239,7 +247,28 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         ptx::tc_fence_after();
         const int taps = r < nl ? kTaps : 1;
         const int dil = r < nl ? a.dil[r] : 1;
-        if (a.cmb) {
+        if (a.ilv) {
+          uint32_t st = 0u;
+          for (int t = 0; t < taps; ++t) {
+            const int o = (t - taps / 2) * dil;
+            if (!(o > -L && o < L)) continue;
+            for (int kb = 0; kb < 2; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
+                const uint64_t da = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes + (uint32_t)(a.pad_before + 2 * o) * 128u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (st | (uint32_t)k) != 0u);
+                ptx::umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              st = 1u;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else if (a.cmb) {
           // combined mode: acc0 (cols 0..127) <- taps on the combined planes, both sequences;
           // cols 256.. <- sequence A's isolated taps, cols 128.. <- sequence B's
           const uint32_t c_base = ptx::smem_u32(s_c);
@@ -755,19 +784,23 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int ew = warp - 2;
     const int half = ew >> 2;
     const int quad = warp & 3;
-    const int m = quad >> 1;
     const int etid = threadIdx.x - 64;
-    const int row = (quad & 1) * 32 + lane;                      // position within the sequence
+    const bool ilv = a.ilv != 0;
     const bool cmb = a.cmb != 0;
-    const int arow = a.pad_before + a.iso_b * m + row;           // isolated planes (pad_before, iso_b: multiples of 8)
+    const int rq = quad * 32 + lane;                             // tile row = TMEM lane
+    const int m = ilv ? (rq & 1) : (quad >> 1);                  // sequence of the item
+    const int row = ilv ? (rq >> 1) : ((quad & 1) * 32 + lane);  // position within the sequence
+    // plane row: interleaved = pad + tile row; otherwise the isolated planes (pad_before, iso_b: multiples of 8)
+    const int arow = ilv ? a.pad_before + rq : a.pad_before + a.iso_b * m + row;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_acc = t_lane + (cmb ? 0 : m * kH) + half * 64;
+    const uint32_t t_acc = t_lane + ((cmb || ilv) ? 0 : m * kH) + half * 64;
     const uint32_t t_iso = t_lane + (m == 0 ? 2 * kH : kH) + half * 64;       // cmb: this sequence's isolated taps
-    const uint32_t t_res = cmb ? t_lane + 3 * kH + half * 64 : t_acc + 2 * kH;   // cmb: one block, lanes 0..63 / 64..127
+    const uint32_t t_res = ilv ? t_lane + kH + half * 64                      // ilv: accumulator | residual
+                               : (cmb ? t_lane + 3 * kH + half * 64 : t_acc + 2 * kH);   // cmb: one block, lanes 0..63 / 64..127
     uint8_t* a_rowh = s_a + (size_t)half * plane_bytes + (size_t)arow * 128;
     uint8_t* c_rowh = s_c + (size_t)half * c_plane_bytes + (size_t)(a.pad_c + 64 * m + row) * 128;   // combined planes
-    const int x7 = arow & 7;                                     // == row & 7 on both kinds of plane
-    const bool wact = (row - lane) < L;
+    const int x7 = arow & 7;                                     // == tile row & 7 on every kind of plane
+    const bool wact = ilv ? (quad * 32 < 2 * L) : ((row - lane) < L);
     const int ch0 = half * 64;
     const Tok* tokens = reinterpret_cast<const Tok*>(a.tokens);
     uint32_t tphase = 0;

@@ -231,8 +231,29 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
   // sequences on a second pair of planes where they sit 64 rows apart, for taps whose offset fits the
   // zero gap (|o| <= 64 - L); the other taps stay on the isolated planes.  L = 50: 173 instead of 281
   // MMA groups per item.  SVDD_DEN_CMB=0 (read per call) keeps the two-tile scheme for the A/B test.
+  // Interleaved mode (two sequences per CTA, split epilogue): plane row 2p / 2p+1 = position p of
+  // sequence A / B, a tap offset o is a row offset of 2 o, ONE 128-row MMA per tap serves both sequences
+  // for every tap (L = 50: 141 MMA groups per item; combined mode 173, two tiles 281), one pair of planes,
+  // accumulator + residual = 256 TMEM columns.  SVDD_DEN_ILV=0 (read per call) falls back to the
+  // combined mode below (and SVDD_DEN_CMB=0 further to the two-tile scheme): the A/B and cross-checks.
+  const char* env_ilv = getenv("SVDD_DEN_ILV");
+  bool use_ilv = false;
+  if (a.split && !(env_ilv && atoi(env_ilv) == 0)) {
+    denf::Args c = a;
+    int max_o = 0;
+    for (int i = 0; i < h->n_layers; ++i)
+      for (int t = 0; t < kTaps; ++t) {
+        const int o = (t - kTaps / 2) * h->dil[i], ao = o < 0 ? -o : o;
+        if (ao < L && ao > max_o) max_o = ao;
+      }
+    c.ilv = 1;
+    c.pad_before = (2 * max_o + 7) & ~7;
+    c.a_rows = c.pad_before + 128 + c.pad_before;
+    const int smem_i = denf::smem_bytes(c.a_rows);
+    if (smem_i <= 227 * 1024) { a = c; smem = smem_i; use_ilv = true; }
+  }
   const char* env_cmb = getenv("SVDD_DEN_CMB");
-  if (a.split && !(env_cmb && atoi(env_cmb) == 0)) {
+  if (!use_ilv && a.split && !(env_cmb && atoi(env_cmb) == 0)) {
     denf::Args c = a;
     c.cmb = 1;
     c.cmb_max = 64 - L;

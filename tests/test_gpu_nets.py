@@ -128,6 +128,7 @@ def test_denoiser_combined_planes_match_two_tile_scheme(cuda, L, n, monkeypatch)
   m = helpers.build_denoiser(44, L).to(cuda)
   x = helpers.random_tokens(n, L, 13, 0.5).to(cuda).to(torch.uint8)
   den = m.packed()
+  monkeypatch.setenv('SVDD_DEN_ILV', '0')
   monkeypatch.setenv('SVDD_DEN_CMB', '0')
   two = den.forward(x, 0.0).clone()
   monkeypatch.setenv('SVDD_DEN_CMB', '1')
@@ -143,6 +144,16 @@ def test_denoiser_combined_planes_match_two_tile_scheme(cuda, L, n, monkeypatch)
   # odd batch: the last CTA item holds one sequence only
   one = den.forward(x[:1].contiguous(), 0.0)
   assert torch.equal(one[0], cmb[0])
+  # the default: interleaved planes (row 2p / 2p+1 = position p of sequence A / B; one MMA per tap for both)
+  monkeypatch.setenv('SVDD_DEN_ILV', '1')
+  ilv = den.forward(x, 0.0).clone()
+  assert torch.equal(ilv, den.forward(x, 0.0)), 'interleaved mode is not deterministic'
+  e3 = float((ilv - two).abs().max()) / scale
+  print(f'[denoiser interleaved vs two-tile L={L} n={n}] rel.err {e3:.3e}')
+  assert e3 < 6e-3
+  assert torch.equal(den.forward(x[:1].contiguous(), 0.0)[0], ilv[0])
+  if n >= 3:      # a sequence gives the same logits in the A slot and in the B slot of an item
+    assert torch.equal(den.forward(x[1:3].contiguous(), 0.0)[0], ilv[1])
 
 
 def test_convgru_value(cuda):

@@ -16,9 +16,9 @@ m = synthetic.build_denoiser(44, L).to(dev)
 den = m.packed()
 x = synthetic.random_tokens(n, L, 5, 0.5).to(dev).to(torch.uint8)
 out = {}
-for cmb in ('0', '1', '16', '1', '16'):
+for cmb in ('0', '1', 'ilv', '1', 'ilv'):
+  os.environ['SVDD_DEN_ILV'] = '1' if cmb == 'ilv' else '0'
   os.environ['SVDD_DEN_CMB'] = '0' if cmb == '0' else '1'
-  os.environ['SVDD_DEN_EW'] = '16' if cmb == '16' else '8'
   y = den.forward(x, 0.0)
   torch.cuda.synchronize()
   ts = []
@@ -28,7 +28,7 @@ for cmb in ('0', '1', '16', '1', '16'):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
   out[cmb] = y.clone()
-  print(f'mode {cmb} (0 = two tiles, 1 = combined planes / 8 warps, 16 = combined / 16 warps): n={n} L={L} min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
-for k in ('1', '16'):
+  print(f'mode {cmb} (0 = two tiles, 1 = combined planes, ilv = interleaved planes): n={n} L={L} min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
+for k in ('1', 'ilv'):
   d = float((out['0'] - out[k]).abs().max())
   print(f'max |d| mode 0 vs {k}: {d:.3e} (scale {float(out["0"].abs().max()):.3g})')
