@@ -15,6 +15,7 @@
 
 #include "conv_gemm.cuh"
 #include "den_fused.cuh"
+#include "den_short.cuh"
 #include "weights.cuh"
 
 namespace svdd {
@@ -290,6 +291,30 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
   SVDD_TRY(encode_tmap_2d_bf16(&tmW0, h->fc0_w, kH, kH, 64, kH));
   const int64_t items = a.two_seq ? (n_rows + 1) / 2 : n_rows;
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+  // Interleaved mode with TWO items (four sequences) in flight per CTA (csrc/den_short.cuh): while the
+  // epilogue warps work on one item's round the tensor core runs the other's.  SVDD_DEN_PAIR=0 (read
+  // per call) keeps one item per CTA (den_fused_kernel): the A/B and the cross-check in the tests.
+  {
+    // Measured (tools/ab_den_cmb.py): 51 200 x 50: 15.9 vs 21.1 ms; 999 x 33: 0.37 vs 0.47 ms; but 10 x 50:
+    // 0.20 vs 0.14 ms -- with fewer items than SMs one item per CTA finishes sooner, so two items share a
+    // CTA only when there are more items than SMs (SVDD_DEN_PAIR=1 / 0 forces either).
+    const char* env_pair = getenv("SVDD_DEN_PAIR");
+    const bool want_pair = env_pair ? atoi(env_pair) != 0 : items > num_sms();
+    if (a.ilv && want_pair && dens::smem_bytes(a.pad_before) <= 227 * 1024) {
+      const int smem2 = dens::smem_bytes(a.pad_before);
+      const int64_t pairs = (items + 1) / 2;
+      const unsigned grid2 = (unsigned)(pairs < num_sms() ? pairs : num_sms());
+      auto launch2 = [&](auto kern) -> int {
+        SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SVDD_CUDA(launch_k(kern, dim3(grid2), dim3(dens::kThreads), (size_t)smem2, st, 1, tmW, tmW0, a));
+        return SVDD_OK;
+      };
+      if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch2(dens::den_short_kernel<int64_t>));
+      else SVDD_TRY(launch2(dens::den_short_kernel<uint8_t>));
+      count_launch();
+      return SVDD_OK;
+    }
+  }
   // SVDD_DEN_EW=16 (read per call): combined mode with the 16-warp quad epilogue (thread = quarter
   // of a row).  Measured SLOWER than the 8-warp split epilogue -- 27.9 vs 24.2 ms per 51200 x 50 pass,
   // 0.61 vs 0.54 ms at 999 x 33: the round is a chain of fixed latencies (accumulator hand-over,

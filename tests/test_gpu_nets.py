@@ -144,9 +144,17 @@ def test_denoiser_combined_planes_match_two_tile_scheme(cuda, L, n, monkeypatch)
   # odd batch: the last CTA item holds one sequence only
   one = den.forward(x[:1].contiguous(), 0.0)
   assert torch.equal(one[0], cmb[0])
-  # the default: interleaved planes (row 2p / 2p+1 = position p of sequence A / B; one MMA per tap for both)
+  # interleaved planes (row 2p / 2p+1 = position p of sequence A / B; one MMA per tap for both), one item per CTA ...
   monkeypatch.setenv('SVDD_DEN_ILV', '1')
+  monkeypatch.setenv('SVDD_DEN_PAIR', '0')
+  ilv1 = den.forward(x, 0.0).clone()
+  # ... and the default: two items (four sequences) in flight per CTA (csrc/den_short.cuh)
+  monkeypatch.setenv('SVDD_DEN_PAIR', '1')
   ilv = den.forward(x, 0.0).clone()
+  assert torch.equal(ilv, ilv1), 'two items in flight must not change a single bit'
+  for k in (1, 2, 3, 5):          # partial pairs / items at the end of the batch
+    if k <= n:
+      assert torch.equal(den.forward(x[:k].contiguous(), 0.0), ilv[:k]), k
   assert torch.equal(ilv, den.forward(x, 0.0)), 'interleaved mode is not deterministic'
   e3 = float((ilv - two).abs().max()) / scale
   print(f'[denoiser interleaved vs two-tile L={L} n={n}] rel.err {e3:.3e}')
