@@ -3,8 +3,8 @@
 #   * full -m gpu test suite, bench.py (N = 1) and its reference arm
 #   * ncu launch list (time, tensor pipe, DRAM bytes) of one eager c2 reverse step, one RNA
 #     SVDD-PM step (c5-shaped, B = 256) and one DiT forward
-#   * ncu --set full of the tower kernel, the fused denoiser at L = 50 (combined mode) and the DiT
-#     attention kernel; raw pages as CSV
+#   * ncu --set full of the tower kernel, the fused denoiser at L = 50 (one item per CTA and
+#     den_short_kernel), the GRU recurrence and the DiT attention kernel; raw pages as CSV
 #   gpurun --timeout 2400 -- 'bash tools/r02_profile.sh r02'
 TAG=${1:-r02}
 OUT=gpurun_out
@@ -18,7 +18,8 @@ timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measur
     --csv --log-file $OUT/${TAG}_launches_c2_step.csv python tools/profile_step.py --steps 1 > $OUT/${TAG}_launches.log 2>&1
 timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measured/" \
     --csv --log-file $OUT/${TAG}_launches_c5_step.csv python tools/profile_step_rna.py --steps 1 > $OUT/${TAG}_launches_c5.log 2>&1
-for spec in "tower:tower_kernel:profile_step.py:0" "den_l50:den_fused_kernel:profile_step_rna.py:1" "gru_umma:cg_gru_umma_kernel:profile_step_rna.py --B 1024:0" "dit_attn:dit_attn_small_kernel:time_dit.py 64 200:1"; do
+SPECS_ONLY=${2:-}
+for spec in "tower:tower_kernel:profile_step.py:0" "den_single_l50:den_fused_kernel:profile_step_rna.py:1" "den_short:den_short_kernel:profile_step_rna.py:0" "gru_umma:cg_gru_umma_kernel:profile_step_rna.py --B 1024:0" "dit_attn:dit_attn_small_kernel:time_dit.py 64 200:1"; do
   name=${spec%%:*}; rest=${spec#*:}; re=${rest%%:*}; rest=${rest#*:}; script=${rest%%:*}; skip=${rest#*:}
   inc="--nvtx --nvtx-include measured/"
   if [ "$name" = "dit_attn" ]; then inc=""; export SVDD_TIME_DIT_NO_PROFILE=1; fi
