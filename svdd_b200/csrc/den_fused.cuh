@@ -236,10 +236,19 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // ONE elected thread runs the whole loop (as the producer does).  With an elect region per
+    // weight stage the issuing warp spent ~60 instructions per stage on descriptor set-up, elect /
+    // reconverge and loop control and was the critical path of den_short_kernel (see there); here
+    // the descriptors are kept as their low words and advanced by adds.
+    if (ptx::elect_one()) {
     constexpr uint32_t idesc = ptx::make_idesc_bf16(128, kH);
+    constexpr uint32_t kStage16 = kStageBytes >> 4;
     uint32_t stage = 0, phase = 0;
     uint32_t round = 0;                      // aready phase counter
     const uint32_t a_base = ptx::smem_u32(s_a);
+    const uint32_t a_lo = ptx::kmajor_sw128_desc_lo(a_base);
+    const uint32_t ring_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_ring));
+    const uint32_t plane16 = (uint32_t)plane_bytes >> 4;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
       const bool live1 = tile_live(it, 1);
       for (int r = 0; r <= nl; ++r, ++round) {
@@ -249,21 +258,19 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const int dil = r < nl ? a.dil[r] : 1;
         if (a.ilv) {
           uint32_t st = 0u;
+          const uint32_t aq = a_lo + (uint32_t)a.pad_before * 8u;   // one plane row = 8 descriptor units
           for (int t = 0; t < taps; ++t) {
             const int o = (t - taps / 2) * dil;
             if (!(o > -L && o < L)) continue;
-            for (int kb = 0; kb < 2; ++kb) {
+            for (uint32_t kb = 0; kb < 2; ++kb) {
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
-                const uint64_t da = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes + (uint32_t)(a.pad_before + 2 * o) * 128u);
+              const uint32_t db = ring_lo + stage * kStage16;
+              const uint32_t da = aq + (uint32_t)(16 * o) + kb * plane16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (st | (uint32_t)k) != 0u);
-                ptx::umma_commit(&empty_bar[stage]);
-              }
-              __syncwarp();
+              for (uint32_t k = 0; k < 4; ++k)
+                ptx::umma_bf16_lo(tmem_base, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
+              ptx::umma_commit(&empty_bar[stage]);
               st = 1u;
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -271,78 +278,75 @@ den_fused_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         } else if (a.cmb) {
           // combined mode: acc0 (cols 0..127) <- taps on the combined planes, both sequences;
           // cols 256.. <- sequence A's isolated taps, cols 128.. <- sequence B's
-          const uint32_t c_base = ptx::smem_u32(s_c);
+          const uint32_t c_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_c));
+          const uint32_t cplane16 = (uint32_t)c_plane_bytes >> 4;
           uint32_t st_c = 0u, st_a = 0u, st_b = 0u;
           for (int t = 0; t < taps; ++t) {
             const int o = (t - taps / 2) * dil;
             if (!(o > -L && o < L)) continue;
             const bool comb = (o < 0 ? -o : o) <= a.cmb_max;
-            for (int kb = 0; kb < 2; ++kb) {
+            for (uint32_t kb = 0; kb < 2; ++kb) {
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
-                if (comb) {
-                  const uint64_t da = ptx::make_kmajor_sw128_desc(c_base + kb * c_plane_bytes + (uint32_t)(a.pad_c + o) * 128u);
+              const uint32_t db = ring_lo + stage * kStage16;
+              if (comb) {
+                const uint32_t da = c_lo + kb * cplane16 + (uint32_t)((a.pad_c + o) * 8);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (st_c | (uint32_t)k) != 0u);
-                } else {
-                  const uint64_t da0 = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes + (uint32_t)(a.pad_before + o) * 128u);
+                for (uint32_t k = 0; k < 4; ++k)
+                  ptx::umma_bf16_lo(tmem_base, da + 2 * k, db + 2 * k, idesc, (st_c | k) != 0u);
+              } else {
+                const uint32_t da0 = a_lo + kb * plane16 + (uint32_t)((a.pad_before + o) * 8);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem_base + 2 * kH, da0 + 2 * k, db + 2 * k, idesc, (st_a | (uint32_t)k) != 0u);
-                  if (live1) {
-                    const uint64_t da1 = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes +
-                                                                     (uint32_t)(a.pad_before + a.iso_b - 64 + o) * 128u);
+                for (uint32_t k = 0; k < 4; ++k)
+                  ptx::umma_bf16_lo(tmem_base + 2 * kH, da0 + 2 * k, db + 2 * k, idesc, (st_a | k) != 0u);
+                if (live1) {
+                  const uint32_t da1 = a_lo + kb * plane16 + (uint32_t)((a.pad_before + a.iso_b - 64 + o) * 8);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      ptx::umma_bf16(tmem_base + kH, da1 + 2 * k, db + 2 * k, idesc, (st_b | (uint32_t)k) != 0u);
-                  }
+                  for (uint32_t k = 0; k < 4; ++k)
+                    ptx::umma_bf16_lo(tmem_base + kH, da1 + 2 * k, db + 2 * k, idesc, (st_b | k) != 0u);
                 }
-                ptx::umma_commit(&empty_bar[stage]);
               }
-              __syncwarp();
+              ptx::umma_commit(&empty_bar[stage]);
               if (comb) st_c = 1u; else { st_a = 1u; st_b = 1u; }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
         } else {
-        uint32_t started[2] = {0u, 0u};
-        for (int t = 0; t < taps; ++t) {
-          const int o = (t - taps / 2) * dil;
-          const bool hit0 = tap_hits(0, o, L, two_seq);
-          const bool hit1 = live1 && tap_hits(1, o, L, two_seq);
-          if (!(hit0 || hit1)) continue;
-          for (int kb = 0; kb < 2; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
+          uint32_t started[2] = {0u, 0u};
+          for (int t = 0; t < taps; ++t) {
+            const int o = (t - taps / 2) * dil;
+            const bool hit0 = tap_hits(0, o, L, two_seq);
+            const bool hit1 = live1 && tap_hits(1, o, L, two_seq);
+            if (!(hit0 || hit1)) continue;
+            // 128 rows of a K half starting at tile_plane_row: the tap is a row offset
+            const uint32_t da0 = a_lo + (uint32_t)((a.pad_before + tile_plane_row(0, o, two_seq)) * 8);
+            const uint32_t da1 = a_lo + (uint32_t)((a.pad_before + tile_plane_row(1, o, two_seq)) * 8);
+            for (uint32_t kb = 0; kb < 2; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              const uint32_t db = ring_lo + stage * kStage16;
+              if (hit0) {
 #pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                if (m == 0 ? !hit0 : !hit1) continue;
-                // 128 rows of K half kb starting at tile_plane_row: the tap is a row offset
-                const uint32_t sa = a_base + kb * plane_bytes + (uint32_t)(a.pad_before + tile_plane_row(m, o, two_seq)) * 128u;
-                const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                for (uint32_t k = 0; k < 4; ++k)
+                  ptx::umma_bf16_lo(tmem_base, da0 + kb * plane16 + 2 * k, db + 2 * k, idesc, (started[0] | k) != 0u);
+              }
+              if (hit1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(tmem_base + m * kH, da + 2 * k, db + 2 * k, idesc, (started[m] | (uint32_t)k) != 0u);
-                started[m] = 1u;
+                for (uint32_t k = 0; k < 4; ++k)
+                  ptx::umma_bf16_lo(tmem_base + kH, da1 + kb * plane16 + 2 * k, db + 2 * k, idesc, (started[1] | k) != 0u);
               }
               ptx::umma_commit(&empty_bar[stage]);
+              started[0] |= hit0 ? 1u : 0u;
+              started[1] |= hit1 ? 1u : 0u;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            started[0] |= hit0 ? 1u : 0u;
-            started[1] |= hit1 ? 1u : 0u;
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        }
-        if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
-        __syncwarp();
+        ptx::umma_commit(tfull_bar);
       }
     }
+    }
+    __syncwarp();
   } else if constexpr (EW == 16) {
     // ===================== quad epilogue (combined mode, 16 warps) =====================
     // TMEM lane quadrant q = warp & 3 holds rows 32 (q & 1) .. +31 of sequence q >> 1; the four

@@ -132,46 +132,63 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, kH);
-    uint32_t stage = 0, phase = 0;
-    uint32_t rounds[2] = {0u, 0u};           // aready completions consumed per item slot
-    const uint32_t a_base = ptx::smem_u32(s_a);
-    for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
-      const bool live1 = 2 * p + 1 < items;
-      for (int r = 0; r <= nl; ++r) {
-        const int taps = r < nl ? kTaps : 1;
-        const int dil = r < nl ? a.dil[r] : 1;
-        for (int q = 0; q < 2; ++q) {
-          if (q == 1 && !live1) continue;
-          ptx::mbar_wait(&aready_bar[q], rounds[q] & 1);
-          ++rounds[q];
-          ptx::tc_fence_after();
-          const uint32_t row0 = (uint32_t)(pad + q * (128 + pad));
-          uint32_t st = 0u;
-          for (int t = 0; t < taps; ++t) {
-            const int o = (t - taps / 2) * dil;
-            if (!tap_used(o)) continue;
-            for (int kb = 0; kb < 2; ++kb) {
+    // ONE elected thread runs the whole loop (as the producer does): with an elect region per
+    // weight stage the issuing warp needed ~60 instructions for every 4 MMAs (descriptor set-up,
+    // elect / reconverge, loop control: ~575 cycles per stage against 256 tensor cycles; ncu source
+    // page, profiles/r02_ncu_full_den_short_source_before.csv) and was the kernel's critical path.
+    // Descriptors are kept as their low words and advanced by adds; a tap always takes two ring
+    // stages (kStages is even), so both are handled in one iteration.
+    static_assert(kStages % 2 == 0, "a tap uses two consecutive ring stages");
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, kH);
+      constexpr uint32_t kStage16 = kStageBytes >> 4;
+      const uint32_t ring_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_ring));
+      const uint32_t a_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_a));
+      const uint32_t plane16 = (uint32_t)plane_bytes >> 4;
+      uint32_t stage = 0, phase = 0;
+      uint32_t rounds[2] = {0u, 0u};           // aready completions consumed per item slot
+      for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
+        const bool live1 = 2 * p + 1 < items;
+        for (int r = 0; r <= nl; ++r) {
+          const int taps = r < nl ? kTaps : 1;
+          const int dil = r < nl ? a.dil[r] : 1;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !live1) continue;
+            ptx::mbar_wait(&aready_bar[q], rounds[q] & 1);
+            ++rounds[q];
+            ptx::tc_fence_after();
+            const uint32_t tm = tmem_base + q * 2 * kH;
+            // one plane row = 128 bytes = 8 descriptor units; tap offset o = 2 o rows
+            const uint32_t aq = a_lo + (uint32_t)(pad + q * (128 + pad)) * 8u;
+            uint32_t st = 0u;
+            for (int t = 0; t < taps; ++t) {
+              const int o = (t - taps / 2) * dil;
+              if (!tap_used(o)) continue;
+              const uint32_t da = aq + (uint32_t)(16 * o);
+              const uint32_t db = ring_lo + stage * kStage16;
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s_ring + stage * kStageBytes));
-                const uint64_t da = ptx::make_kmajor_sw128_desc(a_base + kb * plane_bytes + (uint32_t)((int)row0 + 2 * o) * 128u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(tmem_base + q * 2 * kH, da + 2 * k, db + 2 * k, idesc, (st | (uint32_t)k) != 0u);
-                ptx::umma_commit(&empty_bar[stage]);
-              }
-              __syncwarp();
+              for (uint32_t k = 0; k < 4; ++k)
+                ptx::umma_bf16_lo(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
+              ptx::umma_commit(&empty_bar[stage]);
+              ptx::mbar_wait(&full_bar[stage + 1], phase);
+              ptx::tc_fence_after();
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k)
+                ptx::umma_bf16_lo(tm, da + plane16 + 2 * k, db + kStage16 + 2 * k, idesc, 1u);
+              ptx::umma_commit(&empty_bar[stage + 1]);
               st = 1u;
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              stage += 2;
+              if (stage == kStages) { stage = 0; phase ^= 1; }
             }
+            ptx::umma_commit(&tfull_bar[q]);
           }
-          if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[q]);
-          __syncwarp();
         }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue: two threads per row (64 channels each), items in turn =====================
     const int ew = warp - 2;

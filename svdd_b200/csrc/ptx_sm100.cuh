@@ -216,6 +216,24 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout: SWIZZLE_128B
   return d;
 }
+// The same descriptor as two words: the high word is a constant, the low word carries the start
+// address (and the unused leading-byte-offset field), so an issuing thread can keep descriptors as
+// 32-bit values and advance them with plain adds (+2 per 32-byte K step, +8 per 128-byte row).
+constexpr uint32_t kKmajorSw128DescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t kmajor_sw128_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(kKmajorSw128DescHi)
+      : "memory");
+}
 // kind::f16 instruction descriptor: BF16 x BF16 -> FP32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4)                     // D format F32

@@ -18,7 +18,6 @@ timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measur
     --csv --log-file $OUT/${TAG}_launches_c2_step.csv python tools/profile_step.py --steps 1 > $OUT/${TAG}_launches.log 2>&1
 timeout 600 ncu --metrics $M1 --clock-control none --nvtx --nvtx-include "measured/" \
     --csv --log-file $OUT/${TAG}_launches_c5_step.csv python tools/profile_step_rna.py --steps 1 > $OUT/${TAG}_launches_c5.log 2>&1
-SPECS_ONLY=${2:-}
 for spec in "tower:tower_kernel:profile_step.py:0" "den_single_l50:den_fused_kernel:profile_step_rna.py:1" "den_short:den_short_kernel:profile_step_rna.py:0" "gru_umma:cg_gru_umma_kernel:profile_step_rna.py --B 1024:0" "dit_attn:dit_attn_small_kernel:time_dit.py 64 200:1"; do
   name=${spec%%:*}; rest=${spec#*:}; re=${rest%%:*}; rest=${rest#*:}; script=${rest%%:*}; skip=${rest#*:}
   inc="--nvtx --nvtx-include measured/"
