@@ -104,6 +104,12 @@ def run(args, tweedie=False):
     np.savez(os.path.join(args.out_dir, name), decoding=ours, baseline=baseline)
     print('decoding median %.4f  baseline median %.4f  -> %s.npz' %
           (float(np.median(ours)), float(np.median(baseline)), os.path.join(args.out_dir, name)))
+    t = model.timing
+    n = t['batch_size']
+    print('timing: SVDD %d x %d sequences in %.3f s (%.1f seq/s incl. capture and final scoring); '
+          'baseline %d x %d rollouts in %.3f s (%.1f seq/s)' %
+          (t['svdd_batches'], n, t['svdd_s'], t['svdd_batches'] * n / t['svdd_s'],
+           t['baseline_rollouts'], n, t['baseline_s'], t['baseline_rollouts'] * n / t['baseline_s']))
   return out
 
 

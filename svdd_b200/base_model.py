@@ -19,6 +19,7 @@ Differences that are forced by the environment or are additions:
 Training (``forward``, optimizers) is out of scope.
 """
 import os
+import time
 
 import torch
 from torch import nn
@@ -177,15 +178,27 @@ class BaseModel(nn.Module):
     self.eval_time_step_targets = [torch.cat(y, 0) for y in ys]
 
   # -- decoding ----------------------------------------------------------------------------------
+  @staticmethod
+  def _tick():
+    if torch.cuda.is_available():
+      torch.cuda.synchronize()
+    return time.perf_counter()
+
   def _decode(self, gen_batch_num, sample_M, sampler, topk):
+    """The body shared by controlled_decode / controlled_decode_tweedie (Enformer.py:439-477,
+    762-813).  ``self.timing`` afterwards holds the wall-clock seconds of its two phases (one
+    device synchronisation at each phase boundary): the value-weighted SVDD batches with their
+    final value / reward scoring, and the gen_batch_num * sample_M plain baseline rollouts."""
     rows, offset = self._local_batch()
     samples, value_preds, reward_preds = [], [], []
+    t0 = self._tick()
     for i in range(gen_batch_num):
       batch = sampler(rows, offset + i * self.NUM_SAMPLES_PER_BATCH)
       batch = sharding.gather_rows(batch)                # final gather of the sequences
       samples.append(batch)
       value_preds.append(self._value(batch))
       reward_preds.append(self._reward(batch))
+    t1 = self._tick()
     print('Value-weighted sampling done.')
     baseline_preds, all_preds = [], []
     for i in range(gen_batch_num * sample_M):            # Enformer.py:456-467
@@ -194,7 +207,10 @@ class BaseModel(nn.Module):
       if i < gen_batch_num:
         baseline_preds.append(pred)
       all_preds.append(pred)
+    t2 = self._tick()
     print('Baseline sampling done.')
+    self.timing = {'svdd_s': t1 - t0, 'baseline_s': t2 - t1, 'svdd_batches': gen_batch_num,
+                   'baseline_rollouts': gen_batch_num * sample_M, 'batch_size': self.NUM_SAMPLES_PER_BATCH}
     baseline = torch.cat(baseline_preds)
     if topk:                                              # Enformer.py:471-475
       all_values = torch.cat(all_preds)

@@ -89,6 +89,9 @@ struct Args {
   int iso_b;                 // isolated planes: row distance between the two sequences (legacy: 128)
   unsigned char iso[kMaxLayers + 1];   // round r has taps on the isolated planes
   int dil[kMaxLayers];
+  // den_short_kernel only, tuning aid (SVDD_DEN_TRACE=<csv>, tools/den_trace.py): SM clock stamps of CTA 0's
+  // third pair, [round][item][8 slots]
+  unsigned long long* trace;
 };
 
 __host__ __device__ inline int smem_bytes(int a_rows, int c_rows = 0) {

@@ -102,6 +102,11 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   pdl_trigger();
 
   auto tap_used = [&](int o) { return o > -L && o < L; };
+  // tuning aid: SM clock at the hand-over points of one pair (the CTA's third) of CTA 0
+  auto stamp = [&](int64_t p, int r, int q, int slot) {
+    if (a.trace != nullptr && blockIdx.x == 0 && p == 2 * (int64_t)gridDim.x)
+      a.trace[(size_t)(r * 2 + q) * 8 + slot] = (unsigned long long)clock64();
+  };
 
   if (warp == 0) {
     // ===================== weight producer: the taps of (item 0, round), (item 1, round), ... =====================
@@ -158,6 +163,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             ptx::mbar_wait(&aready_bar[q], rounds[q] & 1);
             ++rounds[q];
             ptx::tc_fence_after();
+            stamp(p, r, q, 0);
             const uint32_t tm = tmem_base + q * 2 * kH;
             // one plane row = 128 bytes = 8 descriptor units; tap offset o = 2 o rows
             const uint32_t aq = a_lo + (uint32_t)(pad + q * (128 + pad)) * 8u;
@@ -169,6 +175,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
               const uint32_t db = ring_lo + stage * kStage16;
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tc_fence_after();
+              if (st == 0u) stamp(p, r, q, 1);
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k)
                 ptx::umma_bf16_lo(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
@@ -184,6 +191,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
               if (stage == kStages) { stage = 0; phase ^= 1; }
             }
             ptx::umma_commit(&tfull_bar[q]);
+            stamp(p, r, q, 2);
           }
         }
       }
@@ -250,18 +258,25 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
                                  denf::pack2(v[8 * j + 4], v[8 * j + 5]), denf::pack2(v[8 * j + 6], v[8 * j + 7])));
       }
     };
-    // slots of round r: [bias_r, tbias_{r+1}, gamma_{r+1}, beta_{r+1}]; staged once per round, by item 0's turn
-    auto stage_params = [&](int r, float* P) {
-      for (int i = etid; i < kH; i += kEpiThreads) {
-        P[i] = r < nl ? a.conv_b[r * kH + i] : a.fc0_b[i];
-        if (r + 1 < nl) {
-          P[1 * kH + i] = a.time_bias[(r + 1) * kH + i];
-          P[2 * kH + i] = a.ln_g[(r + 1) * kH + i];
-          P[3 * kH + i] = a.ln_b[(r + 1) * kH + i];
-        }
+    // slots of round r: [bias_r, tbias_{r+1}, gamma_{r+1}, beta_{r+1}] = 512 floats, two per thread.
+    // The values of round r + 1 are LOADED at the top of round r (global / L2 latency hidden behind the
+    // round's epilogues) and STORED to the other buffer at its end; the block barrier at the top of
+    // round r + 1 publishes them.  (Loading them at the top of their own round put ~0.5 us of load
+    // latency + barrier in front of item 0's epilogue every round.)
+    auto load_params = [&](int r, float& p0, float& p1) {
+      const int i = etid & (kH - 1);
+      if (etid < kH) {
+        p0 = r < nl ? a.conv_b[r * kH + i] : a.fc0_b[i];
+        p1 = r + 1 < nl ? a.ln_g[(r + 1) * kH + i] : 0.0f;
+      } else {
+        p0 = r + 1 < nl ? a.time_bias[(r + 1) * kH + i] : 0.0f;
+        p1 = r + 1 < nl ? a.ln_b[(r + 1) * kH + i] : 0.0f;
       }
     };
-
+    auto store_params = [&](float* P, float p0, float p1) {
+      P[etid] = p0;                  // [bias | tbias]
+      P[2 * kH + etid] = p1;         // [gamma | beta]
+    };
     for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
       const bool live1 = 2 * p + 1 < items;
       // ---- embed both items: Conv(5 -> 128, k9) as a weight gather, ReLU, LayerNorm_0 ----
@@ -272,7 +287,9 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           P[2 * kH + i] = a.ln_g[i];
           P[3 * kH + i] = a.ln_b[i];
         }
-        epi_sync();
+        float np0, np1;
+        load_params(0, np0, np1);
+        epi_sync();                          // every thread has left the previous pair's final round
         for (int q = 0; q < 2; ++q) {
           if (q == 1 && !live1) continue;
           const int64_t seq = 2 * (2 * p + q) + m;
@@ -323,21 +340,25 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&aready_bar[q]);
         }
+        store_params(s_param + 4 * kH, np0, np1);      // round 0 reads buffer 1
       }
       // ---- conv layers: item 0's round r, item 1's round r, item 0's round r+1, ... ----
       for (int r = 0; r < nl; ++r) {
         float* P = s_param + ((r + 1) & 1) * (4 * kH);
-        stage_params(r, P);
-        epi_sync();
+        epi_sync();                          // round r's slots visible; round r - 1's buffer is free
+        float np0, np1;
+        load_params(r + 1, np0, np1);
         for (int q = 0; q < 2; ++q) {
           if (q == 1 && !live1) continue;
           const int64_t seq = 2 * (2 * p + q) + m;
           const bool valid = (seq < a.n_rows) && (pos < L);
           const uint32_t t_acc = t_lane + q * 2 * kH, t_res = t_acc + kH;
           uint8_t* a_rowh = s_a + (size_t)half * plane_bytes + (size_t)(pad + q * (128 + pad) + rq) * 128;
+          if (etid == 0) stamp(p, r, q, 3);
           ptx::mbar_wait(&tfull_bar[q], tphase[q]);
           tphase[q] ^= 1;
           ptx::tc_fence_after();
+          if (etid == 0) stamp(p, r, q, 4);
           if (wact) {
             float v[64];
             uint32_t racc[2][32], rres[2][32];
@@ -346,6 +367,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             ptx::tmem_ld_32x32(t_acc + 32, racc[1]);
             ptx::tmem_ld_32x32(t_res + 32, rres[1]);
             ptx::tmem_ld_wait();
+            if (etid == 0) stamp(p, r, q, 5);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               float pb[32];
@@ -360,18 +382,20 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
               denf::tmem_st_32x32(t_res + c * 32, rres[c]);
             }
             write_operand(v, P, r + 1 < nl, valid, a_rowh);
+            if (etid == 0) stamp(p, r, q, 6);
             denf::tmem_st_wait();
           }
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&aready_bar[q]);
+          if (etid == 0) stamp(p, r, q, 7);
         }
+        store_params(s_param + (r & 1) * (4 * kH), np0, np1);     // round r + 1 reads buffer (r + 2) & 1
       }
       // ---- final_conv: ReLU(1x1) then 1x1 to the 5 logits (models/dnaconv.py:163-165,201) ----
       {
         float* P = s_param + ((nl + 1) & 1) * (4 * kH);
-        stage_params(nl, P);
         epi_sync();
         for (int q = 0; q < 2; ++q) {
           if (q == 1 && !live1) continue;

@@ -11,7 +11,9 @@
 // [N*L,128] (ping-pong: layer i reads one through TMA while its epilogue writes the other).
 #include <new>
 
+#include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 
 #include "conv_gemm.cuh"
 #include "den_fused.cuh"
@@ -309,9 +311,33 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
         SVDD_CUDA(launch_k(kern, dim3(grid2), dim3(dens::kThreads), (size_t)smem2, st, 1, tmW, tmW0, a));
         return SVDD_OK;
       };
+      // SVDD_DEN_TRACE=<csv path> (tuning aid, tools/den_trace.py): SM clock stamps of the hand-over points of
+      // CTA 0's third pair; synchronises the stream, so never set it on a timed or captured path
+      const char* trace_path = getenv("SVDD_DEN_TRACE");
+      constexpr size_t kTraceWords = (size_t)(denf::kMaxLayers + 1) * 2 * 8;
+      if (trace_path && *trace_path) {
+        SVDD_CUDA(cudaMalloc(&a.trace, kTraceWords * 8));
+        SVDD_CUDA(cudaMemsetAsync(a.trace, 0, kTraceWords * 8, st));
+      }
       if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch2(dens::den_short_kernel<int64_t>));
       else SVDD_TRY(launch2(dens::den_short_kernel<uint8_t>));
       count_launch();
+      if (a.trace != nullptr) {
+        std::vector<unsigned long long> host(kTraceWords);
+        SVDD_CUDA(cudaStreamSynchronize(st));
+        SVDD_CUDA(cudaMemcpy(host.data(), a.trace, kTraceWords * 8, cudaMemcpyDeviceToHost));
+        SVDD_CUDA(cudaFree(a.trace));
+        if (FILE* f = fopen(trace_path, "w")) {
+          fprintf(f, "# round,item,mma_ready,mma_first,mma_issued,epi_wait,epi_tfull,epi_ld,epi_written,epi_arrived (SM clocks)\n");
+          for (int r = 0; r <= a.n_layers; ++r)
+            for (int q = 0; q < 2; ++q) {
+              fprintf(f, "%d,%d", r, q);
+              for (int k = 0; k < 8; ++k) fprintf(f, ",%llu", host[(size_t)(r * 2 + q) * 8 + k]);
+              fprintf(f, "\n");
+            }
+          fclose(f);
+        }
+      }
       return SVDD_OK;
     }
   }

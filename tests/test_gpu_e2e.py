@@ -307,6 +307,7 @@ def test_cli_decode_and_tweedie_write_reference_npz_layout(cuda, tmp_path):
     assert sorted(d.files) == ['baseline', 'decoding']
     assert d['decoding'].shape == (8,) and d['decoding'].dtype == np.float32
     assert d['baseline'].shape == (8,) and np.isfinite(d['decoding']).all()
+    assert 'timing: SVDD 1 x 8 sequences' in r.stdout and 'baseline 3 x 8 rollouts' in r.stdout
 
 
 def test_base_model_tuple_and_svdd_gain(cuda):
@@ -321,6 +322,8 @@ def test_base_model_tuple_and_svdd_gain(cuda):
   assert samples[0].shape == (32, 50) and v.shape == r.shape == base.shape == (32,)
   assert top.shape == (32,) and torch.allclose(v, r)
   assert float(r.mean()) > float(base.mean())
+  assert m.timing['svdd_batches'] == 1 and m.timing['baseline_rollouts'] == 8
+  assert m.timing['svdd_s'] > 0 and m.timing['baseline_s'] > 0
 
 
 # ---------------------------------------------------------------------------------------------
