@@ -20,6 +20,7 @@
 // (TMEM lane quadrant = warp & 3; two threads per row, 64 channels each, LayerNorm statistics
 // combined pairwise through shared memory as in den_fused's split epilogue).
 #pragma once
+#include "conv_gemm2.cuh"
 #include "den_fused.cuh"
 
 namespace svdd {
@@ -27,8 +28,8 @@ namespace dens {
 
 using denf::kH;
 using denf::kTaps;
-constexpr int kStages = 4;
-constexpr int kStageBytes = denf::kStageBytes;
+constexpr int kStageBytes = denf::kStageBytes;   // one (tap, K half) weight tile: 128 x 64 bf16
+constexpr int kRingBytes = 4 * kStageBytes;      // per CTA: 4 whole tiles (CG = 1) or 8 half tiles (CG = 2)
 constexpr int kEpiThreads = 256;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kParamBytes = denf::kParamBytes;       // [parity][bias, tbias, gamma, beta][128]
@@ -40,20 +41,86 @@ constexpr int kBarBytes = 256;
 // rows of one K-half plane: pad | item 0 (128) | pad | item 1 (128) | pad
 __host__ __device__ inline int plane_rows(int pad) { return 3 * pad + 256; }
 __host__ __device__ inline int smem_bytes(int pad) {
-  return 2 * plane_rows(pad) * 128 + kStages * kStageBytes + kParamBytes + kW2Bytes + kStatBytes + kLgxBytes + kBarBytes + 1024;
+  return 2 * plane_rows(pad) * 128 + kRingBytes + kParamBytes + kW2Bytes + kStatBytes + kLgxBytes + kBarBytes + 1024;
 }
 
-template <typename Tok>
+// ---- helpers for the CTA-pair variant -------------------------------------------------------------
+template <int CG>
+__device__ __forceinline__ void umma_bf16_lo_cg(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo,
+                                                uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    ptx::umma_bf16_lo(tmem_d, desc_a_lo, desc_b_lo, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(ptx::kKmajorSw128DescHi)
+        : "memory");
+  }
+}
+// "this warp's rows of the item's next operand are written": on the own CTA's barrier, or (CG = 2)
+// on the pair leader's, with release semantics at cluster scope -- the stores (made visible to the
+// async proxy by the caller's fence.proxy.async) are read by THIS SM's tensor core on behalf of an
+// MMA the leader issues after observing the barrier.
+template <int CG>
+__device__ __forceinline__ void arrive_operand_ready(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    ptx::mbar_arrive(bar);
+  } else {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                 ::"r"(ptx::smem_u32(bar) & gemm2::kPeerMask) : "memory");
+  }
+}
+// the leader's wait on that barrier: acquire at cluster scope
+template <int CG>
+__device__ __forceinline__ void mbar_wait_cg(uint64_t* bar, uint32_t parity) {
+  if constexpr (CG == 1) {
+    ptx::mbar_wait(bar, parity);
+  } else {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
+      if (ok) break;
+      __nanosleep(16);
+      if (++spins == (1u << 24)) {
+        printf("svdd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
+// CG = 2 (SVDD_DEN_CG=2, an experiment kept with its cross-check): the kernel runs as CTA PAIRS (cluster of
+// two) and every MMA is a cta_group::2 instruction (M = 256) that covers the same item slot of both
+// CTAs: each CTA stages only HALF of every weight tile (64 of the 128 output channels; ring of 8 half
+// tiles), the leader CTA's issuing thread drives both, the peer's epilogue warps arrive on the leader's
+// `aready` barriers, `tfull` / ring `empty` commits are multicast.  Measured (tools/den_trace.py,
+// profiles/r02_den_trace_cg{1,2}.txt): the MMA phase of a 9-tap item and round takes 3.5 us instead of
+// 3.7 us and the pass is within +-2.5 % of CG = 1 -- each SM's tensor core still reads the WHOLE weight
+// tile (its half locally, the other half from the peer's shared memory), so only the TMA write of
+// the ring is halved; see the note on shared-memory bandwidth at the MMA issuer below.
+template <typename Tok, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ denf::Args a) {
+  constexpr int kStages = 4 * CG;                 // ring stages
+  constexpr int kStB = kStageBytes / CG;          // bytes of one stage in this CTA
+  const int rank = CG == 2 ? (int)gemm2::cluster_ctarank() : 0;
+  const int64_t group = blockIdx.x / CG, n_groups = gridDim.x / CG;     // CTA pairs (CG = 2) or CTAs
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int pad = a.pad_before;
   const int plane_bytes = plane_rows(pad) * 128;
   uint8_t* s_a = smem;                                   // [2 K halves][plane_rows][64 bf16], 128B swizzle
-  uint8_t* s_ring = s_a + 2 * plane_bytes;               // [kStages][128 x 64 bf16]
-  float* s_param = reinterpret_cast<float*>(s_ring + kStages * kStageBytes);
+  uint8_t* s_ring = s_a + 2 * plane_bytes;               // [kStages][128 / CG x 64 bf16]
+  float* s_param = reinterpret_cast<float*>(s_ring + kRingBytes);
   float* s_w2 = s_param + kParamBytes / 4;               // [5][128] + b2[5]
   float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_w2) + kW2Bytes);
   float* s_lgx = s_stat + kStatBytes / 4;
@@ -68,6 +135,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   const int L = a.L, nl = a.n_layers;
   const int64_t items = (a.n_rows + 1) / 2;              // two sequences per item
   const int64_t pairs = (items + 1) / 2;                 // two items per pass of a CTA
+  const int64_t passes = (pairs + CG - 1) / CG;          // a CTA pair takes two pairs per pass; a CTA beyond the last pair runs on invalid rows
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmW);
@@ -81,13 +149,12 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       }
       for (int q = 0; q < 2; ++q) {
         ptx::mbar_init(&tfull_bar[q], 1);
-        ptx::mbar_init(&aready_bar[q], 8);
+        ptx::mbar_init(&aready_bar[q], 8 * CG);
       }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    gemm2::tmem_alloc_cg<CG>(tmem_slot, 512);
   }
   for (int i = threadIdx.x; i < 2 * plane_bytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -95,7 +162,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (threadIdx.x < kVocab) s_w2[kVocab * kH + threadIdx.x] = a.fc2_b[threadIdx.x];
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) gemm2::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
@@ -104,7 +171,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   auto tap_used = [&](int o) { return o > -L && o < L; };
   // tuning aid: SM clock at the hand-over points of one pair (the CTA's third) of CTA 0
   auto stamp = [&](int64_t p, int r, int q, int slot) {
-    if (a.trace != nullptr && blockIdx.x == 0 && p == 2 * (int64_t)gridDim.x)
+    if (a.trace != nullptr && blockIdx.x == 0 && p == 2 * CG * n_groups)
       a.trace[(size_t)(r * 2 + q) * 8 + slot] = (unsigned long long)clock64();
   };
 
@@ -112,8 +179,9 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // ===================== weight producer: the taps of (item 0, round), (item 1, round), ... =====================
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
-        const bool live1 = 2 * p + 1 < items;
+      for (int64_t pass = group; pass < passes; pass += n_groups) {
+        const int64_t p = pass * CG + rank;
+        const bool live1 = CG == 2 || 2 * p + 1 < items;
         for (int r = 0; r <= nl; ++r) {
           const int taps = r < nl ? kTaps : 1;
           const int dil = r < nl ? a.dil[r] : 1;
@@ -122,12 +190,15 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             for (int t = 0; t < taps; ++t) {
               if (!tap_used((t - taps / 2) * dil)) continue;
               for (int kb = 0; kb < 2; ++kb) {
+                // CG = 2: this CTA's half of the tile (output channels rank * 64 ..), both halves
+                // complete the LEADER's full barrier
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                 if (r < nl)
-                  ptx::tma_load_2d(s_ring + stage * kStageBytes, &tmW, &full_bar[stage], kb * 64, (r * kTaps + t) * kH);
+                  gemm2::tma_load_2d_cg<CG>(s_ring + stage * kStB, &tmW, &full_bar[stage], kb * 64,
+                                            (r * kTaps + t) * kH + rank * (kH / CG));
                 else
-                  ptx::tma_load_2d(s_ring + stage * kStageBytes, &tmW0, &full_bar[stage], kb * 64, 0);
+                  gemm2::tma_load_2d_cg<CG>(s_ring + stage * kStB, &tmW0, &full_bar[stage], kb * 64, rank * (kH / CG));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
             }
@@ -143,24 +214,32 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // page, profiles/r02_ncu_full_den_short_source_before.csv) and was the kernel's critical path.
     // Descriptors are kept as their low words and advanced by adds; a tap always takes two ring
     // stages (kStages is even), so both are handled in one iteration.
+    //
+    // What paces the MMAs (tools/den_trace.py): shared memory, not the tensor pipe and not the weight
+    // stream.  A 128 x 128 x 16 SS-mode MMA reads 8 KB of operands in its 64 cycles, the SM's whole
+    // 128 B/clk, and TMA writes another 16 KB into the ring per stage: 4 x 8 + 16 KB = 384 cycles per
+    // stage against 256 tensor cycles, i.e. 3.6 us per 9-tap item and round -- what the trace shows,
+    // independent of the ring depth (4 / 5 stages), of the number of CTAs running (37 / 74 / 148) and
+    // of the polling (spinning instead of sleeping polls: slower).
     static_assert(kStages % 2 == 0, "a tap uses two consecutive ring stages");
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, kH);
-      constexpr uint32_t kStage16 = kStageBytes >> 4;
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128 * CG, kH);
+      constexpr uint32_t kStage16 = kStB >> 4;
       const uint32_t ring_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_ring));
       const uint32_t a_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(s_a));
       const uint32_t plane16 = (uint32_t)plane_bytes >> 4;
       uint32_t stage = 0, phase = 0;
       uint32_t rounds[2] = {0u, 0u};           // aready completions consumed per item slot
-      for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
-        const bool live1 = 2 * p + 1 < items;
+      for (int64_t pass = group; pass < passes; pass += n_groups) {
+        const int64_t p = pass * CG;
+        const bool live1 = CG == 2 || 2 * p + 1 < items;
         for (int r = 0; r <= nl; ++r) {
           const int taps = r < nl ? kTaps : 1;
           const int dil = r < nl ? a.dil[r] : 1;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (q == 1 && !live1) continue;
-            ptx::mbar_wait(&aready_bar[q], rounds[q] & 1);
+            mbar_wait_cg<CG>(&aready_bar[q], rounds[q] & 1);
             ++rounds[q];
             ptx::tc_fence_after();
             stamp(p, r, q, 0);
@@ -178,19 +257,19 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
               if (st == 0u) stamp(p, r, q, 1);
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k)
-                ptx::umma_bf16_lo(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
-              ptx::umma_commit(&empty_bar[stage]);
+                umma_bf16_lo_cg<CG>(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
+              gemm2::umma_commit_cg<CG>(&empty_bar[stage]);
               ptx::mbar_wait(&full_bar[stage + 1], phase);
               ptx::tc_fence_after();
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k)
-                ptx::umma_bf16_lo(tm, da + plane16 + 2 * k, db + kStage16 + 2 * k, idesc, 1u);
-              ptx::umma_commit(&empty_bar[stage + 1]);
+                umma_bf16_lo_cg<CG>(tm, da + plane16 + 2 * k, db + kStage16 + 2 * k, idesc, 1u);
+              gemm2::umma_commit_cg<CG>(&empty_bar[stage + 1]);
               st = 1u;
               stage += 2;
               if (stage == kStages) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(&tfull_bar[q]);
+            gemm2::umma_commit_cg<CG>(&tfull_bar[q]);
             stamp(p, r, q, 2);
           }
         }
@@ -277,8 +356,9 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       P[etid] = p0;                  // [bias | tbias]
       P[2 * kH + etid] = p1;         // [gamma | beta]
     };
-    for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
-      const bool live1 = 2 * p + 1 < items;
+    for (int64_t pass = group; pass < passes; pass += n_groups) {
+      const int64_t p = pass * CG + rank;
+      const bool live1 = CG == 2 || 2 * p + 1 < items;
       // ---- embed both items: Conv(5 -> 128, k9) as a weight gather, ReLU, LayerNorm_0 ----
       {
         float* P = s_param;                  // slots 1..3 <- layer 0's norm
@@ -338,7 +418,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&aready_bar[q]);
+          if (lane == 0) arrive_operand_ready<CG>(&aready_bar[q]);
         }
         store_params(s_param + 4 * kH, np0, np1);      // round 0 reads buffer 1
       }
@@ -388,7 +468,7 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&aready_bar[q]);
+          if (lane == 0) arrive_operand_ready<CG>(&aready_bar[q]);
           if (etid == 0) stamp(p, r, q, 7);
         }
         store_params(s_param + (r & 1) * (4 * kH), np0, np1);     // round r + 1 reads buffer (r + 2) & 1
@@ -450,10 +530,10 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
   __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) gemm2::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    gemm2::tmem_dealloc_cg<CG>(tmem_base, 512);
   }
 }
 

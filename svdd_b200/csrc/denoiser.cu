@@ -305,10 +305,22 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
     if (a.ilv && want_pair && dens::smem_bytes(a.pad_before) <= 227 * 1024) {
       const int smem2 = dens::smem_bytes(a.pad_before);
       const int64_t pairs = (items + 1) / 2;
-      const unsigned grid2 = (unsigned)(pairs < num_sms() ? pairs : num_sms());
+      // SVDD_DEN_CG=2 (read per call): CTA pairs with cta_group::2 MMAs, each CTA staging half of every weight
+      // tile (csrc/den_short.cuh).  Measured within +-2.5 % of independent CTAs (the default): kept as an
+      // experiment with its cross-check in the tests.
+      const char* env_cg = getenv("SVDD_DEN_CG");
+      const int cg = env_cg && atoi(env_cg) == 2 && num_sms() >= 2 ? 2 : 1;
+      const int64_t passes = (pairs + cg - 1) / cg;
+      const int64_t max_groups = num_sms() / cg;
+      unsigned grid2 = (unsigned)(cg * (passes < max_groups ? passes : max_groups));
+      // SVDD_DEN_GRID (tuning aid): cap the number of CTAs, to tell L2 contention from per-SM limits
+      if (const char* eg = getenv("SVDD_DEN_GRID")) { const int g = atoi(eg) / cg * cg; if (g > 0 && (unsigned)g < grid2) grid2 = (unsigned)g; }
+      CUtensorMap tmWh, tmW0h;      // box = one CTA's share of a weight tile: 64 K x (128 / cg) output channels
+      SVDD_TRY(encode_tmap_2d_bf16(&tmWh, h->conv_w, kH, (uint64_t)h->n_layers * kTaps * kH, 64, kH / cg));
+      SVDD_TRY(encode_tmap_2d_bf16(&tmW0h, h->fc0_w, kH, kH, 64, kH / cg));
       auto launch2 = [&](auto kern) -> int {
         SVDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SVDD_CUDA(launch_k(kern, dim3(grid2), dim3(dens::kThreads), (size_t)smem2, st, 1, tmW, tmW0, a));
+        SVDD_CUDA(launch_k(kern, dim3(grid2), dim3(dens::kThreads), (size_t)smem2, st, cg, tmWh, tmW0h, a));
         return SVDD_OK;
       };
       // SVDD_DEN_TRACE=<csv path> (tuning aid, tools/den_trace.py): SM clock stamps of the hand-over points of
@@ -319,8 +331,13 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
         SVDD_CUDA(cudaMalloc(&a.trace, kTraceWords * 8));
         SVDD_CUDA(cudaMemsetAsync(a.trace, 0, kTraceWords * 8, st));
       }
-      if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch2(dens::den_short_kernel<int64_t>));
-      else SVDD_TRY(launch2(dens::den_short_kernel<uint8_t>));
+      if (cg == 2) {
+        if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch2(dens::den_short_kernel<int64_t, 2>));
+        else SVDD_TRY(launch2(dens::den_short_kernel<uint8_t, 2>));
+      } else {
+        if (tok_dtype == SVDD_TOK_I64) SVDD_TRY(launch2(dens::den_short_kernel<int64_t, 1>));
+        else SVDD_TRY(launch2(dens::den_short_kernel<uint8_t, 1>));
+      }
       count_launch();
       if (a.trace != nullptr) {
         std::vector<unsigned long long> host(kTraceWords);

@@ -152,6 +152,13 @@ def test_denoiser_combined_planes_match_two_tile_scheme(cuda, L, n, monkeypatch)
   monkeypatch.setenv('SVDD_DEN_PAIR', '1')
   ilv = den.forward(x, 0.0).clone()
   assert torch.equal(ilv, ilv1), 'two items in flight must not change a single bit'
+  # ... and as CTA pairs that split every weight tile (cta_group::2 MMAs; an experiment kept behind SVDD_DEN_CG=2)
+  monkeypatch.setenv('SVDD_DEN_CG', '2')
+  assert torch.equal(den.forward(x, 0.0), ilv), 'CTA pairs must not change a single bit'
+  for k in (1, 3, 5):
+    if k <= n:
+      assert torch.equal(den.forward(x[:k].contiguous(), 0.0), ilv[:k]), k
+  monkeypatch.delenv('SVDD_DEN_CG')
   for k in (1, 2, 3, 5):          # partial pairs / items at the end of the batch
     if k <= n:
       assert torch.equal(den.forward(x[:k].contiguous(), 0.0), ilv[:k]), k

@@ -16,9 +16,10 @@ m = synthetic.build_denoiser(44, L).to(dev)
 den = m.packed()
 x = synthetic.random_tokens(n, L, 5, 0.5).to(dev).to(torch.uint8)
 out = {}
-for cmb in ('0', 'ilv', 'pair', 'ilv', 'pair'):
-  os.environ['SVDD_DEN_ILV'] = '1' if cmb in ('ilv', 'pair') else '0'
-  os.environ['SVDD_DEN_PAIR'] = '1' if cmb == 'pair' else '0'
+for cmb in ('0', 'ilv', 'pair1', 'pair', 'pair1', 'pair'):
+  os.environ['SVDD_DEN_ILV'] = '1' if cmb in ('ilv', 'pair', 'pair1') else '0'
+  os.environ['SVDD_DEN_PAIR'] = '1' if cmb in ('pair', 'pair1') else '0'
+  os.environ['SVDD_DEN_CG'] = '2' if cmb == 'pair' else '1'
   os.environ['SVDD_DEN_CMB'] = '0' if cmb == '0' else '1'
   y = den.forward(x, 0.0)
   torch.cuda.synchronize()
@@ -29,7 +30,7 @@ for cmb in ('0', 'ilv', 'pair', 'ilv', 'pair'):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
   out[cmb] = y.clone()
-  print(f'mode {cmb} (0 = two tiles, ilv = interleaved planes, pair = interleaved + two items in flight): n={n} L={L} min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
-for k in ('ilv', 'pair'):
+  print(f'mode {cmb} (0 = two tiles, ilv = interleaved planes, pair1 = + two items in flight (default), pair = + CTA pairs (SVDD_DEN_CG=2)): n={n} L={L} min {min(ts):.3f} ms median {sorted(ts)[2]:.3f} ms')
+for k in ('ilv', 'pair1', 'pair'):
   d = float((out['0'] - out[k]).abs().max())
   print(f'max |d| mode 0 vs {k}: {d:.3e} (scale {float(out["0"].abs().max()):.3g})')

@@ -39,13 +39,15 @@ us = lambda c: c / mhz
 print(f'pass {ms:.3f} ms; clock assumed {mhz:.0f} MHz; times in us relative to the first stamp')
 print('round item | mma: ready first-issue issued | epi: wait tfull ld written arrived')
 for r in rows:
-  print(f'{r[0]:5d} {r[1]:4d} | ' + ' '.join(f'{us(v - t0):8.2f}' for v in r[2:5]) + ' | ' + ' '.join(f'{us(v - t0):8.2f}' for v in r[5:10]))
+  print(f'{r[0]:5d} {r[1]:4d} | ' + ' '.join(f'{us(v - t0):8.2f}' for v in r[2:5]) + ' | ' + ' '.join(f'{us(v - t0):8.2f}' for v in r[5:10]) + (f' | w {us(r[10]):5.2f}' if len(r) > 10 else ''))
 body = [r for r in rows if 2 <= r[0] <= 18]
 def mean(f):
   return st.mean(us(f(r)) for r in body)
 print('means over rounds 2..18, both items:')
 print(f'  aready seen -> first MMA issued (weights)      {mean(lambda r: r[3] - r[2]):6.2f} us')
 print(f'  first MMA issued -> all issued                 {mean(lambda r: r[4] - r[3]):6.2f} us')
+if len(body[0]) > 10:
+  print(f'    of which waiting for weight stages           {mean(lambda r: r[10]):6.2f} us')
 print(f'  all issued -> epilogue sees tfull              {mean(lambda r: r[6] - r[4]):6.2f} us')
 print(f'  epilogue waits for tfull                       {mean(lambda r: r[6] - r[5]):6.2f} us')
 print(f'  tfull -> accumulator + residual in registers   {mean(lambda r: r[7] - r[6]):6.2f} us')
