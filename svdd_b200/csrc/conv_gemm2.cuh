@@ -151,6 +151,23 @@ __device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t da, uint6
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// the same with both descriptors given as their low words (high word = ptx::kKmajorSw128DescHi)
+template <int CG>
+__device__ __forceinline__ void umma_bf16_lo_cg(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    ptx::umma_bf16_lo(tmem_d, da_lo, db_lo, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(idesc), "r"(accumulate), "r"(ptx::kKmajorSw128DescHi)
+        : "memory");
+  }
+}
 // arrives (once all prior MMAs of this thread retire) on the barrier at this smem offset in
 // every CTA of the pair
 template <int CG>
@@ -508,6 +525,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
+    // (Measured and not kept: ONE elected thread running the whole issue loop with descriptors advanced by
+    // 32-bit adds, the change that took den_short_kernel's issuing warp off its critical path.  Here a stage is
+    // 4 MMAs of 128 cycles, twice den_short's, and the per-stage elect region is not the limit: the k5
+    // convolutions went from 482 to 502 us at stage 1, the summed GEMM table from 3.90 to 3.98 ms.)
     if (rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM * CG, BN);
       uint32_t stage = 0, phase = 0;

@@ -45,22 +45,6 @@ __host__ __device__ inline int smem_bytes(int pad) {
 }
 
 // ---- helpers for the CTA-pair variant -------------------------------------------------------------
-template <int CG>
-__device__ __forceinline__ void umma_bf16_lo_cg(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo,
-                                                uint32_t idesc, uint32_t accumulate) {
-  if constexpr (CG == 1) {
-    ptx::umma_bf16_lo(tmem_d, desc_a_lo, desc_b_lo, idesc, accumulate);
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "mov.b64 da, {%1, %5};\n\t"
-        "mov.b64 db, {%2, %5};\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
-        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(ptx::kKmajorSw128DescHi)
-        : "memory");
-  }
-}
 // "this warp's rows of the item's next operand are written": on the own CTA's barrier, or (CG = 2)
 // on the pair leader's, with release semantics at cluster scope -- the stores (made visible to the
 // async proxy by the caller's fence.proxy.async) are read by THIS SM's tensor core on behalf of an
@@ -257,13 +241,13 @@ den_short_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
               if (st == 0u) stamp(p, r, q, 1);
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k)
-                umma_bf16_lo_cg<CG>(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
+                gemm2::umma_bf16_lo_cg<CG>(tm, da + 2 * k, db + 2 * k, idesc, (st | k) != 0u);
               gemm2::umma_commit_cg<CG>(&empty_bar[stage]);
               ptx::mbar_wait(&full_bar[stage + 1], phase);
               ptx::tc_fence_after();
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k)
-                umma_bf16_lo_cg<CG>(tm, da + plane16 + 2 * k, db + kStage16 + 2 * k, idesc, 1u);
+                gemm2::umma_bf16_lo_cg<CG>(tm, da + plane16 + 2 * k, db + kStage16 + 2 * k, idesc, 1u);
               gemm2::umma_commit_cg<CG>(&empty_bar[stage + 1]);
               st = 1u;
               stage += 2;

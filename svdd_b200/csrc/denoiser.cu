@@ -297,7 +297,7 @@ static int den_fused_forward(svdd_denoiser* h, const void* tokens, int tok_dtype
   // epilogue warps work on one item's round the tensor core runs the other's.  SVDD_DEN_PAIR=0 (read
   // per call) keeps one item per CTA (den_fused_kernel): the A/B and the cross-check in the tests.
   {
-    // Measured (tools/ab_den_cmb.py): 51 200 x 50: 15.9 vs 21.1 ms; 999 x 33: 0.37 vs 0.47 ms; but 10 x 50:
+    // Measured (tools/ab_den_cmb.py): 51 200 x 50: 14.0-14.5 vs 19.2 ms; 999 x 33: 0.37 vs 0.47 ms; but 10 x 50:
     // 0.20 vs 0.14 ms -- with fewer items than SMs one item per CTA finishes sooner, so two items share a
     // CTA only when there are more items than SMs (SVDD_DEN_PAIR=1 / 0 forces either).
     const char* env_pair = getenv("SVDD_DEN_PAIR");

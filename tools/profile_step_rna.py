@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=1)
 ap.add_argument('--B', type=int, default=256)
 ap.add_argument('--M', type=int, default=50)
+ap.add_argument('--mc', action='store_true', help='SVDD-MC with the ConvGRU value net (BASELINE config 1: --mc --B 10 --M 10)')
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 torch.manual_seed(44)
@@ -23,8 +24,13 @@ model = diffusion_gosai.Diffusion(config.load_config('rna')).to(dev).eval()
 model.use_cuda_graph = False
 oe, oh = synthetic.build_convgru_oracle()
 rm = value_nets.OriBaseModel(oe.to(dev), oh.to(dev))
-run = lambda n: model.controlled_sample_tweedie(rm, num_steps=n, eval_sp_size=args.B, sample_M=args.M,
-                                                options='True', task='rna')
+if args.mc:
+  ve, vh = synthetic.build_convgru_value()
+  ve, vh = ve.to(dev), vh.to(dev)
+  run = lambda n: model.controlled_sample(ve, vh, num_steps=n, eval_sp_size=args.B, sample_M=args.M)
+else:
+  run = lambda n: model.controlled_sample_tweedie(rm, num_steps=n, eval_sp_size=args.B, sample_M=args.M,
+                                                  options='True', task='rna')
 run(1)
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_push('measured')
