@@ -28,7 +28,7 @@ Enformer-style value net, synthetic (all-mask prior + counter-based noise).
             index), extrapolated over the 128 steps only; reported, not a target.
   other_configs  the other BASELINE.json configs, N-aware: c3 (DNA SVDD-PM, B = 128 per GPU),
             c4 (DNA SVDD-MC, batch 4096 / N per rank, M = 20: strong scaling) and c5 (RNA SVDD-PM,
-            batch 8192 / N per rank, M = 50, alpha 0 and 0.1), a few reverse steps each, with
+            batch 8192 / N per rank, M = 50, alpha 0, 0.1 and 1), a few reverse steps each, with
             their own tensor roofline fraction.
 
 --impl reference times that CPU port alone (the reference itself is Python that cannot
@@ -314,7 +314,7 @@ def other_config_legs(device, rank, world, dna_model, emb, head, barrier):
   oe, oh = synthetic.build_convgru_oracle()
   rm5 = value_nets.OriBaseModel(oe.to(device), oh.to(device))
   B5 = 8192 // world
-  for alpha in (0.0, 0.1):
+  for alpha in (0.0, 0.1, 1.0):     # BASELINE config 5's sweep
     leg(f'c5_alpha{alpha:g}', f'RNA MRL SVDD-PM M=50, alpha={alpha:g}, batch 8192 sharded x{world} ({B5} sequences per GPU), L=50',
         rna, lambda n, a=alpha: rna.controlled_sample_tweedie(rm5, num_steps=n, eval_sp_size=B5, sample_M=50, options='True',
                                                               task='rna', alpha=a, row_offset=rank * B5),
