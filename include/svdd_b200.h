@@ -219,6 +219,60 @@ int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok_dtype,
                         float* scores, int64_t n_rows, int L, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* ---- one whole reverse step ------------------------------------------------
+ * Replaces the body of Diffusion._ddpm_update_finetune_controlled
+ * (diffusion_gosai.py:1175-1228, SVDD-MC: tweedie = 0) and of
+ * _ddpm_update_finetune_controlled_twedie (:1374-1460 with options == "True",
+ * SVDD-PM: tweedie = 1) by ONE call that sequences stages 1-4 on `stream`:
+ *   MC:  denoiser(x) -> subs_sample (M candidates) -> scorer(candidates) -> select_gather
+ *   PM:  denoiser(x) -> subs_sample -> denoiser(candidates) -> x0_argmax -> scorer(x0) -> select_gather
+ * It is a pure composition of the entry points above (same kernels, same order), so the tokens are
+ * bit-identical to calling them one by one; no allocation and no synchronisation, i.e. safe to
+ * capture into a CUDA graph.  The return tuple of the reference's step functions maps to
+ * x_out (final_samples), x (unchanged), q_out (q_xs, optional); copy_flag is (x != 4).
+ *
+ * denoiser       the CNN backbone; time_bias_t / time_bias_s: its time-conditioning rows for
+ *                sigma(t) and sigma(t - dt) (the same constant rows without time conditioning,
+ *                diffusion_gosai.py:334-335; time_bias_s may be NULL = time_bias_t);
+ * scorer         svdd_convgru* or svdd_enformer* according to scorer_kind: the value net
+ *                (head(embedding(.)), :1207-1209) for MC, the reward oracle (:1430) for PM;
+ * x, x_out       [B,L] tokens in / selected tokens out; idx_out optional int32 [B];
+ * mc_t, mc_s, alpha, U, U_sel, seed, seed_dev, step, row_offset: as in svdd_subs_sample /
+ *                svdd_select_gather;
+ * cand_out       optional [M,B,L] (the candidates; workspace if NULL), scores_out optional [M,B],
+ *                q_out optional [B,L,5];
+ * ws             256-byte aligned device workspace of svdd_step_workspace_bytes(args) bytes
+ *                (logits, candidates, scores, PM buffers and the networks' shared scratch). */
+typedef enum svdd_scorer_kind { SVDD_SCORER_CONVGRU = 0, SVDD_SCORER_ENFORMER = 1 } svdd_scorer_kind;
+typedef struct svdd_step_args {
+  svdd_denoiser* denoiser;
+  const float* time_bias_t;
+  const float* time_bias_s;
+  int scorer_kind;
+  void* scorer;
+  int tweedie;
+  const void* x;
+  void* x_out;
+  int tok_dtype;
+  int32_t* idx_out;
+  int B, L, M;
+  float mc_t, mc_s, alpha;
+  const float* U;
+  const float* U_sel;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+  int step;
+  int64_t row_offset;
+  void* cand_out;
+  float* scores_out;
+  float* q_out;
+  void* ws;
+  size_t ws_bytes;
+  void* stream;
+} svdd_step_args;
+size_t svdd_step_workspace_bytes(const svdd_step_args* args);
+int svdd_step(const svdd_step_args* args);
+
 /* Test hook for stage 2: same contract as svdd_subs_sample, but every Gumbel-max draw is
  * taken on the exact logf + IEEE-division path (the reference's arithmetic, operation for
  * operation).  svdd_subs_sample decides a draw with one approximate log per element only

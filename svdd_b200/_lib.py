@@ -32,6 +32,21 @@ class _Tensor(ctypes.Structure):
               ('ndim', ctypes.c_int32), ('shape', ctypes.c_int64 * 4)]
 
 
+class _StepArgs(ctypes.Structure):
+  """svdd_step_args (include/svdd_b200.h), field for field."""
+  _fields_ = [('denoiser', ctypes.c_void_p), ('time_bias_t', ctypes.c_void_p),
+              ('time_bias_s', ctypes.c_void_p), ('scorer_kind', ctypes.c_int),
+              ('scorer', ctypes.c_void_p), ('tweedie', ctypes.c_int), ('x', ctypes.c_void_p),
+              ('x_out', ctypes.c_void_p), ('tok_dtype', ctypes.c_int), ('idx_out', ctypes.c_void_p),
+              ('B', ctypes.c_int), ('L', ctypes.c_int), ('M', ctypes.c_int),
+              ('mc_t', ctypes.c_float), ('mc_s', ctypes.c_float), ('alpha', ctypes.c_float),
+              ('U', ctypes.c_void_p), ('U_sel', ctypes.c_void_p), ('seed', ctypes.c_uint64),
+              ('seed_dev', ctypes.c_void_p), ('step', ctypes.c_int), ('row_offset', ctypes.c_int64),
+              ('cand_out', ctypes.c_void_p), ('scores_out', ctypes.c_void_p),
+              ('q_out', ctypes.c_void_p), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_size_t),
+              ('stream', ctypes.c_void_p)]
+
+
 def _declare(lib):
   c = ctypes
   vp, i32, i64, u64, f32 = c.c_void_p, c.c_int, c.c_int64, c.c_uint64, c.c_float
@@ -76,6 +91,9 @@ def _declare(lib):
     fn = getattr(lib, f'svdd_{net}_score', None)
     if fn is not None:
       fn.argtypes = [vp, vp, i32, vp, i64, i32, vp, c.c_size_t, vp]
+  lib.svdd_step.argtypes = [c.POINTER(_StepArgs)]
+  lib.svdd_step_workspace_bytes.argtypes = [c.POINTER(_StepArgs)]
+  lib.svdd_step_workspace_bytes.restype = c.c_size_t
 
 
 def lib():
@@ -187,6 +205,53 @@ def select_gather(scores, cand, alpha=0.0, U_sel=None, seed=0, step=0,
                                  _ptr(U_sel), int(seed), _ptr(seed_dev), int(step),
                                  int(row_offset), _ptr(x_out), _ptr(idx), B, L, M, _stream()))
   return (x_out, idx) if want_idx else x_out
+
+
+# -- one whole reverse step ----------------------------------------------------------
+def step(denoiser, scorer, x, M, mc_t, mc_s, sigma_t=0.0, sigma_s=None, tweedie=False, alpha=0.0,
+         U=None, U_sel=None, seed=0, step=0, row_offset=0, seed_dev=None, want_q=False, out=None, ws=None):
+  """svdd_step: stages 1-4 of one controlled reverse step behind ONE C call
+  (Diffusion._ddpm_update_finetune_controlled / _controlled_twedie, diffusion_gosai.py:1175-1228 /
+  1374-1460).  denoiser: DenoiserHandle; scorer: ConvGRUHandle / EnformerHandle (the value net for
+  MC, the reward oracle for PM).  -> dict(x, idx, cand, scores, q)."""
+  _require_cuda(x, U, U_sel)
+  x = x.contiguous()
+  B, L = x.shape
+  dev = x.device
+  a = _StepArgs()
+  tb_t = denoiser.time_bias(sigma_t)
+  tb_s = denoiser.time_bias(sigma_t if sigma_s is None else sigma_s)
+  a.denoiser, a.time_bias_t, a.time_bias_s = denoiser._h, tb_t.data_ptr(), tb_s.data_ptr()
+  a.scorer_kind = {'convgru': 0, 'enformer': 1}[scorer._net]
+  a.scorer, a.tweedie = scorer._h, int(bool(tweedie))
+  x_out = out if out is not None else torch.empty_like(x)
+  idx = torch.empty((B,), dtype=torch.int32, device=dev)
+  cand = torch.empty((M, B, L), dtype=x.dtype, device=dev)
+  scores = torch.empty((M, B), dtype=torch.float32, device=dev)
+  q = torch.empty((B, L, 5), dtype=torch.float32, device=dev) if want_q else None
+  a.x, a.x_out, a.tok_dtype, a.idx_out = x.data_ptr(), x_out.data_ptr(), tok_dtype(x), idx.data_ptr()
+  a.B, a.L, a.M = B, L, M
+  a.mc_t, a.mc_s, a.alpha = float(mc_t), float(mc_s), float(alpha)
+  if U is not None:
+    assert U.shape == (M, B, L, 5) and U.dtype == torch.float32
+    U = U.contiguous()
+    a.U = U.data_ptr()
+  if U_sel is not None:
+    assert U_sel.shape == (B, M) and U_sel.dtype == torch.float32
+    U_sel = U_sel.contiguous()
+    a.U_sel = U_sel.data_ptr()
+  a.seed, a.step, a.row_offset = int(seed), int(step), int(row_offset)
+  a.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
+  a.cand_out, a.scores_out = cand.data_ptr(), scores.data_ptr()
+  a.q_out = None if q is None else q.data_ptr()
+  need = int(lib().svdd_step_workspace_bytes(ctypes.byref(a)))
+  if need == 0 and B > 0:
+    check(-1)
+  if ws is None or ws.numel() < need:
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+  a.ws, a.ws_bytes, a.stream = ws.data_ptr(), need, _stream().value
+  check(lib().svdd_step(ctypes.byref(a)))
+  return dict(x=x_out, idx=idx, cand=cand, scores=scores, q=q, ws=ws)
 
 
 def x0_argmax(logits, x, out=None):

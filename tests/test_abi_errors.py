@@ -42,6 +42,23 @@ def test_stage2_rejects_bad_shapes_without_touching_a_device():
   assert rc == 0
 
 
+def test_step_rejects_bad_argument_blocks_without_touching_a_device():
+  L = _lib.lib()
+  assert L.svdd_step(None) == INVALID and 'null argument' in _err()
+  a = _lib._StepArgs()
+  a.B, a.L, a.M = 2, 50, 3
+  assert L.svdd_step(ctypes.byref(a)) == INVALID and 'handles are required' in _err()
+  assert L.svdd_step_workspace_bytes(ctypes.byref(a)) == 0
+  a.denoiser, a.scorer, a.scorer_kind = 1, 1, 9        # checked before any handle is dereferenced
+  assert L.svdd_step(ctypes.byref(a)) == INVALID and 'scorer_kind' in _err()
+  a.scorer_kind, a.M = 0, 0
+  assert L.svdd_step(ctypes.byref(a)) == INVALID and 'bad shape' in _err()
+  a.M, a.tok_dtype = 3, 5
+  assert L.svdd_step(ctypes.byref(a)) == INVALID and 'tok_dtype' in _err()
+  a.tok_dtype, a.B = _lib.SVDD_TOK_U8, 0               # an empty batch does nothing
+  assert L.svdd_step(ctypes.byref(a)) == 0
+
+
 def test_python_wrappers_raise_with_the_library_message():
   with pytest.raises(_lib.SvddError):           # CPU tensors: no silent fallback
     _lib.subs_sample(torch.zeros(1, 2, 5), torch.zeros(1, 2, dtype=torch.int64), 1, 0.5, 0.4)

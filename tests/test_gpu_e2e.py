@@ -685,3 +685,84 @@ def test_cli_dna_decode_and_tweedie(cuda, tmp_path, script, extra, name):
   assert sorted(d.files) == ['baseline', 'decoding']
   assert d['decoding'].shape == (8,) and d['decoding'].dtype == np.float32
   assert d['baseline'].shape == (8,) and np.isfinite(d['decoding']).all() and np.isfinite(d['baseline']).all()
+
+
+@pytest.mark.parametrize('task,tweedie,alpha', [('rna', False, 0.0), ('rna', True, 0.0), ('rna', False, 0.1),
+                                                ('dna', False, 0.0), ('dna', True, 0.0)])
+def test_svdd_step_one_call_equals_the_stage_calls(cuda, task, tweedie, alpha):
+  """svdd_step (include/svdd_b200.h: the whole body of _ddpm_update_finetune_controlled /
+  _controlled_twedie behind ONE C call) is bit-identical to sequencing the stage entry points,
+  for both scorer kinds, MC and PM, argmax and soft selection, with Philox and injected noise."""
+  m = _rna_model(cuda) if task == 'rna' else _dna_model(cuda)
+  L = 50 if task == 'rna' else 200
+  B, M = (6, 5) if task == 'rna' else (4, 10)
+  if task == 'rna':
+    emb, head = helpers.build_convgru_oracle() if tweedie else helpers.build_convgru_value()
+  else:
+    emb, head = helpers.build_enformer(full=False)
+  scorer = diffusion_gosai._as_scorer(emb.to(cuda), head.to(cuda))
+  den = m.backbone.packed()
+  g = torch.Generator().manual_seed(77)
+  x = torch.randint(0, 4, (B, L), generator=g).to(torch.uint8)
+  x[torch.rand(B, L, generator=g) < 0.6] = 4
+  x = x.to(cuda)
+  mc_t, mc_s = 0.61, 0.55
+  for U in (None, torch.rand(M, B, L, 5, generator=g).to(cuda)):
+    kw = dict(U=U, seed=991, step=7, row_offset=3)
+    logits = den.forward(x, 0.0)
+    cand, q = _lib.subs_sample(logits, x, M, mc_t, mc_s, want_q=True, **kw)
+    flat = cand.reshape(M * B, L)
+    if tweedie:
+      flat = _lib.x0_argmax(den.forward(flat, 0.0), flat)
+    scores = scorer.score(flat).reshape(M, B)
+    x_ref, idx_ref = _lib.select_gather(scores, cand, alpha=alpha, seed=991, step=7, row_offset=3, want_idx=True)
+    before = _lib.launch_count()
+    got = _lib.step(den, scorer, x, M, mc_t, mc_s, tweedie=tweedie, alpha=alpha, want_q=True, **kw)
+    assert _lib.launch_count() > before
+    assert torch.equal(got['cand'], cand)
+    assert torch.equal(got['q'], q)
+    assert torch.equal(got['scores'], scores)
+    assert torch.equal(got['idx'], idx_ref)
+    assert torch.equal(got['x'], x_ref)
+    # carry-over: an unmasked position never changes (copy_flag of the reference's return tuple)
+    keep = x != 4
+    assert torch.equal(got['x'][keep], x[keep])
+
+
+def test_svdd_step_is_graph_capturable_and_rejects_a_short_workspace(cuda):
+  m = _rna_model(cuda)
+  emb, head = helpers.build_convgru_value()
+  scorer = diffusion_gosai._as_scorer(emb.to(cuda), head.to(cuda))
+  den = m.backbone.packed()
+  B, M = 8, 4
+  x = torch.full((B, 50), 4, dtype=torch.uint8, device=cuda)
+  seed_dev = torch.tensor([5, 0], dtype=torch.int64, device=cuda)
+  eager = _lib.step(den, scorer, x, M, 0.9, 0.8, seed_dev=seed_dev)
+  out = torch.empty_like(x)
+  s = torch.cuda.Stream()
+  s.wait_stream(torch.cuda.current_stream())
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.stream(s):
+    with torch.cuda.graph(graph, stream=s):
+      held = _lib.step(den, scorer, x, M, 0.9, 0.8, seed_dev=seed_dev, out=out, ws=eager['ws'])
+  graph.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(out, eager['x'])
+  seed_dev[0] = 6                      # a new run key replays the same graph with fresh noise
+  graph.replay()
+  torch.cuda.synchronize()
+  assert not torch.equal(out, eager['x'])
+  del held
+  # too small a workspace is an error, not a write past the end
+  import ctypes
+  a = _lib._StepArgs()
+  a.denoiser, a.scorer, a.scorer_kind = den._h, scorer._h, 0
+  tb = den.time_bias(0.0)
+  a.time_bias_t, a.x, a.x_out, a.tok_dtype = tb.data_ptr(), x.data_ptr(), out.data_ptr(), _lib.SVDD_TOK_U8
+  a.B, a.L, a.M, a.mc_t, a.mc_s = B, 50, M, 0.9, 0.8
+  need = _lib.lib().svdd_step_workspace_bytes(ctypes.byref(a))
+  assert need > 0
+  ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+  a.ws, a.ws_bytes = ws.data_ptr(), need - 256
+  assert _lib.lib().svdd_step(ctypes.byref(a)) == -4
+  assert b'workspace' in _lib.lib().svdd_last_error()
