@@ -30,13 +30,13 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box);
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool swizzle64 = false);
 int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
 }
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool swizzle64) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -45,7 +45,9 @@ int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int r
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base),
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  // 64-byte-wide boxes (slab32) take the 64B swizzle: with SWIZZLE_128B a 64-byte box row
+                  // still occupies a 128-byte shared-memory row (compute-sanitizer: footprint 2x)
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)",
@@ -379,15 +381,28 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       const cuuint32_t wb[2] = {64, (cuuint32_t)(bn2 / cg)};
       SVDD_TRY(encode_bf16_map(&tW, W, 2, wd, ws, wb));
     }
-    // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes x box_l x BS
+    // EPI_PAIR / EPI_POOL2 on the 8-warp kernel: 32-column slabs, four per column half (conv_gemm2.cuh);
+    // SVDD_SLAB32=0 (read per call) selects the two 64-column slabs per half of rounds 1-2 (bit-identical)
+    bool use_pair16 = false, use_pool16 = false;
+    {
+      static int epi16 = -1;
+      if (epi16 < 0) { const char* e = getenv("SVDD_EPI16"); epi16 = e ? atoi(e) : 1; }
+      const char* e16 = getenv("SVDD_POOL16");
+      use_pair16 = epi16 >= 2 && mode == EPI_PAIR && bn2 == 256 && cg == 2 && !g.halo;
+      use_pool16 = e16 && atoi(e16) && mode == EPI_POOL2 && bn2 == 256 && cg == 2 && !g.halo && ep2.out == nullptr &&
+                   ep2.out2 != nullptr;
+      const char* es32 = getenv("SVDD_SLAB32");
+      ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !use_pair16 && !use_pool16 && (es32 == nullptr || atoi(es32) != 0)) ? 1 : 0;
+    }
+    // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes (slab32: 64) x box_l x BS
     auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l, int pitch = 0) -> int {
       if (p == nullptr) { *m = tA; return SVDD_OK; }
       const cuuint64_t es = dt == DT_F32 ? 4 : 2;
       const cuuint64_t dims[3] = {(cuuint64_t)g.N_w, (cuuint64_t)Lr, (cuuint64_t)g.S};
       const cuuint64_t str[2] = {(cuuint64_t)ld * es, (cuuint64_t)(pitch > 0 ? pitch : Lr) * ld * es};
-      const cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_l, (cuuint32_t)g.BS};
+      const cuuint32_t box[3] = {(cuuint32_t)((ep2.slab32 ? 64 : 128) / es), (cuuint32_t)box_l, (cuuint32_t)g.BS};
       return encode_map(m, dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3,
-                        dims, str, box);
+                        dims, str, box, ep2.slab32 != 0);
     };
     auto aligned16 = [](const void* p, int64_t ld_elems, int es) {
       return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_elems * es) % 16 == 0;
@@ -452,7 +467,7 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       // measured on c2: the stem (K = 64, pure epilogue) 304 -> 152 us; EPI_PAIR no gain (279 -> 302 us at
       // stage 0: with the MMA pipe busy the epilogue competes for shared-memory bandwidth, not for
       // latency hiding), so EPI_PAIR takes this variant only with SVDD_EPI16=2
-      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && ((mode == EPI_PAIR && epi16 >= 2) || gen16)) {
+      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && (use_pair16 || gen16)) {
         if (mode == EPI_PAIR) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
         return launch2_impl<256, EPI_GENERIC, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
       }
@@ -462,9 +477,7 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       // 199 us, stage 3: 66 vs 54 us): one 32-byte row segment per thread and load is 32 separate
       // sectors per warp instruction, and the 8-warp variant's slab traffic was never the limit (ncu:
       // ~6 % of its stall samples wait for a slab).  Bit-identical results; kept with its test.
-      const char* e16 = getenv("SVDD_POOL16");
-      const int pool16 = e16 ? atoi(e16) : 0;
-      if (pool16 && mode == EPI_POOL2 && bn2 == 256 && cg == 2 && !g.halo && ep2.out == nullptr && ep2.out2 != nullptr)
+      if (use_pool16)
         return launch2_impl<256, EPI_POOL2, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }
     if (g.halo) {

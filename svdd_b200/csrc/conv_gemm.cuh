@@ -84,6 +84,10 @@ struct EpiParams {
   // conv_gemm2, set by the launcher: `res` is `out` itself (fp32, in place) -> the residual is
   // never loaded, the epilogue stores acc (+bias, act) with a TMA reduce-add into `out`
   int res_reduce = 0;
+  // conv_gemm2, EPI_PAIR / EPI_POOL2 on 8 epilogue warps, set by the launcher (SVDD_SLAB32, default on):
+  // 32-column slabs (128 rows x 64 B), FOUR per column half, so that the TMA loads of step k + 1 are in
+  // flight while step k is computed (tensor maps of res / res2 / out / out2 carry 32-column boxes)
+  int slab32 = 0;
   // debugging aid (SVDD_TIMELINE=1): CTA 0 stamps clock64() at its pipeline milestones
   unsigned long long* timeline = nullptr;
 };

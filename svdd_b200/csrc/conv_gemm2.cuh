@@ -27,6 +27,15 @@
 //   buffer b = j & 1;  rin[h][b]  : store warp -> math warps  "buffer free / residual landed"
 //                      rout[h][b] : math warps -> store warp  "slab written"
 // The store warp provisions job j+2 right after job j's TMA store has drained the buffer.
+//
+// EPI_PAIR / EPI_POOL2 (8 epilogue warps) take 32-column slabs instead (ep.slab32: 128 rows x 64 B,
+// FOUR buffers per column half in the same 64 KB, b = j & 3): a step consumes two jobs (an input and
+// an output slab, or two inputs), and with two buffers per half the loads of step k+1 could only be
+// issued once step k's math had released them -- ncu showed the math warps waiting for their input
+// slabs ~35 % of the time (profiles/r02_summary.md).  With four, step k+1's inputs land during step k.
+// The slabs are dense 64-byte rows under the 64B swizzle (tensor maps with SWIZZLE_64B): unit u (16 B)
+// of row r sits at r * 64 + ((u ^ ((r >> 1) & 3)) << 4); eight consecutive rows of one unit cover all
+// 32 banks once.
 #pragma once
 #include "conv_gemm.cuh"
 
@@ -247,6 +256,28 @@ __device__ __forceinline__ void slab_write(uint8_t* row_base, int x7, bool f32, 
     }
   }
 }
+// 32-column bf16 slabs (64-byte rows, 64B swizzle): pair_base = slab + (r >> 1) * 128, hi = (r & 1) << 2,
+// x7 = (r >> 1) & 3
+__device__ __forceinline__ void slab32_write(uint8_t* pair_base, int hi, int x7, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    ptx::sts128(pair_base + (((hi | u) ^ x7) << 4),
+        make_uint4(gemm_detail::pack_bf16x2(v[8 * u], v[8 * u + 1]), gemm_detail::pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                   gemm_detail::pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), gemm_detail::pack_bf16x2(v[8 * u + 6], v[8 * u + 7])));
+}
+__device__ __forceinline__ void slab32_read(const uint8_t* pair_base, int hi, int x7, float* v) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 q = ptx::lds128(pair_base + (((hi | u) ^ x7) << 4));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      v[8 * u + 2 * k] = __low2float(hh);
+      v[8 * u + 2 * k + 1] = __high2float(hh);
+    }
+  }
+}
 __device__ __forceinline__ void slab_read(const uint8_t* row_base, int x7, bool f32, int chunk_in_slab, float* v) {
   if (f32) {
 #pragma unroll
@@ -352,10 +383,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]         (leader's copy is the live one)
-  uint64_t* rin_bar = bars + 2 * kStages + 4;      // [half][buf]
-  uint64_t* rout_bar = bars + 2 * kStages + 8;     // [half][buf]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
-  uint64_t* fulla_bar = bars + 2 * kStages + 14;   // [kStagesAH]  HALO only
+  uint64_t* rin_bar = bars + 2 * kStages + 4;      // [half][buf]  (8 entries: slab32 has 4 buffers per half)
+  uint64_t* rout_bar = bars + 2 * kStages + 12;    // [half][buf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 20);
+  uint64_t* fulla_bar = bars + 2 * kStages + 22;   // [kStagesAH]  HALO only
   uint64_t* emptya_bar = fulla_bar + C::kStagesAH; // [kStagesAH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,8 +419,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // slab buffers used per 64/32-column step: EPI_PAIR = {residual in, (yd | y0) out},
   // EPI_POOL2 = {y0 in / next operand out, yd in}
   const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
-  const int slab_chunks = out_f32 ? 1 : 2;                            // 32-column chunks per slab
+  // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 warps
+  const bool slab32 = (kPair || kPool2) && EW == 8 && ep.slab32 != 0;
+  const int slab_chunks = (out_f32 || slab32) ? 1 : 2;                // 32-column chunks per slab
   const int slab_cols = slab_chunks * 32;
+  const int slab_bytes = slab32 ? kSlabBytes / 2 : kSlabBytes;
+  const uint32_t nbuf_mask = slab32 ? 3u : 1u;                        // buffers per half - 1
+  const int nbuf_shift = slab32 ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -409,7 +445,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_init(&tfull_bar[i], 1);
         ptx::mbar_init(&tempty_bar[i], CG * EW);
       }
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         ptx::mbar_init(&rin_bar[i], 1);
         ptx::mbar_init(&rout_bar[i], kEpiWarps / 2);
       }
@@ -758,8 +794,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int r = quad * 32 + lane;      // tile row owned by this thread
     const int x7 = r & 7;
     uint8_t* my_bufs = staging + half * 2 * kSlabBytes + r * 128;     // + (job & 1) * kSlabBytes
-    uint64_t* my_rin = rin_bar + half * 2;
-    uint64_t* my_rout = rout_bar + half * 2;
+    uint8_t* my_bufs32 = staging + half * 2 * kSlabBytes + (r >> 1) * 128;   // slab32: + (job & 3) * kSlabBytes / 2
+    const int hi32 = (r & 1) << 2, x7p = (r >> 1) & 3;
+    uint64_t* my_rin = rin_bar + half * (slab32 ? 4 : 2);
+    uint64_t* my_rout = rout_bar + half * (slab32 ? 4 : 2);
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t job = 0;                    // staged-slab counter of this half
     for (int t = first_tile; t < total_tiles; t += tile_step) {
@@ -794,11 +832,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c0 = cbase + c * 32;   // column within the tile
         const int cis = c % slab_chunks; // chunk within its slab
         if (n_out > 0 && cis == 0) {
+          if (slab32) {
+            buf0 = my_bufs32 + (job & 3) * (kSlabBytes / 2);
+            ptx::mbar_wait(&my_rin[job & 3], (job >> 2) & 1);
+            buf1 = my_bufs32 + ((job + 1) & 3) * (kSlabBytes / 2);
+            ptx::mbar_wait(&my_rin[(job + 1) & 3], ((job + 1) >> 2) & 1);
+          } else {
           buf0 = my_bufs + (job & 1) * kSlabBytes;
           ptx::mbar_wait(&my_rin[job & 1], (job >> 1) & 1);
           if (n_out == 2) {
             buf1 = my_bufs + ((job + 1) & 1) * kSlabBytes;
             ptx::mbar_wait(&my_rin[(job + 1) & 1], ((job + 1) >> 1) & 1);
+          }
           }
         }
         float v[32];
@@ -815,8 +860,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if constexpr (kPool2) {
           // v = Wp.(y1 - y0): pooled = y0 + sigmoid(v) * (y1 - y0)
           float yd[32];
-          slab_read(buf0, x7, false, cis, pv);
-          slab_read(buf1, x7, false, cis, yd);
+          if (slab32) {
+            slab32_read(buf0, hi32, x7p, pv);
+            slab32_read(buf1, hi32, x7p, yd);
+          } else {
+            slab_read(buf0, x7, false, cis, pv);
+            slab_read(buf1, x7, false, cis, yd);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             // sigmoid(v) = 0.5 + 0.5 tanh(v / 2): one MUFU op per element instead of ex2 + rcp (the
@@ -838,7 +888,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
             }
             act32(v, ep.act2);
-            slab_write(buf0, x7, false, cis, v);     // in place: this thread owns the row
+            if (slab32) slab32_write(buf0, hi32, x7p, v);
+            else slab_write(buf0, x7, false, cis, v);     // in place: this thread owns the row
           }
         } else {
         if (ep.scale != nullptr) {
@@ -855,7 +906,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (!ep.act_after_res) act32(v, ep.act);
         if (has_res || (kPair && ep.res != nullptr)) {
-          if (has_out || kPair) {
+          if (kPair && slab32) {
+            slab32_read(buf0, hi32, x7p, pv);
+          } else if (has_out || kPair) {
             slab_read(buf0, x7, out_f32, cis, pv);
           } else if (valid && n0 + c0 < n_end) {   // HEADDOT with a residual: direct (unused by the nets)
             gemm_detail::load_row32(ep.res, ep.res_dtype, row * ep.ld_res + n0 + c0, pv);
@@ -880,6 +933,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             v[i] = odd ? (valid ? v[i] - other : 0.0f) : v[i];
           }
           const int pr = r >> 1;
+          if (slab32)       // rows 0..63 (yd) / 64..127 (y0) of a 64-byte-row slab; buf1 = slab + (r >> 1) * 128
+            slab32_write(buf1 + (odd ? 0 : (kBM / 2) * 64) + (pr >> 1) * 128 - pr * 128, (pr & 1) << 2, (pr >> 1) & 3, v);
+          else
           slab_write(buf1 + (odd ? 0 : (kBM / 2) * 128) + pr * 128 - r * 128, pr & 7, false, cis, v);
         } else {
         if (has_out) slab_write(buf0, x7, out_f32, cis, v);
@@ -904,8 +960,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive(&my_rout[job & 1]);
-            if (n_out == 2) ptx::mbar_arrive(&my_rout[(job + 1) & 1]);
+            ptx::mbar_arrive(&my_rout[job & nbuf_mask]);
+            if (n_out == 2) ptx::mbar_arrive(&my_rout[(job + 1) & nbuf_mask]);
           }
           job += n_out;
         }
@@ -961,10 +1017,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else
     if (n_out > 0 && ptx::elect_one()) {
       uint8_t* bufs = staging + half * 2 * kSlabBytes;
-      uint64_t* my_rin = rin_bar + half * 2;
-      uint64_t* my_rout = rout_bar + half * 2;
+      uint64_t* my_rin = rin_bar + half * (slab32 ? 4 : 2);
+      uint64_t* my_rout = rout_bar + half * (slab32 ? 4 : 2);
       const int slabs = kHalf / slab_cols;
-      const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
+      const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * (slab32 ? 64 : 128));
       // job iterator: (tile, slab, buffer-of-the-step)
       struct It { int t; int slab, o; };
       auto advance = [&](It& it) {
@@ -976,33 +1032,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (kPool2) return o == 0 ? &tmRes : &tmRes2;
         return (has_res && o == 0) ? &tmRes : nullptr;
       };
-      auto provision = [&](const It& it, uint32_t j) {     // make buffer j&1 ready for job j
+      auto provision = [&](const It& it, uint32_t j) {     // make buffer j & nbuf_mask ready for job j
         if (it.t >= total_tiles) return;
         const CUtensorMap* m = load_map(it.o);
+        const uint32_t b = j & nbuf_mask;
         if (m != nullptr) {
           const TileCoord c = tile_coords(it.t, rank);
-          ptx::mbar_arrive_expect_tx(&my_rin[j & 1], res_bytes);
-          ptx::tma_load_3d(bufs + (j & 1) * kSlabBytes, m, &my_rin[j & 1],
+          ptx::mbar_arrive_expect_tx(&my_rin[b], res_bytes);
+          ptx::tma_load_3d(bufs + b * slab_bytes, m, &my_rin[b],
                            c.n0 + half * kHalf + it.slab * slab_cols, c.l0, c.s0);
         } else {
-          ptx::mbar_arrive(&my_rin[j & 1]);
+          ptx::mbar_arrive(&my_rin[b]);
         }
       };
       It cur{first_tile, 0, 0}, ahead{first_tile, 0, 0};
-      provision(ahead, 0);
-      advance(ahead);
-      provision(ahead, 1);
-      advance(ahead);
+      for (uint32_t j = 0; j <= nbuf_mask; ++j) {
+        provision(ahead, j);
+        advance(ahead);
+      }
       for (uint32_t j = 0; cur.t < total_tiles; ++j) {
         const TileCoord c = tile_coords(cur.t, rank);
-        ptx::mbar_wait(&my_rout[j & 1], (j >> 1) & 1);
-        const uint8_t* buf = bufs + (j & 1) * kSlabBytes;
+        ptx::mbar_wait(&my_rout[j & nbuf_mask], (j >> nbuf_shift) & 1);
+        const uint8_t* buf = bufs + (j & nbuf_mask) * slab_bytes;
         const int col = c.n0 + half * kHalf + cur.slab * slab_cols;
         bool stored = false;
         if (kPair) {
           if (cur.o == 1) {               // rows 0..63: yd, rows 64..127: y0, both at half length
             tma_store_3d(&tmOut2, buf, col, c.l0 >> 1, c.s0);
-            tma_store_3d(&tmOut, buf + (kBM / 2) * 128, col, c.l0 >> 1, c.s0);
+            tma_store_3d(&tmOut, buf + (kBM / 2) * (slab32 ? 64 : 128), col, c.l0 >> 1, c.s0);
             stored = true;
           }
         } else if (kPool2) {
@@ -1017,7 +1074,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           bulk_commit();
           bulk_wait_read0();
         }
-        provision(ahead, j + 2);
+        provision(ahead, j + nbuf_mask + 1);
         advance(ahead);
         advance(cur);
       }

@@ -432,6 +432,46 @@ def test_enformer_pool16_matches_slab_variant(cuda, full, n_cand, monkeypatch):
   assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('full,n_cand', [(False, 70), (True, 130)])
+def test_enformer_slab32_matches_wide_slabs(cuda, full, n_cand, monkeypatch):
+  """EPI_PAIR / EPI_POOL2 with four 32-column slabs per column half (the default: step k + 1's TMA
+  loads are in flight during step k) against the two 64-column slabs per half of rounds 1-2
+  (SVDD_SLAB32=0, read per call): same arithmetic per element, bit-identical scores.  Also at a
+  batch large enough for every CTA pair to walk several tiles (buffer rotation wraps)."""
+  emb, head = helpers.build_enformer(full=full)
+  emb, head = emb.to(cuda), head.to(cuda)
+  for n in (n_cand, 3, 1):
+    tok = helpers.random_tokens(n, 200, 72 + n, 0.5).to(cuda)
+    monkeypatch.setenv('SVDD_SLAB32', '0')
+    ref = value_nets.score_tokens(emb, head, tok).cpu()
+    monkeypatch.setenv('SVDD_SLAB32', '1')
+    got = value_nets.score_tokens(emb, head, tok).cpu()
+    print(f'\n[slab32 full={full} n={n}] max|d| = {float((got - ref).abs().max()):.3e}')
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize('S,L,C', [(5, 100, 768), (9, 13, 128), (64, 50, 896), (1300, 2, 128), (700, 200, 256)])
+def test_pair_pool_slab32_bitwise(cuda, S, L, C, monkeypatch):
+  """The pair-split 1x1 conv + difference pooling in isolation, slab32 against the wide slabs:
+  every output tensor (y0, yd, pooled fp32, pooled activation) bit-identical, incl. ragged column
+  tiles, odd lengths and many tiles per CTA pair."""
+  g = torch.Generator().manual_seed(S + L + C)
+  A = torch.randn(S, L, C, generator=g).to(cuda).bfloat16()
+  res = torch.randn(S, L, C, generator=g).to(cuda).bfloat16()
+  W1 = (torch.randn(C, C, generator=g) * C ** -0.5).to(cuda).bfloat16()
+  bias = torch.randn(C, generator=g).to(cuda)
+  Wp = (2 * torch.eye(C) + torch.randn(C, C, generator=g) * C ** -0.5).to(cuda).bfloat16()
+  scale2 = (1 + 0.2 * torch.randn(C, generator=g)).to(cuda)
+  shift2 = (0.3 * torch.randn(C, generator=g)).to(cuda)
+  outs = {}
+  for mode in ('0', '1'):
+    monkeypatch.setenv('SVDD_SLAB32', mode)
+    outs[mode] = [t.clone() for t in _lib.selftest_pair_pool(A, W1, bias, res, Wp, scale2, shift2, want_act=True)]
+    torch.cuda.synchronize()
+  for a, b, name in zip(outs['0'], outs['1'], ('y0', 'yd', 'pooled', 'pooled_act')):
+    assert torch.equal(a, b), name
+
+
 def test_module_call_surface_head_of_embedding(cuda):
   """Drop-in surface: the reference spells scoring as ``head(embedding(onehot))``
   (diffusion_gosai.py:1208-1209) and ``reward_model(onehot.transpose(1, 2))[:, 0]`` (:1430).  The
