@@ -143,12 +143,12 @@ int gemm2_cg() {
   return v;
 }
 
-template <int BN, int MODE, int CG, bool HALO = false, int EW = 8>
+template <int BN, int MODE, int CG, bool HALO = false, int EW = 8, bool WIDE = false>
 int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                  const CUtensorMap& tmR, const CUtensorMap& tmR2, const GemmShape& g, const EpiParams& ep,
                  cudaStream_t stream) {
   using C = gemm2::Cfg2<BN, CG>;
-  auto kern = gemm2::gemm2_kernel<BN, MODE, CG, HALO, EW>;
+  auto kern = gemm2::gemm2_kernel<BN, MODE, CG, HALO, EW, WIDE>;
   constexpr int kSmem = HALO ? C::kSmemBytesH : C::kSmemBytes;
   static bool configured = false;
   if (!configured) {
@@ -392,7 +392,8 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       use_pool16 = e16 && atoi(e16) && mode == EPI_POOL2 && bn2 == 256 && cg == 2 && !g.halo && ep2.out == nullptr &&
                    ep2.out2 != nullptr;
       const char* es32 = getenv("SVDD_SLAB32");
-      ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !use_pair16 && !use_pool16 && (es32 == nullptr || atoi(es32) != 0)) ? 1 : 0;
+      const bool wide = es32 != nullptr && atoi(es32) == 0 && bn2 == 256 && cg == 2;   // the only WIDE instantiations
+      ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !use_pair16 && !use_pool16 && !wide) ? 1 : 0;
     }
     // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes (slab32: 64) x box_l x BS
     auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l, int pitch = 0) -> int {
@@ -483,6 +484,10 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     if (g.halo) {
       if (bn2 == 256) return launch2_impl<256, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
       if (bn2 == 128) return launch2_impl<128, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+    }
+    if ((mode == EPI_PAIR || mode == EPI_POOL2) && !ep2.slab32) {     // SVDD_SLAB32=0 (cross-check tests)
+      if (mode == EPI_PAIR) return launch2_impl<256, EPI_PAIR, 2, false, 8, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      return launch2_impl<256, EPI_POOL2, 2, false, 8, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }
 #define CASE2(BN_, MODE_, CG_) \
     if (bn2 == BN_ && mode == MODE_ && cg == CG_) return launch2_impl<BN_, MODE_, CG_>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream)

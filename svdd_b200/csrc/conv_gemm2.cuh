@@ -362,7 +362,9 @@ __device__ __forceinline__ void act16(float* v, int act) {
 // only, one staged output or EPI_PAIR in place).  The epilogue-bound launches (stem, residual 1x1)
 // are limited by two epilogue warps per scheduler not hiding their own latencies (30 % issue-active);
 // EW = 16 doubles the warps per scheduler inside the same 64 KB of staging.
-template <int BN, int MODE, int CG, bool HALO = false, int EW = 8>
+// WIDE (EPI_PAIR / EPI_POOL2 on 8 warps only): the two 64-column slabs per half of rounds 1-2 instead of
+// the four 32-column ones; instantiated for the cross-check tests (SVDD_SLAB32=0) only.
+template <int BN, int MODE, int CG, bool HALO = false, int EW = 8, bool WIDE = false>
 __global__ void __launch_bounds__(64 + 32 * EW + 32 * kStoreWarps, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -420,7 +422,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // EPI_POOL2 = {y0 in / next operand out, yd in}
   const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
   // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 warps
-  const bool slab32 = (kPair || kPool2) && EW == 8 && ep.slab32 != 0;
+  constexpr bool slab32 = (kPair || kPool2) && EW == 8 && !WIDE;
   const int slab_chunks = (out_f32 || slab32) ? 1 : 2;                // 32-column chunks per slab
   const int slab_cols = slab_chunks * 32;
   const int slab_bytes = slab32 ? kSlabBytes / 2 : kSlabBytes;
@@ -798,6 +800,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int hi32 = (r & 1) << 2, x7p = (r >> 1) & 3;
     uint64_t* my_rin = rin_bar + half * (slab32 ? 4 : 2);
     uint64_t* my_rout = rout_bar + half * (slab32 ? 4 : 2);
+    const bool gelu_half = kPool2 && ep.scale2 != nullptr && ep.act2 == ACT_GELU;
+    const float pool_half = gelu_half ? 0.5f : 1.0f;
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t job = 0;                    // staged-slab counter of this half
     for (int t = first_tile; t < total_tiles; t += tile_step) {
@@ -812,7 +816,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool in_n = n0 + i < n_end;
         if (ep.bias) P[P_BIAS * BN + i] = in_n ? ep.bias[n0 + i] : 0.0f;
         if (ep.scale) { P[P_SCALE * BN + i] = in_n ? ep.scale[n0 + i] : 0.0f; P[P_SHIFT * BN + i] = in_n ? ep.shift[n0 + i] : 0.0f; }
-        if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? ep.shift2[n0 + i] : 0.0f; }
+        // EPI_POOL2 feeding a GELU: the BN affine is staged HALVED, h = x / 2 exactly (power of two), and
+        // gelu(x) = h + h * tanh(1.702 h) -- one multiply less per element, bit-identical to gelu_tanh(x)
+        if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? pool_half * ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? pool_half * ep.shift2[n0 + i] : 0.0f; }
         if (MODE == EPI_HEADDOT) P[P_HEADW * BN + i] = in_n ? ep.head_w[n0 + i] : 0.0f;
       }
       gemm_detail::epi_bar_sync();
@@ -887,7 +893,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = v[i] * ps[i] + pv[i];
             }
-            act32(v, ep.act2);
+            if (gelu_half) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"((2.0f * 0.851f) * v[i]));
+                v[i] = fmaf(v[i], t, v[i]);
+              }
+            } else {
+              act32(v, ep.act2);
+            }
             if (slab32) slab32_write(buf0, hi32, x7p, v);
             else slab_write(buf0, x7, false, cis, v);     // in place: this thread owns the row
           }
