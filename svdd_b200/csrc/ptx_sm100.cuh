@@ -70,8 +70,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint of every mbarrier wait (ns; 0 = plain try_wait + nanosleep polling).  Measured with
+// -DSVDD_MBAR_HINT_NS=0 against 2000 on the final round-2 kernels: fused denoiser 0.245 -> 0.229 ms
+// (L = 200, B = 128), 1.97 -> 1.81 ms (B = 1280), 15.0 -> 14.3 ms (51 200 x L = 50); GEMM family and
+// GRU neutral (a third of the GEMM kernels' executed instructions were polls of the waiting roles).
 #ifndef SVDD_MBAR_HINT_NS
-#define SVDD_MBAR_HINT_NS 0
+#define SVDD_MBAR_HINT_NS 2000
 #endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
