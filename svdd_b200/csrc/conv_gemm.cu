@@ -385,15 +385,20 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     // SVDD_SLAB32=0 (read per call) selects the two 64-column slabs per half of rounds 1-2 (bit-identical)
     bool use_pair16 = false, use_pool16 = false;
     {
-      static int epi16 = -1;
-      if (epi16 < 0) { const char* e = getenv("SVDD_EPI16"); epi16 = e ? atoi(e) : 1; }
+      // 16 epilogue warps on the same slabs (thread = row x 16 columns): pooling -6..-8 %, residual 1x1
+      // -2..-4 % per launch on the c2 pass -- after slab32 both families run at the SM's shared-memory
+      // bandwidth (operand reads of the MMAs + the slab traffic: 6.3 / 5.7 us per 256 x 256 tile at
+      // K = 768 against 7.6 / 6.2 measured), so more warps buy little.  SVDD_PAIR16=0 / SVDD_POOL16=0
+      // (read per call) select the 8-warp kernels; bit-identical.
+      const char* ep16 = getenv("SVDD_PAIR16");
       const char* e16 = getenv("SVDD_POOL16");
-      use_pair16 = epi16 >= 2 && mode == EPI_PAIR && bn2 == 256 && cg == 2 && !g.halo;
-      use_pool16 = e16 && atoi(e16) && mode == EPI_POOL2 && bn2 == 256 && cg == 2 && !g.halo && ep2.out == nullptr &&
-                   ep2.out2 != nullptr;
+      const bool shape16 = bn2 == 256 && cg == 2 && !g.halo;
+      use_pair16 = mode == EPI_PAIR && shape16 && (ep16 == nullptr || atoi(ep16) != 0);
+      use_pool16 = mode == EPI_POOL2 && shape16 && ep2.out == nullptr && ep2.out2 != nullptr && (e16 == nullptr || atoi(e16) != 0);
       const char* es32 = getenv("SVDD_SLAB32");
       const bool wide = es32 != nullptr && atoi(es32) == 0 && bn2 == 256 && cg == 2;   // the only WIDE instantiations
-      ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !use_pair16 && !use_pool16 && !wide) ? 1 : 0;
+      ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !wide) ? 1 : 0;
+      if (wide) use_pair16 = use_pool16 = false;
     }
     // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes (slab32: 64) x box_l x BS
     auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l, int pitch = 0) -> int {
@@ -457,29 +462,18 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       tR2 = tA;
     }
     {
-      // 16 epilogue warps for the launches whose epilogue is the bottleneck and fits one staged bf16
-      // slab per column quarter: EPI_PAIR (in place) and single-output EPI_GENERIC without residual
+      // 16 epilogue warps (one staged bf16 slab per column quarter) for single-output EPI_GENERIC launches
+      // without residual: the stem (K = 64, pure epilogue) 304 -> 152 us on c2.  SVDD_EPI16=0 disables.
       static int epi16 = -1;
       if (epi16 < 0) { const char* e = getenv("SVDD_EPI16"); epi16 = e ? atoi(e) : 1; }
       const bool one_out = (ep2.out != nullptr) != (ep2.out2 != nullptr);
       const int staged_dt = ep2.out != nullptr ? ep2.out_dtype : ep2.out2_dtype;
       const bool gen16 = mode == EPI_GENERIC && ep2.res == nullptr && !ep2.res_reduce && one_out && staged_dt == DT_BF16 &&
                          !ep2.act_after_res;
-      // measured on c2: the stem (K = 64, pure epilogue) 304 -> 152 us; EPI_PAIR no gain (279 -> 302 us at
-      // stage 0: with the MMA pipe busy the epilogue competes for shared-memory bandwidth, not for
-      // latency hiding), so EPI_PAIR takes this variant only with SVDD_EPI16=2
-      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && (use_pair16 || gen16)) {
-        if (mode == EPI_PAIR) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && gen16)
         return launch2_impl<256, EPI_GENERIC, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
-      }
-      // SVDD_POOL16=1 (read per call): EPI_POOL2 with a staged bf16 output only (every stage but the last)
-      // on 16 epilogue warps, the pooled operands y0 / yd read directly from global memory a chunk ahead
-      // instead of through TMA slabs.  Measured SLOWER on every stage of the c2 pass (stage 0: 281 vs
-      // 199 us, stage 3: 66 vs 54 us): one 32-byte row segment per thread and load is 32 separate
-      // sectors per warp instruction, and the 8-warp variant's slab traffic was never the limit (ncu:
-      // ~6 % of its stall samples wait for a slab).  Bit-identical results; kept with its test.
-      if (use_pool16)
-        return launch2_impl<256, EPI_POOL2, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      if (use_pair16) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      if (use_pool16) return launch2_impl<256, EPI_POOL2, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }
     if (g.halo) {
       if (bn2 == 256) return launch2_impl<256, EPI_GENERIC, 2, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);

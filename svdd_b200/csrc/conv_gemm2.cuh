@@ -357,11 +357,11 @@ __device__ __forceinline__ void act16(float* v, int act) {
   }
 }
 
-// EW = epilogue warps: 8 (thread = row x column half, 32-column chunks, two slab buffers per half)
-// or 16 (thread = row x column quarter, 16-column chunks, ONE slab buffer per quarter; bf16 output
-// only, one staged output or EPI_PAIR in place).  The epilogue-bound launches (stem, residual 1x1)
-// are limited by two epilogue warps per scheduler not hiding their own latencies (30 % issue-active);
-// EW = 16 doubles the warps per scheduler inside the same 64 KB of staging.
+// EW = epilogue warps: 8 (thread = row x column half, 32-column chunks) or 16.  With 16, EPI_GENERIC
+// (one staged bf16 output, no residual: the stem) runs thread = row x column quarter on ONE slab buffer
+// per quarter, and EPI_PAIR / EPI_POOL2 run thread = row x 16 columns on the slab32 protocol of the
+// 8-warp kernel (same slabs, barriers and store warps).  Two epilogue warps per scheduler do not hide
+// their own latencies (30-45 % issue-active); EW = 16 doubles them inside the same 64 KB of staging.
 // WIDE (EPI_PAIR / EPI_POOL2 on 8 warps only): the two 64-column slabs per half of rounds 1-2 instead of
 // the four 32-column ones; instantiated for the cross-check tests (SVDD_SLAB32=0) only.
 template <int BN, int MODE, int CG, bool HALO = false, int EW = 8, bool WIDE = false>
@@ -422,7 +422,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // EPI_POOL2 = {y0 in / next operand out, yd in}
   const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
   // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 warps
-  constexpr bool slab32 = (kPair || kPool2) && EW == 8 && !WIDE;
+  constexpr bool slab32 = (kPair || kPool2) && !WIDE;
+  // 16 epilogue warps on the slab32 protocol: thread = (row, 16-column half of the current 32-column slab)
+  constexpr bool kSlab16 = slab32 && EW == 16;
   const int slab_chunks = (out_f32 || slab32) ? 1 : 2;                // 32-column chunks per slab
   const int slab_cols = slab_chunks * 32;
   const int slab_bytes = slab32 ? kSlabBytes / 2 : kSlabBytes;
@@ -449,7 +451,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 8; ++i) {
         ptx::mbar_init(&rin_bar[i], 1);
-        ptx::mbar_init(&rout_bar[i], kEpiWarps / 2);
+        ptx::mbar_init(&rout_bar[i], kSlab16 ? 8 : kEpiWarps / 2);
       }
       if (HALO) {
         for (int i = 0; i < C::kStagesAH; ++i) {
@@ -630,17 +632,44 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
-  } else if (EW == 16 && warp < 2 + EW) {
-    // ===================== epilogue math, 16 warps: thread = (row, column quarter) =====================
-    if constexpr (EW == 16) {
-      static_assert(EW != 16 || (BN == 256 && !HALO && (MODE == EPI_GENERIC || MODE == EPI_PAIR || MODE == EPI_POOL2)), "EW = 16 variants");
+  } else if (kSlab16 && warp < 2 + EW) {
+    // ===== epilogue math, 16 warps on 32-column slabs (EPI_PAIR / EPI_POOL2): thread = (row, 16 columns) =====
+    // Same slabs, barriers and store warps as the 8-warp slab32 path; the eight warps of a column half
+    // split every 32-column slab in two, so four warps per scheduler hide each other's latencies
+    // (tcgen05.ld, lds, MUFU) where two could not (30-45 % issue-active).
+    if constexpr (kSlab16) {
       const int ew = warp - 2;
       const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-      const int grp = ew >> 2;             // column quarter
+      const int grp = ew >> 2;
+      const int half = grp >> 1, sub = grp & 1;
       const int etid = threadIdx.x - 64;
       const int r = quad * 32 + lane;
-      const int x7 = r & 7;
-      uint8_t* buf = staging + grp * kSlabBytes + r * 128;
+      uint8_t* my_bufs32 = staging + half * 2 * kSlabBytes + (r >> 1) * 128;
+      const int hi32 = ((r & 1) << 2) | (sub << 1), x7p = (r >> 1) & 3;
+      uint64_t* my_rin = rin_bar + half * 4;
+      uint64_t* my_rout = rout_bar + half * 4;
+      const bool gelu_half = kPool2 && ep.scale2 != nullptr && ep.act2 == ACT_GELU;
+      const float pool_half = gelu_half ? 0.5f : 1.0f;
+      auto rd16 = [&](const uint8_t* pair_base, float* o) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint4 q = ptx::lds128(pair_base + (((hi32 | u) ^ x7p) << 4));
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            o[8 * u + 2 * k] = __low2float(hh);
+            o[8 * u + 2 * k + 1] = __high2float(hh);
+          }
+        }
+      };
+      auto wr16 = [&](uint8_t* pair_base, int hi, int x7, const float* o) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          ptx::sts128(pair_base + (((hi | u) ^ x7) << 4),
+              make_uint4(gemm_detail::pack_bf16x2(o[8 * u], o[8 * u + 1]), gemm_detail::pack_bf16x2(o[8 * u + 2], o[8 * u + 3]),
+                         gemm_detail::pack_bf16x2(o[8 * u + 4], o[8 * u + 5]), gemm_detail::pack_bf16x2(o[8 * u + 6], o[8 * u + 7])));
+      };
       uint32_t acc_stage = 0, acc_phase = 0, job = 0;
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord tc = tile_coords(t, rank);
@@ -652,30 +681,125 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const bool in_n = n0 + i < n_end;
           if (ep.bias) P[P_BIAS * BN + i] = in_n ? ep.bias[n0 + i] : 0.0f;
           if (ep.scale) { P[P_SCALE * BN + i] = in_n ? ep.scale[n0 + i] : 0.0f; P[P_SHIFT * BN + i] = in_n ? ep.shift[n0 + i] : 0.0f; }
+          if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? pool_half * ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? pool_half * ep.shift2[n0 + i] : 0.0f; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + half * kHalf + sub * 16;
+        uint32_t raw[2][16];
+        ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        ptx::tc_fence_after();
+        tmem_ld_32x16(taddr, raw[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int c0 = half * kHalf + c * 32 + sub * 16;   // column within the tile
+          uint8_t* buf0 = my_bufs32 + (job & 3) * (kSlabBytes / 2);
+          uint8_t* buf1 = my_bufs32 + ((job + 1) & 3) * (kSlabBytes / 2);
+          ptx::mbar_wait(&my_rin[job & 3], (job >> 2) & 1);
+          ptx::mbar_wait(&my_rin[(job + 1) & 3], ((job + 1) >> 2) & 1);
+          float v[16], pv[16];
+          ptx::tmem_ld_wait();
+          if (c + 1 < kChunks) tmem_ld_32x16(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[c & 1][i]);
+          if (c + 1 == kChunks) {          // accumulator fully read: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
+          }
+          if constexpr (kPool2) {
+            float yd[16];
+            rd16(buf0, pv);
+            rd16(buf1, yd);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v[i]));
+              v[i] = fmaf(fmaf(0.5f, th, 0.5f), yd[i], pv[i]);
+            }
+            if (ep.scale2 != nullptr) {
+              float ps[16];
+              load_param16(P + P_SCALE2 * BN + c0, ps);
+              load_param16(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+            }
+            if (gelu_half) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float tt;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tt) : "f"((2.0f * 0.851f) * v[i]));
+                v[i] = fmaf(v[i], tt, v[i]);
+              }
+            } else {
+              act16(v, ep.act2);
+            }
+            wr16(buf0, hi32, x7p, v);      // in place: this thread owns these 32 bytes of the row
+          } else {
+            if (ep.scale != nullptr) {
+              float ps[16];
+              load_param16(P + P_SCALE * BN + c0, ps);
+              load_param16(P + P_SHIFT * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+            }
+            if (ep.bias != nullptr) {
+              load_param16(P + P_BIAS * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pv[i];
+            }
+            if (!ep.act_after_res) act16(v, ep.act);
+            if (ep.res != nullptr) {
+              rd16(buf0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pv[i];
+            }
+            if (ep.act_after_res) act16(v, ep.act);
+            const bool odd = (r & 1) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float other = __shfl_xor_sync(0xffffffffu, v[i], 1);
+              v[i] = odd ? (valid ? v[i] - other : 0.0f) : v[i];
+            }
+            const int pr = r >> 1;
+            wr16(buf1 + (odd ? 0 : (kBM / 2) * 64) + (pr >> 1) * 128 - pr * 128, ((pr & 1) << 2) | (sub << 1), (pr >> 1) & 3, v);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(&my_rout[job & 3]);
+            ptx::mbar_arrive(&my_rout[(job + 1) & 3]);
+          }
+          job += 2;
+        }
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (EW == 16 && warp < 2 + EW) {
+    // ===================== epilogue math, 16 warps: thread = (row, column quarter) =====================
+    // EPI_GENERIC with one staged bf16 output and no residual (the stem): ONE slab buffer per quarter
+    if constexpr (EW == 16 && !kSlab16) {
+      static_assert(EW != 16 || kSlab16 || (BN == 256 && !HALO && MODE == EPI_GENERIC), "EW = 16 variants");
+      const int ew = warp - 2;
+      const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+      const int grp = ew >> 2;             // column quarter
+      const int etid = threadIdx.x - 64;
+      const int r = quad * 32 + lane;
+      const int x7 = r & 7;
+      uint8_t* buf = staging + grp * kSlabBytes + r * 128;
+      uint32_t acc_stage = 0, acc_phase = 0, job = 0;
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord tc = tile_coords(t, rank);
+        const int n0 = tc.n0;
+        float* P = s_param + acc_stage * (kParamVecs * BN);
+        for (int i = etid; i < BN; i += 32 * EW) {
+          const bool in_n = n0 + i < n_end;
+          if (ep.bias) P[P_BIAS * BN + i] = in_n ? ep.bias[n0 + i] : 0.0f;
+          if (ep.scale) { P[P_SCALE * BN + i] = in_n ? ep.scale[n0 + i] : 0.0f; P[P_SHIFT * BN + i] = in_n ? ep.shift[n0 + i] : 0.0f; }
           if (ep.scale2) { P[P_SCALE2 * BN + i] = in_n ? ep.scale2[n0 + i] : 0.0f; P[P_SHIFT2 * BN + i] = in_n ? ep.shift2[n0 + i] : 0.0f; }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + grp * 64;
         uint32_t raw[2][16];
-        // EPI_POOL2: the two pooled operands (y0, yd: bf16 rows of `res` / `res2`) are read DIRECTLY
-        // from global memory, one 16-column chunk ahead of its use and before the accumulator wait
-        // -- the 8-warp variant stages them through TMA slabs and, with both slab buffers of a column
-        // half taken by the inputs, serialises load -> math -> store per 64-column step
-        uint4 py0[2][2], pyd[2][2];
-        const __nv_bfloat16* y0p = nullptr;
-        const __nv_bfloat16* ydp = nullptr;
-        if constexpr (MODE == EPI_POOL2) {
-          const int64_t r0 = (int64_t)s * (ep.res_pitch > 0 ? ep.res_pitch : g.L) + l;
-          const int64_t r1 = (int64_t)s * (ep.res2_pitch > 0 ? ep.res2_pitch : g.L) + l;
-          y0p = reinterpret_cast<const __nv_bfloat16*>(ep.res) + r0 * ep.ld_res + n0 + grp * 64;
-          ydp = reinterpret_cast<const __nv_bfloat16*>(ep.res2) + r1 * ep.ld_res2 + n0 + grp * 64;
-          const bool ok = valid && n0 + grp * 64 < n_end;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            py0[0][u] = ok ? __ldg(reinterpret_cast<const uint4*>(y0p) + u) : make_uint4(0, 0, 0, 0);
-            pyd[0][u] = ok ? __ldg(reinterpret_cast<const uint4*>(ydp) + u) : make_uint4(0, 0, 0, 0);
-          }
-        }
         ptx::mbar_wait(&tfull_bar[acc_stage], acc_phase);
         ptx::tc_fence_after();
         tmem_ld_32x16(taddr, raw[0]);
@@ -684,16 +808,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int c0 = grp * 64 + c * 16;  // column within the tile
           if (c == 0) ptx::mbar_wait(&rin_bar[grp], job & 1);
           float v[16], pv[16];
-          if constexpr (MODE == EPI_POOL2) {
-            if (c + 1 < 4) {
-              const bool ok = valid && n0 + c0 + 16 < n_end;
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                py0[(c + 1) & 1][u] = ok ? __ldg(reinterpret_cast<const uint4*>(y0p + (c + 1) * 16) + u) : make_uint4(0, 0, 0, 0);
-                pyd[(c + 1) & 1][u] = ok ? __ldg(reinterpret_cast<const uint4*>(ydp + (c + 1) * 16) + u) : make_uint4(0, 0, 0, 0);
-              }
-            }
-          }
           ptx::tmem_ld_wait();
           if (c + 1 < 4) tmem_ld_32x16(taddr + (c + 1) * 16, raw[(c + 1) & 1]);
 #pragma unroll
@@ -703,37 +817,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive_leader<CG>(&tempty_bar[acc_stage]);
           }
-          if constexpr (MODE == EPI_POOL2) {
-            // v = Wp.(y1 - y0): pooled = y0 + sigmoid(v) * yd; out2 = act2(pooled * scale2 + shift2)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint32_t w0[4] = {py0[c & 1][u].x, py0[c & 1][u].y, py0[c & 1][u].z, py0[c & 1][u].w};
-              const uint32_t wd[4] = {pyd[c & 1][u].x, pyd[c & 1][u].y, pyd[c & 1][u].z, pyd[c & 1][u].w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w0[k]);
-                const __nv_bfloat162 hd = *reinterpret_cast<const __nv_bfloat162*>(&wd[k]);
-                const float y0v[2] = {__low2float(h0), __high2float(h0)};
-                const float ydv[2] = {__low2float(hd), __high2float(hd)};
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int i = 8 * u + 2 * k + e;
-                  float th;
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v[i]));
-                  v[i] = fmaf(fmaf(0.5f, th, 0.5f), ydv[e], y0v[e]);
-                }
-              }
-            }
-            if (ep.scale2 != nullptr) {
-              float ps[16];
-              load_param16(P + P_SCALE2 * BN + c0, ps);
-              load_param16(P + P_SHIFT2 * BN + c0, pv);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
-            }
-            act16(v, ep.act2);
-            slab_write16(buf, x7, c, v);
-          } else {
           if (ep.scale != nullptr) {
             float ps[16];
             load_param16(P + P_SCALE * BN + c0, ps);
@@ -746,37 +829,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += pv[i];
           }
-          if constexpr (MODE == EPI_PAIR) {
-            if (ep.res != nullptr) {
-              slab_read16(buf, x7, c, pv);
+          act16(v, ep.act);
+          if (ep.out2 != nullptr) {
+            if (ep.scale2 != nullptr) {
+              float ps[16];
+              load_param16(P + P_SCALE2 * BN + c0, ps);
+              load_param16(P + P_SHIFT2 * BN + c0, pv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += pv[i];
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
             }
-            const bool odd = (r & 1) != 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float other = __shfl_xor_sync(0xffffffffu, v[i], 1);
-              v[i] = odd ? (valid ? v[i] - other : 0.0f) : v[i];
-            }
-            const int pr = r >> 1;
-            // in place: the pair rows land on other threads' residual rows of the same columns
-            if (ep.res != nullptr) asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-            slab_write16(buf + (odd ? 0 : (kBM / 2) * 128) + pr * 128 - r * 128, pr & 7, c, v);
-          } else {
-            act16(v, ep.act);
-            if (ep.out2 != nullptr) {
-              if (ep.scale2 != nullptr) {
-                float ps[16];
-                load_param16(P + P_SCALE2 * BN + c0, ps);
-                load_param16(P + P_SHIFT2 * BN + c0, pv);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
-              }
-              act16(v, ep.act2);
-            }
-            slab_write16(buf, x7, c, v);
+            act16(v, ep.act2);
           }
-          }   // MODE != EPI_POOL2
+          slab_write16(buf, x7, c, v);
           if (c == 3) {
             ptx::fence_proxy_async_smem();
             __syncwarp();
@@ -989,20 +1053,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {
     // ===================== slab store / prefetch warp (one per column half) =====================
     const int half = warp - (2 + EW);
-    if constexpr (EW == 16) {
+    if constexpr (EW == 16 && !kSlab16) {
       // one buffer per column quarter, quarters 2*half and 2*half+1 served in turn
       if (ptx::elect_one()) {
-        const uint32_t res_bytes = (uint32_t)(g.BL * g.BS * 128);
-        const bool load_res = kPair && ep.res != nullptr;
-        auto provision = [&](int t, int grp) {
+        auto provision = [&](int t, int grp) {          // output-only slabs: nothing to load
           if (t >= total_tiles) return;
-          if (load_res) {
-            const TileCoord c = tile_coords(t, rank);
-            ptx::mbar_arrive_expect_tx(&rin_bar[grp], res_bytes);
-            ptx::tma_load_3d(staging + grp * kSlabBytes, &tmRes, &rin_bar[grp], c.n0 + grp * 64, c.l0, c.s0);
-          } else {
-            ptx::mbar_arrive(&rin_bar[grp]);
-          }
+          ptx::mbar_arrive(&rin_bar[grp]);
         };
         provision(first_tile, 2 * half);
         provision(first_tile, 2 * half + 1);
@@ -1015,12 +1071,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::mbar_wait(&rout_bar[grp], j & 1);
             const uint8_t* buf = staging + grp * kSlabBytes;
             const int col = c.n0 + grp * 64;
-            if (kPair) {                  // rows 0..63: yd, rows 64..127: y0, both at half length
-              tma_store_3d(&tmOut2, buf, col, c.l0 >> 1, c.s0);
-              tma_store_3d(&tmOut, buf + (kBM / 2) * 128, col, c.l0 >> 1, c.s0);
-            } else {
-              tma_store_3d(has_out ? &tmOut : &tmOut2, buf, col, c.l0, c.s0);
-            }
+            tma_store_3d(has_out ? &tmOut : &tmOut2, buf, col, c.l0, c.s0);
             bulk_commit();
           }
           bulk_wait_read0();

@@ -416,20 +416,21 @@ def test_value_rank_agreement(cuda):
 
 @pytest.mark.parametrize('full,n_cand', [(False, 70), (True, 130)])
 def test_enformer_pool16_matches_slab_variant(cuda, full, n_cand, monkeypatch):
-  """Difference pooling (EPI_POOL2) with 16 epilogue warps and the pooled operands read directly
-  from global memory against the 8-warp variant that stages them through TMA slabs
-  (SVDD_POOL16=0, read per call): the same arithmetic on the same bf16 values, so the scores are
-  bit-identical.  The small net has ragged 256-wide column tiles (N = 384), the full one is the
-  bench network."""
+  """The residual 1x1 conv (EPI_PAIR) and difference pooling (EPI_POOL2) with 16 epilogue warps
+  (thread = row x 16 columns of a 32-column slab; the default) against the 8-warp kernels on the
+  same slabs (SVDD_PAIR16=0 / SVDD_POOL16=0, read per call): the same arithmetic on the same bf16
+  values, so the scores are bit-identical.  The small net has ragged 256-wide column tiles
+  (N = 384), the full one is the bench network."""
   emb, head = helpers.build_enformer(full=full)
   emb, head = emb.to(cuda), head.to(cuda)
   tok = helpers.random_tokens(n_cand, 200, 71, 0.5).to(cuda)
-  monkeypatch.setenv('SVDD_POOL16', '0')
-  ref = value_nets.score_tokens(emb, head, tok).cpu()
-  monkeypatch.setenv('SVDD_POOL16', '1')
-  got = value_nets.score_tokens(emb, head, tok).cpu()
-  print(f'\n[pool16 full={full}] max|d| = {float((got - ref).abs().max()):.3e}')
-  assert torch.equal(got, ref)
+  got = {}
+  for pair16, pool16 in (('0', '0'), ('1', '1'), ('0', '1'), ('1', '0')):
+    monkeypatch.setenv('SVDD_PAIR16', pair16)
+    monkeypatch.setenv('SVDD_POOL16', pool16)
+    got[pair16 + pool16] = value_nets.score_tokens(emb, head, tok).cpu()
+  for k, v in got.items():
+    assert torch.equal(v, got['00']), k
 
 
 @pytest.mark.parametrize('full,n_cand', [(False, 70), (True, 130)])
@@ -445,9 +446,12 @@ def test_enformer_slab32_matches_wide_slabs(cuda, full, n_cand, monkeypatch):
     monkeypatch.setenv('SVDD_SLAB32', '0')
     ref = value_nets.score_tokens(emb, head, tok).cpu()
     monkeypatch.setenv('SVDD_SLAB32', '1')
-    got = value_nets.score_tokens(emb, head, tok).cpu()
-    print(f'\n[slab32 full={full} n={n}] max|d| = {float((got - ref).abs().max()):.3e}')
-    assert torch.equal(got, ref)
+    for w16 in ('1', '0'):                 # 16-warp (default) and 8-warp kernels on the 32-column slabs
+      monkeypatch.setenv('SVDD_PAIR16', w16)
+      monkeypatch.setenv('SVDD_POOL16', w16)
+      got = value_nets.score_tokens(emb, head, tok).cpu()
+      print(f'\n[slab32 full={full} n={n} w16={w16}] max|d| = {float((got - ref).abs().max()):.3e}')
+      assert torch.equal(got, ref)
 
 
 @pytest.mark.parametrize('S,L,C', [(5, 100, 768), (9, 13, 128), (64, 50, 896), (1300, 2, 128), (700, 200, 256)])
@@ -464,12 +468,15 @@ def test_pair_pool_slab32_bitwise(cuda, S, L, C, monkeypatch):
   scale2 = (1 + 0.2 * torch.randn(C, generator=g)).to(cuda)
   shift2 = (0.3 * torch.randn(C, generator=g)).to(cuda)
   outs = {}
-  for mode in ('0', '1'):
+  for mode, w16 in (('0', '0'), ('1', '0'), ('1', '1')):
     monkeypatch.setenv('SVDD_SLAB32', mode)
-    outs[mode] = [t.clone() for t in _lib.selftest_pair_pool(A, W1, bias, res, Wp, scale2, shift2, want_act=True)]
+    monkeypatch.setenv('SVDD_PAIR16', w16)
+    monkeypatch.setenv('SVDD_POOL16', w16)
+    outs[mode + w16] = [t.clone() for t in _lib.selftest_pair_pool(A, W1, bias, res, Wp, scale2, shift2, want_act=True)]
     torch.cuda.synchronize()
-  for a, b, name in zip(outs['0'], outs['1'], ('y0', 'yd', 'pooled', 'pooled_act')):
-    assert torch.equal(a, b), name
+  for k in ('10', '11'):
+    for a, b, name in zip(outs['00'], outs[k], ('y0', 'yd', 'pooled', 'pooled_act')):
+      assert torch.equal(a, b), (k, name)
 
 
 def test_module_call_surface_head_of_embedding(cuda):
