@@ -104,7 +104,10 @@ struct Cfg {
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB: this CTA's 128 rows
   static constexpr int kBBytes = (kBN / 2) * kBK * 2;      // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kBN == 256 ? 4 : 5;
+#ifndef SVDD_TOWER_STAGES
+#define SVDD_TOWER_STAGES 4
+#endif
+  static constexpr int kStages = kBN == 256 ? SVDD_TOWER_STAGES : 5;   // operand ring depth (3: +9 % tower time, measured)
   static constexpr int kBiasBytes = 2 * kBN * 4;
   static constexpr int kAttnWBytes = 16 * 128 * 4;           // softmax weights of one sequence per epilogue warp (H*N*N <= 128)
   static constexpr int kBarBytes = 512;

@@ -27,6 +27,16 @@ for spec in "tower:tower_kernel:profile_step.py:0" "den_single_l50:den_fused_ker
   ncu -i $OUT/${TAG}_${name}_full.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_${name}_raw.csv 2>/dev/null
   rm -f $OUT/${TAG}_${name}_full.ncu-rep
 done
+# the residual 1x1 conv / difference pooling at stage 0 (2nd / 3rd gemm2 launch of the step): raw + top stalls of the source page
+for spec in "pair:1" "pool2:2"; do
+  name=${spec%%:*}; skip=${spec#*:}
+  timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include measured/ -k regex:gemm2_kernel -s $skip -c 1 \
+      -o $OUT/${TAG}_${name}_full -f python tools/profile_step.py --steps 1 > $OUT/${TAG}_${name}_full.log 2>&1
+  ncu -i $OUT/${TAG}_${name}_full.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_${name}_raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_${name}_full.ncu-rep --page source --csv > $OUT/${TAG}_ncu_full_${name}_source.csv 2>/dev/null
+  python tools/ncu_top_stalls.py $OUT/${TAG}_ncu_full_${name}_source.csv 0 25 > $OUT/${TAG}_ncu_${name}_top_stalls.txt 2>&1
+  rm -f $OUT/${TAG}_${name}_full.ncu-rep $OUT/${TAG}_ncu_full_${name}_source.csv
+done
 ls -la $OUT | tail -25
 tail -5 $OUT/${TAG}_pytest.log
 head -c 1500 $OUT/${TAG}_bench.json
