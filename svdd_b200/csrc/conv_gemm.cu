@@ -383,7 +383,7 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
     }
     // EPI_PAIR / EPI_POOL2 on the 8-warp kernel: 32-column slabs, four per column half (conv_gemm2.cuh);
     // SVDD_SLAB32=0 (read per call) selects the two 64-column slabs per half of rounds 1-2 (bit-identical)
-    bool use_pair16 = false, use_pool16 = false;
+    bool use_pair16 = false, use_pool16 = false, use_gen16 = false, gen16_quarter = false;
     {
       // 16 epilogue warps on the same slabs (thread = row x 16 columns): pooling -6..-8 %, residual 1x1
       // -2..-4 % per launch on the c2 pass -- after slab32 both families run at the SM's shared-memory
@@ -399,6 +399,19 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       const bool wide = es32 != nullptr && atoi(es32) == 0 && bn2 == 256 && cg == 2;   // the only WIDE instantiations
       ep2.slab32 = ((mode == EPI_PAIR || mode == EPI_POOL2) && !wide) ? 1 : 0;
       if (wide) use_pair16 = use_pool16 = false;
+      // 16 epilogue warps for single-output bf16 EPI_GENERIC launches without residual (the stem, K = 64, pure
+      // epilogue: 304 us on 8 warps, 145 on 16 with one 64-column slab per column quarter).  The slab32
+      // protocol (four 32-column slabs per half, SVDD_EPI16=3) is measured slightly SLOWER here, 152 vs 145 us:
+      // a store-only epilogue never waited for its slabs, and the narrower TMA boxes cost a little.
+      // SVDD_EPI16 (read per call): 1 = quarter slabs (default), 3 = slab32, 0 = the 8-warp kernel.
+      const char* e_epi = getenv("SVDD_EPI16");
+      const int epi16 = e_epi ? atoi(e_epi) : 1;
+      const bool one_out = (ep2.out != nullptr) != (ep2.out2 != nullptr);
+      const int staged_dt = ep2.out != nullptr ? ep2.out_dtype : ep2.out2_dtype;
+      use_gen16 = epi16 != 0 && shape16 && mode == EPI_GENERIC && ep2.res == nullptr && !ep2.res_reduce && one_out &&
+                  staged_dt == DT_BF16 && !ep2.act_after_res;
+      gen16_quarter = use_gen16 && epi16 != 3;
+      if (use_gen16 && !gen16_quarter) ep2.slab32 = 1;
     }
     // [S, Lr, N] row-major view with leading dimension ld; box = 128 bytes (slab32: 64) x box_l x BS
     auto io_map = [&](CUtensorMap* m, const void* p, int dt, int64_t ld, int Lr, int box_l, int pitch = 0) -> int {
@@ -462,16 +475,10 @@ static int launch_gemm2_window(const void* A, const void* W, const GemmShape& g,
       tR2 = tA;
     }
     {
-      // 16 epilogue warps (one staged bf16 slab per column quarter) for single-output EPI_GENERIC launches
-      // without residual: the stem (K = 64, pure epilogue) 304 -> 152 us on c2.  SVDD_EPI16=0 disables.
-      static int epi16 = -1;
-      if (epi16 < 0) { const char* e = getenv("SVDD_EPI16"); epi16 = e ? atoi(e) : 1; }
-      const bool one_out = (ep2.out != nullptr) != (ep2.out2 != nullptr);
-      const int staged_dt = ep2.out != nullptr ? ep2.out_dtype : ep2.out2_dtype;
-      const bool gen16 = mode == EPI_GENERIC && ep2.res == nullptr && !ep2.res_reduce && one_out && staged_dt == DT_BF16 &&
-                         !ep2.act_after_res;
-      if (epi16 && bn2 == 256 && cg == 2 && !g.halo && gen16)
+      if (use_gen16) {
+        if (gen16_quarter) return launch2_impl<256, EPI_GENERIC, 2, false, 16, true>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
         return launch2_impl<256, EPI_GENERIC, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
+      }
       if (use_pair16) return launch2_impl<256, EPI_PAIR, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
       if (use_pool16) return launch2_impl<256, EPI_POOL2, 2, false, 16>(tA, tW, tO, tO2, tR, tR2, g, ep2, stream);
     }

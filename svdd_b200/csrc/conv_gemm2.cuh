@@ -422,7 +422,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // EPI_POOL2 = {y0 in / next operand out, yd in}
   const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
   // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 warps
-  constexpr bool slab32 = (kPair || kPool2) && !WIDE;
+  constexpr bool slab32 = (kPair || kPool2 || (MODE == EPI_GENERIC && EW == 16)) && !WIDE;
   // 16 epilogue warps on the slab32 protocol: thread = (row, 16-column half of the current 32-column slab)
   constexpr bool kSlab16 = slab32 && EW == 16;
   const int slab_chunks = (out_f32 || slab32) ? 1 : 2;                // 32-column chunks per slab
@@ -633,7 +633,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (kSlab16 && warp < 2 + EW) {
-    // ===== epilogue math, 16 warps on 32-column slabs (EPI_PAIR / EPI_POOL2): thread = (row, 16 columns) =====
+    // ===== epilogue math, 16 warps on 32-column slabs (EPI_PAIR / EPI_POOL2 / the stem's EPI_GENERIC): thread = (row, 16 columns) =====
     // Same slabs, barriers and store warps as the 8-warp slab32 path; the eight warps of a column half
     // split every 32-column slab in two, so four warps per scheduler hide each other's latencies
     // (tcgen05.ld, lds, MUFU) where two could not (30-45 % issue-active).
@@ -692,10 +692,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int c0 = half * kHalf + c * 32 + sub * 16;   // column within the tile
+          constexpr int kJobs = (kPair || kPool2) ? 2 : 1;   // slabs per 32-column step
           uint8_t* buf0 = my_bufs32 + (job & 3) * (kSlabBytes / 2);
           uint8_t* buf1 = my_bufs32 + ((job + 1) & 3) * (kSlabBytes / 2);
           ptx::mbar_wait(&my_rin[job & 3], (job >> 2) & 1);
-          ptx::mbar_wait(&my_rin[(job + 1) & 3], ((job + 1) >> 2) & 1);
+          if (kJobs == 2) ptx::mbar_wait(&my_rin[(job + 1) & 3], ((job + 1) >> 2) & 1);
           float v[16], pv[16];
           ptx::tmem_ld_wait();
           if (c + 1 < kChunks) tmem_ld_32x16(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
@@ -734,6 +735,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               act16(v, ep.act2);
             }
             wr16(buf0, hi32, x7p, v);      // in place: this thread owns these 32 bytes of the row
+          } else if constexpr (MODE == EPI_GENERIC) {
+            // one staged bf16 output, no residual (the stem): out = act(v * scale + shift + bias), or the
+            // second stage act2(. * scale2 + shift2) of it when the launch stores `out2`
+            (void)buf1;
+            if (ep.scale != nullptr) {
+              float ps[16];
+              load_param16(P + P_SCALE * BN + c0, ps);
+              load_param16(P + P_SHIFT * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+            }
+            if (ep.bias != nullptr) {
+              load_param16(P + P_BIAS * BN + c0, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += pv[i];
+            }
+            act16(v, ep.act);
+            if (ep.out2 != nullptr) {
+              if (ep.scale2 != nullptr) {
+                float ps[16];
+                load_param16(P + P_SCALE2 * BN + c0, ps);
+                load_param16(P + P_SHIFT2 * BN + c0, pv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = v[i] * ps[i] + pv[i];
+              }
+              act16(v, ep.act2);
+            }
+            wr16(buf0, hi32, x7p, v);
           } else {
             if (ep.scale != nullptr) {
               float ps[16];
@@ -767,9 +796,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) {
             ptx::mbar_arrive(&my_rout[job & 3]);
-            ptx::mbar_arrive(&my_rout[(job + 1) & 3]);
+            if (kJobs == 2) ptx::mbar_arrive(&my_rout[(job + 1) & 3]);
           }
-          job += 2;
+          job += kJobs;
         }
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }

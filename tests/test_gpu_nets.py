@@ -454,6 +454,21 @@ def test_enformer_slab32_matches_wide_slabs(cuda, full, n_cand, monkeypatch):
       assert torch.equal(got, ref)
 
 
+def test_enformer_stem_epilogue_variants_bitwise(cuda, monkeypatch):
+  """The stem GEMM (EPI_GENERIC, one staged bf16 output, K = 64: pure epilogue) on 16 warps with one
+  64-column slab per column quarter (default), on 16 warps over the 32-column slabs (SVDD_EPI16=3,
+  measured slower) and on the 8-warp kernel (SVDD_EPI16=0, read per call): bit-identical scores on
+  the bench network, with enough candidates for every CTA pair to walk several tiles."""
+  emb, head = helpers.build_enformer(full=True)
+  emb, head = emb.to(cuda), head.to(cuda)
+  tok = helpers.random_tokens(150, 200, 9, 0.5).to(cuda)
+  got = {}
+  for mode in ('0', '1', '3'):
+    monkeypatch.setenv('SVDD_EPI16', mode)
+    got[mode] = value_nets.score_tokens(emb, head, tok).cpu()
+  assert torch.equal(got['1'], got['0']) and torch.equal(got['3'], got['0'])
+
+
 @pytest.mark.parametrize('S,L,C', [(5, 100, 768), (9, 13, 128), (64, 50, 896), (1300, 2, 128), (700, 200, 256)])
 def test_pair_pool_slab32_bitwise(cuda, S, L, C, monkeypatch):
   """The pair-split 1x1 conv + difference pooling in isolation, slab32 against the wide slabs:
