@@ -28,8 +28,9 @@
 //                      rout[h][b] : math warps -> store warp  "slab written"
 // The store warp provisions job j+2 right after job j's TMA store has drained the buffer.
 //
-// EPI_PAIR / EPI_POOL2 (8 epilogue warps) take 32-column slabs instead (ep.slab32: 128 rows x 64 B,
-// FOUR buffers per column half in the same 64 KB, b = j & 3): a step consumes two jobs (an input and
+// EPI_PAIR / EPI_POOL2 take 32-column slabs instead (ep.slab32: 128 rows x 64 B, FOUR buffers per
+// column half in the same 64 KB, b = j & 3; by default with 16 epilogue warps, thread = (row, 16 columns),
+// the eight warps of a column half sharing its slabs): a step consumes two jobs (an input and
 // an output slab, or two inputs), and with two buffers per half the loads of step k+1 could only be
 // issued once step k's math had released them -- ncu showed the math warps waiting for their input
 // slabs ~35 % of the time (profiles/r02_summary.md).  With four, step k+1's inputs land during step k.
@@ -421,7 +422,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // slab buffers used per 64/32-column step: EPI_PAIR = {residual in, (yd | y0) out},
   // EPI_POOL2 = {y0 in / next operand out, yd in}
   const int n_out = (kPair || kPool2) ? 2 : (has_out ? 1 : 0) + (out2_staged ? 1 : 0);
-  // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 warps
+  // 32-column bf16 slabs, four buffers per half (see the header): EPI_PAIR / EPI_POOL2 on 8 or 16 warps
+  // (WIDE = the 64-column slabs of rounds 1-2, cross-check only), and the 16-warp EPI_GENERIC variant
+  // behind SVDD_EPI16=3 (WIDE there = one 64-column slab per column quarter, the default for the stem)
   constexpr bool slab32 = (kPair || kPool2 || (MODE == EPI_GENERIC && EW == 16)) && !WIDE;
   // 16 epilogue warps on the slab32 protocol: thread = (row, 16-column half of the current 32-column slab)
   constexpr bool kSlab16 = slab32 && EW == 16;
