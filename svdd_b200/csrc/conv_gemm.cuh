@@ -112,6 +112,9 @@ struct GemmShape {
   // conv_gemm2: L2-prefetch this CTA's weight slice of its first tile at kernel start (set by the
   // launcher for launches with at most two tiles per CTA pair; SVDD_PREFETCH_W=0 disables)
   int prefetch_w = 0;
+  // conv_gemm2: walk the row tiles from the last to the first.  A layer that consumes what the previous
+  // launch wrote in increasing row order then starts on the rows that are still in L2 ("snake" order)
+  int reverse = 0;
   // rows between consecutive sequences of A when they are not densely packed (0 = L_in)
   int a_pitch = 0;
   // rows that carry real data, for the FLOP accounting of padded layouts (0 = S * L)

@@ -479,7 +479,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto tile_coords = [&](int t, int rr) {
     TileCoord c;
     const int nt = (int)(t % n_tiles);
-    const int mt = (t / n_tiles) * CG + rr;
+    const int mq = (int)(t / n_tiles);
+    const int mt = (g.reverse ? mp_tiles - 1 - mq : mq) * CG + rr;
     c.n0 = g.n_off + nt * BN;    // global column
     c.in_range = mt < m_tiles;
     c.s0 = (int)(mt / tiles_l) * g.BS;       // >= S when out of range: TMA zero-fills / clips

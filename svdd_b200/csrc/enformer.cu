@@ -945,6 +945,12 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
     }
     int len = L;
     bool halo_prev = false;              // the previous stage ran in the padded flat layout
+    // "snake" tile order (SVDD_SNAKE, read per call, default on): every other GEMM of the conv tower walks its
+    // row tiles from the last to the first, so that a layer starts on the rows its producer wrote last
+    // (still in L2) instead of the ones written first (evicted at c2 sizes); bit-identical
+    const char* e_snake = getenv("SVDD_SNAKE");
+    const int snake = (e_snake == nullptr || atoi(e_snake) != 0) ? 1 : 0;
+    int li = 1;                          // the stem walked forwards
     for (int i = 0; i < h->n_stage; ++i) {
       const int fi = h->f[i];
       const int lo = (len + 1) / 2;
@@ -972,6 +978,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
         ep.out = x; ep.out_dtype = DT_BF16; ep.ld_out = fi;
         ep.out2 = y; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
         ep.scale2 = h->bn1_s[i]; ep.shift2 = h->bn1_t[i]; ep.act2 = ACT_GELU;
+        g.reverse = snake & (li++ & 1);
         SVDD_TRY(launch_conv_gemm(a, h->w5[i], g, EPI_GENERIC, ep, st));
         if (debug_dump_enabled()) {
           debug_dump(("ef_z" + std::to_string(i)).c_str(), x, (size_t)rows * len * fi * 2, st);
@@ -1013,6 +1020,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
           }
           ep.out = y0; ep.out_dtype = DT_BF16; ep.ld_out = fi;
           ep.out2 = yd; ep.out2_dtype = DT_BF16; ep.ld_out2 = fi;
+          g.reverse = snake & (li++ & 1);
           SVDD_TRY(launch_conv_gemm(a, h->w1[i], g, EPI_PAIR, ep, st));
           if (debug_dump_enabled()) {
             debug_dump(("ef_y0_" + std::to_string(i)).c_str(), y0, (size_t)rows * lo * fi * 2, st);
@@ -1053,6 +1061,7 @@ extern "C" int svdd_enformer_score(svdd_enformer* h, const void* tokens, int tok
           } else {
             ep.out = b.xt; ep.out_dtype = DT_F32; ep.ld_out = fi;
           }
+          g.reverse = snake & (li++ & 1);
           SVDD_TRY(launch_conv_gemm(ydv, h->wp[i], g, EPI_POOL2, ep, st));
         }
       } else {

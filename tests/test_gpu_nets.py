@@ -467,6 +467,14 @@ def test_enformer_stem_epilogue_variants_bitwise(cuda, monkeypatch):
     monkeypatch.setenv('SVDD_EPI16', mode)
     got[mode] = value_nets.score_tokens(emb, head, tok).cpu()
   assert torch.equal(got['1'], got['0']) and torch.equal(got['3'], got['0'])
+  # "snake" tile order of the conv tower (every other GEMM walks its row tiles backwards, SVDD_SNAKE,
+  # read per call): tiles are independent, so the order cannot change a bit
+  monkeypatch.delenv('SVDD_EPI16')
+  monkeypatch.setenv('SVDD_SNAKE', '0')
+  fwd = value_nets.score_tokens(emb, head, tok).cpu()
+  monkeypatch.setenv('SVDD_SNAKE', '1')
+  assert torch.equal(value_nets.score_tokens(emb, head, tok).cpu(), fwd)
+  assert torch.equal(fwd, got['1'])
 
 
 @pytest.mark.parametrize('S,L,C', [(5, 100, 768), (9, 13, 128), (64, 50, 896), (1300, 2, 128), (700, 200, 256)])
