@@ -781,11 +781,12 @@ int launch_tower(const svdd_enformer* h, const EfWs& b, int64_t R, int n, cudaSt
   a.items_per_block = start;
   a.total_items = start * a.n_blocks + kSubItems * a.RT;
   a.blocks = h->tower_blocks;
-  a.xt = b.xt; a.hn = b.hn; a.qkv = b.qkv; a.ao = b.ao;
+  a.xt = b.xt; a.hn = b.hn; a.qkv = b.qkv; a.ao = b.ao; a.u = b.u;
   a.bn_s = h->bnpw_s; a.bn_t = h->bnpw_t;
   a.flags = b.flags;
   a.sk_flags = b.flags + (size_t)kPhasesPerBlock * a.n_blocks * a.RT;
   { const char* e = getenv("SVDD_TOWER_ATTN_FAST"); a.attn_fast = e ? atoi(e) : 1; }
+  { const char* e = getenv("SVDD_TOWER_DISCARD"); a.discard_qkv = e ? atoi(e) : 1; }
 
   CUtensorMap tm_hn, tm_ao, tm_u, tm_qkv, tm_xt;
   SVDD_TRY(encode_tmap_2d_bf16(&tm_hn, b.hn, (uint64_t)C, (uint64_t)R, 64, 128));

@@ -96,6 +96,12 @@ struct TowerArgs {
   // (accumulator free) [3] accumulator complete (epilogue) [4] epilogue / row math done [5] published
   // [6] pair index
   unsigned long long* trace = nullptr;
+  // SVDD_TOWER_DISCARD (default on): row items drop intermediates whose last reader has finished from L2
+  // (discard.global.L2) instead of letting the dead lines be written back: an attention item its
+  // sequences' qkv rows and LN1 rows, an LN2 item its rows of the attention output (the out-projection
+  // of the row tile is complete), an LN1 item its rows of the previous block's FFN hidden tensor.
+  int discard_qkv = 0;
+  __nv_bfloat16* u = nullptr;   // FFN hidden [R, 2C] (the GEMMs reach it through tm_u)
 };
 
 template <int kBN>                         // tile columns per CTA pair: 256 or 128
@@ -850,6 +856,18 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
             } else {
               ln_rows_generic(xr, bp.ln_g[ph.w_idx], bp.ln_b[ph.w_idx], hr, a.C, valid, lane);
             }
+            if (a.discard_qkv) {
+              // dead now: LN2 -> these rows of the attention output (read by the out-projection, complete);
+              // LN1 of block j > 0 -> these rows of the previous block's FFN hidden tensor (FF2 complete)
+              const int row_bytes = ph.w_idx == 1 ? a.H * a.dv * 2 : 2 * a.C * 2;
+              const char* dead = ph.w_idx == 1 ? reinterpret_cast<const char*>(a.ao + (size_t)row * a.H * a.dv)
+                                               : (it.j > 0 && a.u != nullptr ? reinterpret_cast<const char*>(a.u + (size_t)row * 2 * a.C) : nullptr);
+              if (dead != nullptr && (row_bytes & 127) == 0) {
+                const int lines = valid * (row_bytes >> 7);
+                for (int c = lane; c < lines; c += 32)
+                  asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + (size_t)c * 128) : "memory");
+              }
+            }
           }
         } else if (ph.type == PH_ATTN) {
           const BlockParams& bp = a.blocks[it.j];
@@ -877,6 +895,19 @@ tower_kernel(const __grid_constant__ CUtensorMap tm_hn, const __grid_constant__ 
               if constexpr (NPOS <= 2) {
                 if (hdv == 1536) attn_warp_seq<NPOS, 4, 12>(base, a.nqkv, bp.rcb, bp.rpb, bp.relk, o, a.H, a.dk, a.dv, lane, sw);
                 else attn_warp_seq<NPOS, 4, 3>(base, a.nqkv, bp.rcb, bp.rpb, bp.relk, o, a.H, a.dk, a.dv, lane, sw);
+                // The sequence's qkv rows are dead now (this warp was their only reader; the next block's QKV
+                // GEMM rewrites them whole): drop the lines from L2 instead of letting them be written back --
+                // qkv is 26 MB of fp32 per block, the largest share of the kernel's dead write-backs.
+                if (a.discard_qkv && (a.nqkv & 31) == 0) {
+                  const int lines = NPOS * a.nqkv / 32;          // 128-byte lines of the NPOS contiguous rows
+                  for (int c = lane; c < lines; c += 32)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (size_t)c * 32) : "memory");
+                  if ((a.C & 63) == 0) {                         // LN1's rows: read by the QKV GEMM, complete
+                    const char* hdead = reinterpret_cast<const char*>(a.hn + (size_t)row * a.C);
+                    for (int c = lane; c < NPOS * (a.C >> 6); c += 32)
+                      asm volatile("discard.global.L2 [%0], 128;" ::"l"(hdead + (size_t)c * 128) : "memory");
+                  }
+                }
               }
             }
           } else {

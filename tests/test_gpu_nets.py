@@ -475,6 +475,14 @@ def test_enformer_stem_epilogue_variants_bitwise(cuda, monkeypatch):
   monkeypatch.setenv('SVDD_SNAKE', '1')
   assert torch.equal(value_nets.score_tokens(emb, head, tok).cpu(), fwd)
   assert torch.equal(fwd, got['1'])
+  # the tower's row items drop dead intermediates from L2 (discard.global.L2, SVDD_TOWER_DISCARD, read
+  # per call): a discarded line that was still needed would show up here and in the SVDD_TOWER=0 checks
+  monkeypatch.setenv('SVDD_TOWER_DISCARD', '0')
+  keep = value_nets.score_tokens(emb, head, tok).cpu()
+  monkeypatch.setenv('SVDD_TOWER_DISCARD', '1')
+  for _ in range(3):
+    assert torch.equal(value_nets.score_tokens(emb, head, tok).cpu(), keep)
+  assert torch.equal(keep, fwd)
 
 
 @pytest.mark.parametrize('S,L,C', [(5, 100, 768), (9, 13, 128), (64, 50, 896), (1300, 2, 128), (700, 200, 256)])

@@ -45,8 +45,9 @@ out = {
         'dram_bytes': int(dram(tower[1])),
         'algorithmic_bytes': 385351680,
         'algorithmic_bytes_note': 'bf16 weights of the 44 GEMMs read once (346 MB) + the fp32 residual stream in and out + the bf16 '
-                                  'operand of the pointwise conv; qkv / attention output / FFN hidden are produced and consumed inside '
-                                  'the kernel but leave L2 as write-backs',
+                                  'operand of the pointwise conv; qkv / LayerNorm outputs / attention output / FFN hidden are produced and '
+                                  'consumed inside the kernel and dropped from L2 by their last reader (discard.global.L2; before that '
+                                  'they left L2 as 690 MB of dead write-backs per launch)',
         'ncu_us': tower[1].get('gpu__time_duration.sum', 0.0) / 1e3,
         'tensor_pipe_pct': tower[1].get('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active'),
     },
